@@ -1,0 +1,127 @@
+/* vitsdec -- C ABI of the B200-native VITS waveform decoder (HiFi-GAN Generator).
+ *
+ * Drop-in boundary for ONE path of MedivhJin01/Personalized_Text-to-Speech:
+ *     models.Generator.forward(x, g)          /root/reference/models.py:270-289
+ * as called by SynthesizerTrn.infer            /root/reference/models.py:522
+ *          and SynthesizerTrn.voice_conversion /root/reference/models.py:532
+ *
+ * The reference is Python; its "FFI" for this path is the nn.Module protocol.  The host-side mirror
+ * (personalized_text-to-speech_b200/generator.py) binds these entry points with ctypes and passes
+ * raw device pointers (tensor.data_ptr()) and the current CUDA stream.  No torch types cross this
+ * boundary.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error; vitsdec_last_error() returns a
+ * thread-local message.  All pointers named *_dev are device pointers on the decoder's device; the
+ * library never synchronises the stream except in the *_host convenience entry.  There is no CPU
+ * fallback: on a machine without an sm_100 GPU vitsdec_create fails.
+ */
+#ifndef VITSDEC_H_
+#define VITSDEC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VITSDEC_API __attribute__((visibility("default")))
+#else
+#define VITSDEC_API
+#endif
+
+#define VITSDEC_ABI_VERSION 1
+#define VITSDEC_MAX_UPSAMPLES 8
+#define VITSDEC_MAX_KERNELS 8
+#define VITSDEC_MAX_DILATIONS 8
+
+/* Generator.__init__ arguments (models.py:245; values from configs/<name>.json "model" block) */
+typedef struct vitsdec_hparams {
+  int32_t initial_channel;                                   /* inter_channels (192) */
+  int32_t resblock;                                          /* 1 -> ResBlock1 ('1'), 2 -> ResBlock2 */
+  int32_t num_kernels;                                       /* len(resblock_kernel_sizes) */
+  int32_t resblock_kernel_sizes[VITSDEC_MAX_KERNELS];        /* [3,7,11] */
+  int32_t num_dilations[VITSDEC_MAX_KERNELS];                /* len(resblock_dilation_sizes[j]) */
+  int32_t resblock_dilation_sizes[VITSDEC_MAX_KERNELS][VITSDEC_MAX_DILATIONS]; /* [[1,3,5]]*3 */
+  int32_t num_upsamples;                                     /* len(upsample_rates) */
+  int32_t upsample_rates[VITSDEC_MAX_UPSAMPLES];             /* [8,8,2,2] */
+  int32_t upsample_initial_channel;                          /* 512 */
+  int32_t upsample_kernel_sizes[VITSDEC_MAX_UPSAMPLES];      /* [16,16,4,4] */
+  int32_t gin_channels;                                      /* 256, 0 = no speaker conditioning */
+} vitsdec_hparams;
+
+typedef struct vitsdec_decoder vitsdec_decoder;
+
+VITSDEC_API int vitsdec_abi_version(void);
+VITSDEC_API const char* vitsdec_last_error(void);
+
+/* replaces Generator.__init__ (models.py:245-268).  `device` is a CUDA ordinal. */
+VITSDEC_API int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out);
+VITSDEC_API void vitsdec_destroy(vitsdec_decoder* dec);
+
+/* Number of layers that take weights, and the state_dict prefix of layer i ("conv_pre", "ups.0",
+ * "resblocks.0.convs1.0", ..., "conv_post", "cond").  Mirrors the parameter tree of models.py:249-268. */
+VITSDEC_API int vitsdec_num_layers(const vitsdec_decoder* dec);
+VITSDEC_API const char* vitsdec_layer_name(const vitsdec_decoder* dec, int layer);
+
+/* replaces load_state_dict + the weight_norm pre-forward hook (torch.nn.utils.weight_norm, dim=0;
+ * models.py:254, modules.py:191-206).  fp32 device pointers in the reference's native layouts:
+ *   Conv1d           weight [C_out, C_in, k]      ConvTranspose1d  weight [C_in, C_out, k]
+ * weight_g_dev == NULL  -> `weight_dev` is the plain (already folded) weight;
+ * weight_g_dev != NULL  -> `weight_dev` is weight_v and the fold w = v * g / ||v|| (norm over all dims
+ *                          but 0) happens on the GPU, once, here.
+ * bias_dev may be NULL (conv_post has no bias).  Enqueued on `stream`. */
+VITSDEC_API int vitsdec_load_layer(vitsdec_decoder* dec, const char* name, const float* weight_dev, const float* weight_g_dev,
+                       const float* bias_dev, void* stream);
+
+/* Scratch the caller must provide to vitsdec_decode for a [batch, C, frames] latent. */
+VITSDEC_API size_t vitsdec_workspace_bytes(const vitsdec_decoder* dec, int batch, int frames);
+
+/* replaces Generator.forward(x, g) (models.py:270-289).
+ *   z_dev   fp32 [batch, initial_channel, frames]; element strides z_stride_b / z_stride_c, time stride 1
+ *           (infer passes the slice (z*y_mask)[:,:,:max_len], models.py:522)
+ *   g_dev   fp32 [batch, gin_channels] (the [B, gin, 1] tensor of models.py:502) or NULL
+ *   out_dev fp32 [batch, 1, frames * prod(upsample_rates)] contiguous
+ * Asynchronous on `stream`; `workspace_dev` must stay untouched until the stream reaches this point. */
+VITSDEC_API int vitsdec_decode(vitsdec_decoder* dec, const float* z_dev, int64_t z_stride_b, int64_t z_stride_c,
+                   const float* g_dev, float* out_dev, int batch, int frames, void* workspace_dev,
+                   size_t workspace_bytes, void* stream);
+
+/* End-to-end convenience for hosts without a device allocator: pageable or pinned HOST buffers in and
+ * out (contiguous), H2D + decode + D2H on an internal stream, synchronous. */
+VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, const float* g_host, float* out_host, int batch,
+                        int frames);
+
+/* Options: "impl" = 0 tcgen05 tensor-core kernels (default), 1 CUDA-core cross-check kernels (tests only);
+ *          "desc_mode" = debug knob of the UMMA descriptor; "graph" = 1 capture the decode into a CUDA graph. */
+VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
+VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
+
+/* Kernel launches issued by the last vitsdec_decode on this decoder (for bench.py's gpu_launches). */
+VITSDEC_API int vitsdec_last_launch_count(const vitsdec_decoder* dec);
+
+/* Test hook: copy a named intermediate of the LAST decode out of the workspace as fp32 NCL
+ * [batch, C, L].  Names: "conv_pre", "ups.<i>", "mrf.<i>".  Values are the stored a-form
+ * (post-leaky-relu) mapped back to the residual-stream value.  out_elems = capacity of out_dev. */
+VITSDEC_API int vitsdec_debug_read(vitsdec_decoder* dec, const char* name, float* out_dev, size_t out_elems, int* channels,
+                       int* length, void* stream);
+
+/* Single fused convolution on channels-last bf16 activations (per-kernel parity tests):
+ *   y[b,t,co] = lrelu( bias[co] + sum_j sum_ci w[co,ci,j] * x[b, t + (j-(k-1)/2)*dilation, ci] (+ res), out_slope )
+ *   x_dev / res_dev / y_dev: bf16 [batch, length, channels]; w_dev fp32 [c_out, c_in, k]; bias fp32 [c_out].
+ *   res (optional) is stored post-leaky-relu with slope 1/res_gain.  impl: 0 tcgen05, 1 CUDA cores. */
+VITSDEC_API int vitsdec_op_conv1d(int device, const void* x_dev, const float* w_dev, const float* bias_dev, const void* res_dev,
+                      float res_gain, float out_slope, void* y_dev, int batch, int length, int c_in, int c_out,
+                      int k, int dilation, int impl, int desc_mode, void* stream);
+
+/* Same for ConvTranspose1d(c_in, c_out, k, stride, padding=(k-stride)/2) in polyphase form:
+ *   w_dev fp32 [c_in, c_out, k]; y_dev bf16 [batch, length*stride, c_out]. */
+VITSDEC_API int vitsdec_op_conv_transpose1d(int device, const void* x_dev, const float* w_dev, const float* bias_dev,
+                                float out_slope, void* y_dev, int batch, int length, int c_in, int c_out, int k,
+                                int stride, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITSDEC_H_ */

@@ -1,0 +1,47 @@
+// Shared description of one fused convolution launch (channels-last activations).
+//
+// Activations are [B][L][C] bf16 ("rows" = time samples, channels contiguous) so that a filter tap is a
+// row shift of the same tile.  Every convolution on the decoder path -- conv_pre (models.py:271), the
+// polyphase form of the four ConvTranspose1d `ups` (models.py:277) and the 72 ResBlock convs
+// (modules.py:210-223) -- is   y[b,t,n] = sum_tap sum_ci  W[tap][n][ci] * x[b, t + off[tap], ci]
+// followed by a fused epilogue.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace vd {
+
+constexpr int kMaxTaps = 16;
+
+struct ConvGeom {
+  int B;        // utterances
+  int L;        // rows (time samples) per utterance, input == output rows
+  int c_in;     // K per tap
+  int n_total;  // output columns per row (C_out, or stride*C_out for a polyphase transposed conv)
+  int ntaps;
+  int tap_off[kMaxTaps];  // input-row offset of each tap
+  int tap_nlo[kMaxTaps];  // tap contributes only to columns [nlo, nhi) (polyphase zero blocks)
+  int tap_nhi[kMaxTaps];
+};
+
+// Epilogue:  v = acc + bias[n] (+ bias_b[b][n]) (+ unlrelu(res[b,t,n]))
+//   mrf_mode 0: out = lrelu(v, out_slope)
+//   mrf_mode 1: mrf  = v                       (first MRF branch)          no bf16 output
+//   mrf_mode 2: mrf += v                       (middle MRF branches)       no bf16 output
+//   mrf_mode 3: out = lrelu((mrf + v) * mrf_scale, out_slope)  (last branch; mrf may be null)
+// Activations are stored post-leaky-relu ("a-form"): the next conv's tensor-core operand.  The
+// residual stream x is recovered exactly (up to the bf16 rounding of a) as x = a >= 0 ? a : a * res_gain
+// with res_gain = 1/slope, which is what lets one bf16 tensor serve as both operand and residual.
+struct ConvEpilogue {
+  const float* bias;           // [n_total]
+  const float* bias_b;         // [B][n_total] or null
+  const __nv_bfloat16* res;    // [B][L][n_total] a-form or null
+  float res_gain;              // 1/slope of the a-form stored in `res`
+  float* mrf;                  // [B][L][n_total] fp32 or null
+  int mrf_mode;
+  float mrf_scale;
+  float out_slope;             // 1.0f = identity
+  __nv_bfloat16* out;          // [B][L][n_total]
+};
+
+}  // namespace vd

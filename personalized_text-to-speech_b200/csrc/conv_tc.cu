@@ -1,0 +1,369 @@
+// Implicit-GEMM convolution on the sm_100a tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA).  One kernel serves conv_pre, the polyphase ConvTranspose1d stages and every ResBlock
+// conv of the decoder (reference: models.py:271-287, modules.py:210-223).
+//
+// Mapping.  Activations are channels-last bf16 [B][L][C]; a CTA tile is BM = 128*NACC time rows x BN
+// output columns.  D[time, n] += A[time, ci] * W[n, ci]^T per (tap, 64-channel chunk):
+//   * A operand  = the activation tile, K-major (channels contiguous), 128B-swizzled rows.  ONE TMA
+//     load of rows [t0+halo_lo, t0+BM+halo_hi) serves every tap: a tap is a row offset of the UMMA
+//     shared-memory descriptor into the same tile (no im2col, no per-tap reload).  TMA out-of-bounds
+//     zero fill implements the zero padding at both utterance ends.
+//   * B operand  = packed weights W[tap][n][ci], streamed through an NB-stage ring.
+//   * D          = fp32 in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+// (tcgen05.ld -> bias / residual / MRF / leaky-relu -> bf16 channels-last stores).
+#include <algorithm>
+
+#include "common.cuh"
+#include "conv_tc.h"
+#include "ptx.cuh"
+
+namespace vd {
+
+constexpr int kNA = 2;         // activation-chunk stages
+constexpr int kTcThreads = 192;
+
+template <int BN, int KC>
+struct TcCfg {
+  static constexpr int NACC = BN >= 256 ? 1 : 2;
+  static constexpr int ROWB = KC * 2;
+  static constexpr int B_STAGE = BN * ROWB;
+  static constexpr int NB = 4;
+  static constexpr int ACC_COLS = NACC * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
+};
+
+// 32 consecutive output columns of one row
+__device__ __forceinline__ void epilogue_chunk(const ConvEpilogue& ep, int b, long row, int n, int n_total,
+                                               const uint32_t (&acc)[32], bool valid) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
+    v[j + 0] = __uint_as_float(acc[j + 0]) + bv.x;
+    v[j + 1] = __uint_as_float(acc[j + 1]) + bv.y;
+    v[j + 2] = __uint_as_float(acc[j + 2]) + bv.z;
+    v[j + 3] = __uint_as_float(acc[j + 3]) + bv.w;
+  }
+  if (ep.bias_b) {
+    const float* bb = ep.bias_b + (long)b * n_total + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bb + j));
+      v[j + 0] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+    }
+  }
+  if (!valid) return;
+  const long idx = row * n_total + n;
+  if (ep.res) {
+    const uint4* rp = reinterpret_cast<const uint4*>(ep.res + idx);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 rv = __ldg(rp + q);
+      const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __bfloat1622float2(r2[e]);
+        v[q * 8 + e * 2 + 0] += a.x >= 0.f ? a.x : a.x * ep.res_gain;
+        v[q * 8 + e * 2 + 1] += a.y >= 0.f ? a.y : a.y * ep.res_gain;
+      }
+    }
+  }
+  if (ep.mrf_mode == 1 || ep.mrf_mode == 2) {
+    float4* mp = reinterpret_cast<float4*>(ep.mrf + idx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 m = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      if (ep.mrf_mode == 2) {
+        const float4 o = mp[j];
+        m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+      }
+      mp[j] = m;
+    }
+    return;
+  }
+  if (ep.mrf_mode == 3) {
+    if (ep.mrf) {
+      const float4* mp = reinterpret_cast<const float4*>(ep.mrf + idx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 o = mp[j];
+        v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= ep.mrf_scale;
+  }
+  uint4* op = reinterpret_cast<uint4*>(ep.out + idx);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 ov;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o2[e] = __floats2bfloat162_rn(lrelu(v[q * 8 + e * 2], ep.out_slope), lrelu(v[q * 8 + e * 2 + 1], ep.out_slope));
+    op[q] = ov;
+  }
+}
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ ConvTcParams p) {
+  using C = TcCfg<BN, KC>;
+  constexpr int NACC = C::NACC, ROWB = C::ROWB, B_STAGE = C::B_STAGE, NB = C::NB, ACC_COLS = C::ACC_COLS;
+  constexpr int BM = 128 * NACC;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: the 128B swizzle pattern is a function of the shared-memory address bits
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + kNA * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + NB * B_STAGE);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kNA;
+  uint64_t* b_full = a_empty + kNA;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* acc_full = b_empty + NB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkc = p.g.c_in / KC;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ita = 0, itb = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mb = tile / p.n_tiles;
+        const int b = mb / p.m_tiles;
+        const int t0 = (mb % p.m_tiles) * BM;
+        const int n0 = nt * BN;
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t sa = ita % kNA, pa = (ita / kNA) & 1;
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], p.a_stage_bytes);
+          for (int bx = 0; bx < p.nboxes; ++bx)
+            tma_load_3d(&tmA, &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, kc * KC,
+                        t0 + p.halo_lo + bx * 64, b);
+          ++ita;
+          for (int tap = 0; tap < p.g.ntaps; ++tap) {
+            if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0) continue;
+            const uint32_t sb = itb % NB, pb = (itb / NB) & 1;
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], B_STAGE);
+            tma_load_3d(&tmW, &b_full[sb], smemB + sb * B_STAGE, kc * KC, n0, tap);
+            ++itb;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN, false);
+      const uint32_t a_addr0 = smem_u32(smemA), b_addr0 = smem_u32(smemB);
+      uint32_t ita = 0, itb = 0, itt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
+        const int n0 = (tile % p.n_tiles) * BN;
+        const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
+        mbar_wait(&acc_empty[as], pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + as * ACC_COLS;
+        bool first = true;
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t sa = ita % kNA, pa = (ita / kNA) & 1;
+          mbar_wait(&a_full[sa], pa);
+          for (int tap = 0; tap < p.g.ntaps; ++tap) {
+            if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0) continue;
+            const uint32_t sb = itb % NB, pb = (itb / NB) & 1;
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t a_tap = a_addr0 + sa * p.a_stage_bytes + (p.g.tap_off[tap] - p.halo_lo) * ROWB;
+            const uint32_t b_tap = b_addr0 + sb * B_STAGE;
+#pragma unroll
+            for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                const uint32_t aaddr = a_tap + acc * 128 * ROWB + k * 32;
+                const uint32_t boff = p.desc_mode == 1 ? ((aaddr >> 7) & 7u) : 0u;
+                umma_f16(d_base + acc * BN, umma_desc_kmajor(aaddr, ROWB, boff),
+                         umma_desc_kmajor(b_tap + k * 32, ROWB, 0), idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            first = false;
+            umma_commit(&b_empty[sb]);  // weights stage free once these MMAs retire
+            ++itb;
+          }
+          umma_commit(&a_empty[sa]);
+          ++ita;
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+    const int q = warp & 3;
+    uint32_t itt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
+      const int nt = tile % p.n_tiles;
+      const int mb = tile / p.n_tiles;
+      const int b = mb / p.m_tiles;
+      const int t0 = (mb % p.m_tiles) * BM;
+      const int n0 = nt * BN;
+      const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
+      mbar_wait(&acc_full[as], pacc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int acc = 0; acc < NACC; ++acc) {
+        const int t = t0 + acc * 128 + q * 32 + lane;
+        const bool valid = t < p.g.L;
+        const long row = (long)b * p.g.L + t;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + acc * BN + c0, v);
+          tmem_ld_wait();
+          epilogue_chunk(p.ep, b, row, n0 + c0, p.g.n_total, v, valid);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// bf16 tensor [d2][d1][d0] (d0 contiguous), box {b0, b1, 1}, swizzle span = b0*2 bytes
+static int encode_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                     uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  VD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = b0 * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                        : (b0 * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu) box=(%u,%u)", (int)r,
+             (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1);
+    set_error(buf);
+    return 1;
+  }
+  return 0;
+}
+
+template <int BN, int KC>
+static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
+  static bool attr_set = false;  // benign race: idempotent
+  if (!attr_set) {
+    VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN, KC><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, int num_sms,
+                 int desc_mode) {
+  VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
+  VD_CHECK(g.n_total % 32 == 0, "conv_tc: output columns must be a multiple of 32");
+  VD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, "conv_tc: 1..16 taps supported");
+  const int kc = (g.c_in % 64 == 0) ? 64 : 32;
+  int bn = 32;
+  for (int c : {256, 128, 64}) {
+    if (g.n_total % c == 0) { bn = c; break; }
+  }
+  const int nacc = bn >= 256 ? 1 : 2;
+  const int bm = 128 * nacc;
+  int lo = g.tap_off[0], hi = g.tap_off[0];
+  for (int i = 1; i < g.ntaps; ++i) { lo = std::min(lo, g.tap_off[i]); hi = std::max(hi, g.tap_off[i]); }
+  ConvTcParams& p = pl->p;
+  p.g = g;
+  p.halo_lo = lo;
+  p.nboxes = (bm + (hi - lo) + 63) / 64;
+  p.a_stage_bytes = p.nboxes * 64 * kc * 2;
+  p.m_tiles = (g.L + bm - 1) / bm;
+  p.n_tiles = g.n_total / bn;
+  p.total_tiles = g.B * p.m_tiles * p.n_tiles;
+  p.desc_mode = desc_mode;
+  pl->bn = bn;
+  pl->kc = kc;
+  pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  pl->smem = 1024 + (size_t)kNA * p.a_stage_bytes + 4 * (size_t)bn * kc * 2 + 256;
+  VD_CHECK(pl->smem <= 227 * 1024, "conv_tc: dilation halo too large for shared memory");
+  if (encode_3d(&pl->tmA, x, g.c_in, g.L, g.B, kc, 64)) return 1;
+  if (encode_3d(&pl->tmW, w, g.c_in, g.n_total, g.ntaps, kc, bn)) return 1;
+  return 0;
+}
+
+int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) {
+  pl.p.ep = ep;
+  switch (pl.bn * 100 + pl.kc) {
+    case 25664: return launch_inst<256, 64>(pl, stream);
+    case 12864: return launch_inst<128, 64>(pl, stream);
+    case 6464:  return launch_inst<64, 64>(pl, stream);
+    case 3264:  return launch_inst<32, 64>(pl, stream);
+    case 25632: return launch_inst<256, 32>(pl, stream);
+    case 12832: return launch_inst<128, 32>(pl, stream);
+    case 6432:  return launch_inst<64, 32>(pl, stream);
+    case 3232:  return launch_inst<32, 32>(pl, stream);
+  }
+  set_error("conv_tc: no kernel instance");
+  return 1;
+}
+
+}  // namespace vd

@@ -1,0 +1,667 @@
+// C ABI (include/vitsdec.h) and the decode schedule: which fused convolution runs on which buffer.
+//
+// Reference being replaced: Generator.__init__/forward (/root/reference/models.py:245-289) with
+// ResBlock1/ResBlock2 (/root/reference/modules.py:187-256).  The schedule below is a restatement of that
+// forward in terms of ONE primitive (conv + fused epilogue on channels-last bf16 a-form tensors):
+//
+//   pack_z           z fp32 NCL -> bf16 [B][T][C0]
+//   cond             cb[b] = cond(g[b])                                           models.py:272-273
+//   conv_pre         X = lrelu(conv7(z) + bias + cb[b], 0.1)                      models.py:271-276
+//   per stage i:     U = lrelu(convT_i(X) + bias, 0.1)   (polyphase, 2-3 taps)    models.py:276-277
+//     per branch j:  cur = U
+//        per pair m: H   = lrelu(c1(cur) + b, 0.1)                                modules.py:212-216
+//                    nxt = lrelu(c2(H) + b + x(cur), 0.1)                         modules.py:217-221
+//        the last c2 of a branch feeds the MRF accumulator instead:               models.py:279-284
+//                    first branch S = v; middle S += v; last X = lrelu((S+v)/nk, 0.1 | 0.01)
+//   conv_post        out = tanh(conv7(X))  (X already holds lrelu(., 0.01))       models.py:285-287
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/vitsdec.h"
+#include "common.cuh"
+#include "conv_tc.h"
+#include "pack.h"
+
+namespace vd {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+typedef __nv_bfloat16 bf16;
+constexpr float kSlope = 0.1f;       // modules.py:17 LRELU_SLOPE
+constexpr float kPostSlope = 0.01f;  // F.leaky_relu default, models.py:285
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static int ceildiv(int a, int b) { return -floordiv(-a, b); }
+
+enum LayerKind { kConv = 0, kConvT = 1, kPost = 2, kCond = 3 };
+
+struct Layer {
+  std::string name;
+  LayerKind kind;
+  int c_in = 0, c_out = 0, k = 0, dil = 1, stride = 1;
+  ConvGeom geom{};        // B, L filled per decode
+  bf16* w = nullptr;      // packed operand [ntaps][n_total][c_in]
+  float* bias = nullptr;  // [n_total] (zero when the layer has no bias)
+  float* wf32 = nullptr;  // conv_post / cond keep fp32 weights
+  bool loaded = false;
+};
+
+static void conv_geom(Layer& l) {
+  ConvGeom& g = l.geom;
+  g.c_in = l.c_in;
+  g.n_total = l.c_out;
+  g.ntaps = l.k;
+  for (int j = 0; j < l.k; ++j) {
+    g.tap_off[j] = (j - (l.k - 1) / 2) * l.dil;  // get_padding(k, d) = d(k-1)/2, commons.py:14-15
+    g.tap_nlo[j] = 0;
+    g.tap_nhi[j] = l.c_out;
+  }
+}
+
+// ConvTranspose1d(k, s, p=(k-s)/2): output sample s*i + r reads input rows i + off, kernel index j = r + p - s*off
+static void convT_geom(Layer& l) {
+  ConvGeom& g = l.geom;
+  const int s = l.stride, k = l.k, p = (k - s) / 2;
+  g.c_in = l.c_in;
+  g.n_total = s * l.c_out;
+  const int off_min = ceildiv(p - k + 1, s), off_max = floordiv(s - 1 + p, s);
+  g.ntaps = off_max - off_min + 1;
+  for (int i = 0; i < g.ntaps; ++i) {
+    const int off = off_min + i;
+    g.tap_off[i] = off;
+    const int rlo = std::max(0, s * off - p), rhi = std::min(s, s * off - p + k);
+    g.tap_nlo[i] = rlo * l.c_out;
+    g.tap_nhi[i] = rhi * l.c_out;
+  }
+}
+
+struct PlanKey {
+  int B, T, impl, desc_mode;
+  const void* ws;
+  bool operator<(const PlanKey& o) const {
+    return std::tie(B, T, impl, desc_mode, ws) < std::tie(o.B, o.T, o.impl, o.desc_mode, o.ws);
+  }
+};
+
+struct Step {           // one launch of the conv primitive
+  int layer;
+  const bf16* x;
+  ConvEpilogue ep;
+  int L;
+  ConvTcPlan tc;
+  bf16* dbg_dst = nullptr;  // debug_keep: copy ep.out here after the launch
+  size_t dbg_bytes = 0;
+};
+
+struct Plan {
+  std::vector<Step> steps;
+  bf16* a0;          // packed latent
+  float* cb;         // cond bias [B][C]
+  bf16* x_final;     // input of conv_post
+  int L_final, C_final;
+  std::vector<std::pair<std::string, std::tuple<const bf16*, int, int, float>>> debug;  // name -> (ptr, C, L, gain)
+};
+
+}  // namespace vd
+
+using namespace vd;
+
+struct vitsdec_decoder {
+  vitsdec_hparams hp;
+  int device = 0;
+  int num_sms = 148;
+  std::vector<Layer> layers;
+  std::map<std::string, int> by_name;
+  int l_pre = -1, l_post = -1, l_cond = -1;
+  std::vector<int> l_ups;
+  std::vector<std::vector<int>> l_rb;  // per resblock: conv layer ids in forward order
+  std::vector<int> stage_ch;
+  int hop = 1;
+  float* scale_scratch = nullptr;
+  int impl = 0, desc_mode = 0, debug_keep = 0;
+  int last_launches = 0;
+  std::mutex mu;
+  std::list<std::pair<PlanKey, std::shared_ptr<Plan>>> plans;  // small LRU
+  std::shared_ptr<Plan> last_plan;
+  // decode_host resources
+  cudaStream_t hstream = nullptr;
+  void* hbuf = nullptr;
+  size_t hbuf_bytes = 0;
+};
+
+namespace vd {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int add_layer(vitsdec_decoder* d, const std::string& name, LayerKind kind, int c_in, int c_out, int k, int dil,
+                     int stride) {
+  Layer l;
+  l.name = name; l.kind = kind; l.c_in = c_in; l.c_out = c_out; l.k = k; l.dil = dil; l.stride = stride;
+  if (kind == kConv) conv_geom(l);
+  if (kind == kConvT) convT_geom(l);
+  d->layers.push_back(l);
+  d->by_name[name] = (int)d->layers.size() - 1;
+  return (int)d->layers.size() - 1;
+}
+
+static int alloc_layer(Layer& l) {
+  if (l.kind == kConv || l.kind == kConvT) {
+    const size_t wn = (size_t)l.geom.ntaps * l.geom.n_total * l.geom.c_in;
+    VD_CUDA(cudaMalloc(&l.w, wn * sizeof(bf16)));
+    VD_CUDA(cudaMalloc(&l.bias, (size_t)l.geom.n_total * sizeof(float)));
+    VD_CUDA(cudaMemset(l.bias, 0, (size_t)l.geom.n_total * sizeof(float)));
+  } else {
+    VD_CUDA(cudaMalloc(&l.wf32, (size_t)l.c_out * l.c_in * l.k * sizeof(float)));
+    if (l.kind == kCond) VD_CUDA(cudaMalloc(&l.bias, (size_t)l.c_out * sizeof(float)));
+  }
+  return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t slot;      // bytes of one bf16 activation slot
+  size_t off_a0, off_cb, off_x, off_u, off_h, off_p, off_q, off_s, off_dbg, total;
+};
+
+static WsLayout ws_layout(const vitsdec_decoder* d, int B, int T) {
+  WsLayout w{};
+  size_t slot = (size_t)B * T * d->hp.upsample_initial_channel * 2;  // conv_pre output
+  long L = T;
+  size_t dbg = align_up(slot, 1024);
+  for (size_t i = 0; i < d->stage_ch.size(); ++i) {
+    L *= d->hp.upsample_rates[i];
+    const size_t sz = (size_t)B * L * d->stage_ch[i] * 2;
+    slot = std::max(slot, sz);
+    dbg += 2 * align_up(sz, 1024);
+  }
+  slot = align_up(slot, 1024);
+  size_t o = 0;
+  w.slot = slot;
+  w.off_a0 = o; o += align_up((size_t)B * T * d->hp.initial_channel * 2, 1024);
+  w.off_cb = o; o += align_up((size_t)B * d->hp.upsample_initial_channel * 4, 1024);
+  w.off_x = o; o += slot;
+  w.off_u = o; o += slot;
+  w.off_h = o; o += slot;
+  w.off_p = o; o += slot;
+  w.off_q = o; o += slot;
+  w.off_s = o; o += 2 * slot;
+  w.off_dbg = o;
+  if (d->debug_keep) o += align_up(dbg, 1024);
+  w.total = o;
+  return w;
+}
+
+static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
+  const WsLayout w = ws_layout(d, B, T);
+  bf16* X = reinterpret_cast<bf16*>(ws + w.off_x);
+  bf16* U = reinterpret_cast<bf16*>(ws + w.off_u);
+  bf16* H = reinterpret_cast<bf16*>(ws + w.off_h);
+  bf16* P = reinterpret_cast<bf16*>(ws + w.off_p);
+  bf16* Q = reinterpret_cast<bf16*>(ws + w.off_q);
+  float* S = reinterpret_cast<float*>(ws + w.off_s);
+  pl.a0 = reinterpret_cast<bf16*>(ws + w.off_a0);
+  pl.cb = reinterpret_cast<float*>(ws + w.off_cb);
+  uint8_t* dbg = ws + w.off_dbg;
+
+  auto push = [&](int layer, const bf16* x, int L, const ConvEpilogue& ep) -> int {
+    Step s{};
+    s.layer = layer; s.x = x; s.ep = ep; s.L = L;
+    Layer& ly = d->layers[layer];
+    ConvGeom g = ly.geom;
+    g.B = B; g.L = L;
+    s.tc.p.g = g;
+    if (d->impl == 0) {
+      if (plan_conv_tc(&s.tc, g, x, ly.w, d->num_sms, d->desc_mode)) return 1;
+    }
+    pl.steps.push_back(s);
+    return 0;
+  };
+  auto keep = [&](const std::string& name, int C, int Lr, float gain) {
+    if (!d->debug_keep) return;
+    Step& s = pl.steps.back();
+    s.dbg_dst = reinterpret_cast<bf16*>(dbg);
+    s.dbg_bytes = (size_t)B * Lr * C * 2;
+    pl.debug.push_back({name, {s.dbg_dst, C, Lr, gain}});
+    dbg += align_up(s.dbg_bytes, 1024);
+  };
+  auto ep0 = [&](int layer) {
+    ConvEpilogue e{};
+    e.bias = d->layers[layer].bias;
+    e.res_gain = 1.f / kSlope;
+    e.out_slope = kSlope;
+    e.mrf_scale = 1.f;
+    return e;
+  };
+
+  // conv_pre (+cond): bias_b filled at decode time when g is given
+  {
+    ConvEpilogue e = ep0(d->l_pre);
+    e.out = X;
+    if (push(d->l_pre, pl.a0, T, e)) return 1;
+    keep("conv_pre", d->hp.upsample_initial_channel, T, 1.f / kSlope);
+  }
+  const int nk = d->hp.num_kernels;
+  const int nstage = d->hp.num_upsamples;
+  int L = T;
+  for (int i = 0; i < nstage; ++i) {
+    const int s = d->hp.upsample_rates[i];
+    const int ch = d->stage_ch[i];
+    {  // ups[i]: rows = input rows, columns = s * ch  ==  [B][L*s][ch]
+      ConvEpilogue e = ep0(d->l_ups[i]);
+      e.out = U;
+      if (push(d->l_ups[i], X, L, e)) return 1;
+    }
+    L *= s;
+    keep("ups." + std::to_string(i), ch, L, 1.f / kSlope);
+    const float next_slope = (i == nstage - 1) ? kPostSlope : kSlope;
+    for (int j = 0; j < nk; ++j) {
+      const std::vector<int>& convs = d->l_rb[i * nk + j];
+      const bf16* cur = U;
+      const int nconv = (int)convs.size();
+      const int npairs = d->hp.resblock == 1 ? nconv / 2 : nconv;
+      for (int m = 0; m < npairs; ++m) {
+        const bf16* conv_in = cur;
+        int lid;
+        if (d->hp.resblock == 1) {
+          ConvEpilogue e1 = ep0(convs[2 * m]);
+          e1.out = H;
+          if (push(convs[2 * m], cur, L, e1)) return 1;
+          conv_in = H;
+          lid = convs[2 * m + 1];
+        } else {
+          lid = convs[m];
+        }
+        ConvEpilogue e = ep0(lid);
+        e.res = cur;
+        bf16* dst = (m & 1) ? Q : P;
+        if (m < npairs - 1) {
+          e.out = dst;
+        } else {
+          e.mrf = S;
+          e.mrf_scale = 1.f / nk;
+          if (nk == 1) { e.mrf_mode = 3; e.mrf = nullptr; }
+          else if (j == 0) e.mrf_mode = 1;
+          else if (j < nk - 1) e.mrf_mode = 2;
+          else e.mrf_mode = 3;
+          e.out = X;
+          e.out_slope = next_slope;
+        }
+        if (push(lid, conv_in, L, e)) return 1;
+        cur = dst;
+      }
+    }
+    keep("mrf." + std::to_string(i), ch, L, 1.f / next_slope);
+  }
+  pl.x_final = X;
+  pl.L_final = L;
+  pl.C_final = d->stage_ch.back();
+  return 0;
+}
+
+static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
+  Layer& ly = d->layers[s.layer];
+  if (d->impl == 0) return launch_conv_tc(s.tc, s.ep, st);
+  return launch_conv_simt(s.tc.p.g, s.ep, s.x, ly.w, st);
+}
+
+}  // namespace vd
+
+// =========================================================================================== C ABI
+extern "C" {
+
+int vitsdec_abi_version(void) { return VITSDEC_ABI_VERSION; }
+const char* vitsdec_last_error(void) { return g_err.c_str(); }
+
+int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out) {
+  VD_CHECK(hp && out, "vitsdec_create: null argument");
+  VD_CHECK(hp->resblock == 1 || hp->resblock == 2, "resblock must be 1 or 2");
+  VD_CHECK(hp->num_upsamples >= 1 && hp->num_upsamples <= VITSDEC_MAX_UPSAMPLES, "bad num_upsamples");
+  VD_CHECK(hp->num_kernels >= 1 && hp->num_kernels <= VITSDEC_MAX_KERNELS, "bad num_kernels");
+  VD_CHECK(hp->initial_channel % 32 == 0, "initial_channel must be a multiple of 32");
+  VD_CHECK(hp->upsample_initial_channel % 32 == 0, "upsample_initial_channel must be a multiple of 32");
+  int ndev = 0;
+  VD_CUDA(cudaGetDeviceCount(&ndev));
+  VD_CHECK(device >= 0 && device < ndev, "vitsdec_create: no such CUDA device (there is no CPU fallback)");
+  cudaDeviceProp prop;
+  VD_CUDA(cudaGetDeviceProperties(&prop, device));
+  VD_CHECK(prop.major == 10, "vitsdec needs an sm_100 (B200) device: kernels are tcgen05/TMA only");
+  DeviceGuard guard(device);
+  VD_CHECK(guard.ok, "cudaSetDevice failed");
+
+  std::unique_ptr<vitsdec_decoder> d(new vitsdec_decoder());
+  d->hp = *hp;
+  d->device = device;
+  d->num_sms = prop.multiProcessorCount;
+  const int c0 = hp->upsample_initial_channel;
+  d->l_pre = add_layer(d.get(), "conv_pre", kConv, hp->initial_channel, c0, 7, 1, 1);
+  for (int i = 0; i < hp->num_upsamples; ++i) {
+    const int ci = c0 >> i, co = c0 >> (i + 1);
+    const int k = hp->upsample_kernel_sizes[i], s = hp->upsample_rates[i];
+    VD_CHECK(co % 32 == 0 && co > 0, "every stage needs a multiple of 32 channels");
+    VD_CHECK(k >= s && (k - s) % 2 == 0, "upsample kernel must satisfy k >= stride and (k - stride) even");
+    d->stage_ch.push_back(co);
+    d->hop *= s;
+    d->l_ups.push_back(add_layer(d.get(), "ups." + std::to_string(i), kConvT, ci, co, k, 1, s));
+    VD_CHECK(d->layers.back().geom.ntaps <= kMaxTaps, "upsample kernel too large");
+  }
+  int n = 0;
+  for (int i = 0; i < hp->num_upsamples; ++i) {
+    const int ch = d->stage_ch[i];
+    for (int j = 0; j < hp->num_kernels; ++j, ++n) {
+      const int k = hp->resblock_kernel_sizes[j];
+      const int nd = hp->num_dilations[j];
+      VD_CHECK(k % 2 == 1 && k <= kMaxTaps, "resblock kernel sizes must be odd and <= 16");
+      VD_CHECK(nd >= 1 && nd <= VITSDEC_MAX_DILATIONS, "bad dilation count");
+      std::vector<int> ids;
+      const std::string base = "resblocks." + std::to_string(n) + ".";
+      if (hp->resblock == 1) {
+        VD_CHECK(nd == 3, "ResBlock1 takes exactly 3 dilations (modules.py:188)");
+        std::vector<int> c1, c2;
+        for (int m = 0; m < 3; ++m)
+          c1.push_back(add_layer(d.get(), base + "convs1." + std::to_string(m), kConv, ch, ch, k,
+                                 hp->resblock_dilation_sizes[j][m], 1));
+        for (int m = 0; m < 3; ++m)
+          c2.push_back(add_layer(d.get(), base + "convs2." + std::to_string(m), kConv, ch, ch, k, 1, 1));
+        for (int m = 0; m < 3; ++m) { ids.push_back(c1[m]); ids.push_back(c2[m]); }
+      } else {
+        for (int m = 0; m < nd; ++m)
+          ids.push_back(add_layer(d.get(), base + "convs." + std::to_string(m), kConv, ch, ch, k,
+                                  hp->resblock_dilation_sizes[j][m], 1));
+      }
+      d->l_rb.push_back(ids);
+    }
+  }
+  d->l_post = add_layer(d.get(), "conv_post", kPost, d->stage_ch.back(), 1, 7, 1, 1);
+  if (hp->gin_channels > 0) d->l_cond = add_layer(d.get(), "cond", kCond, hp->gin_channels, c0, 1, 1, 1);
+  for (Layer& l : d->layers)
+    if (alloc_layer(l)) return 1;
+  VD_CUDA(cudaMalloc(&d->scale_scratch, 4096 * sizeof(float)));
+  *out = d.release();
+  return 0;
+}
+
+void vitsdec_destroy(vitsdec_decoder* d) {
+  if (!d) return;
+  DeviceGuard guard(d->device);
+  cudaDeviceSynchronize();
+  for (Layer& l : d->layers) {
+    cudaFree(l.w); cudaFree(l.bias); cudaFree(l.wf32);
+  }
+  cudaFree(d->scale_scratch);
+  if (d->hbuf) cudaFree(d->hbuf);
+  if (d->hstream) cudaStreamDestroy(d->hstream);
+  delete d;
+}
+
+int vitsdec_num_layers(const vitsdec_decoder* d) { return d ? (int)d->layers.size() : 0; }
+const char* vitsdec_layer_name(const vitsdec_decoder* d, int i) {
+  if (!d || i < 0 || i >= (int)d->layers.size()) return nullptr;
+  return d->layers[i].name.c_str();
+}
+
+int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, const float* wg, const float* bias,
+                       void* stream) {
+  VD_CHECK(d && name && w, "vitsdec_load_layer: null argument");
+  auto it = d->by_name.find(name);
+  VD_CHECK(it != d->by_name.end(), std::string("vitsdec_load_layer: unknown layer ") + name);
+  DeviceGuard guard(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(d->mu);
+  Layer& l = d->layers[it->second];
+  if (l.kind == kConv) {
+    VD_CHECK(l.c_out <= 4096, "too many channels");
+    if (launch_wn_scale(w, wg, d->scale_scratch, l.c_out, l.c_in * l.k, st)) return 1;
+    if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st)) return 1;
+    if (launch_replicate_bias(bias, l.bias, l.c_out, 1, st)) return 1;
+  } else if (l.kind == kConvT) {
+    VD_CHECK(l.c_in <= 4096, "too many channels");
+    if (launch_wn_scale(w, wg, d->scale_scratch, l.c_in, l.c_out * l.k, st)) return 1;  // dim 0 of [C_in,C_out,k]
+    if (launch_pack_convT(w, d->scale_scratch, l.w, l.c_in, l.c_out, l.k, l.stride, (l.k - l.stride) / 2,
+                          l.geom.ntaps, l.geom.tap_off[0], st))
+      return 1;
+    if (launch_replicate_bias(bias, l.bias, l.c_out, l.stride, st)) return 1;
+  } else {
+    VD_CHECK(wg == nullptr, "conv_post / cond are not weight-normed in the reference (models.py:264,268)");
+    VD_CUDA(cudaMemcpyAsync(l.wf32, w, (size_t)l.c_out * l.c_in * l.k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (l.kind == kCond) {
+      VD_CHECK(bias != nullptr, "cond needs a bias");
+      VD_CUDA(cudaMemcpyAsync(l.bias, bias, (size_t)l.c_out * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  l.loaded = true;
+  return 0;
+}
+
+size_t vitsdec_workspace_bytes(const vitsdec_decoder* d, int batch, int frames) {
+  if (!d || batch <= 0 || frames <= 0) return 0;
+  return ws_layout(d, batch, frames).total;
+}
+
+int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc, const float* g, float* out, int B,
+                   int T, void* ws, size_t ws_bytes, void* stream) {
+  VD_CHECK(d && z && out && ws, "vitsdec_decode: null argument");
+  VD_CHECK(B > 0 && T > 0, "vitsdec_decode: empty batch or zero frames");
+  VD_CHECK(B <= 65535, "vitsdec_decode: batch too large");
+  VD_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+  VD_CHECK(g == nullptr || d->l_cond >= 0, "g given but the decoder was built with gin_channels=0 (models.py:267)");
+  for (const Layer& l : d->layers)
+    VD_CHECK(l.loaded, "vitsdec_decode: layer " + l.name + " has no weights loaded");
+  DeviceGuard guard(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  std::shared_ptr<Plan> plan;
+  {
+    std::lock_guard<std::mutex> lock(d->mu);
+    VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
+    const PlanKey key{B, T, d->impl, d->desc_mode * 2 + d->debug_keep, ws};
+    for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
+      if (!(it->first < key) && !(key < it->first)) {
+        plan = it->second;
+        d->plans.splice(d->plans.begin(), d->plans, it);
+        break;
+      }
+    }
+    if (!plan) {
+      plan = std::make_shared<Plan>();
+      if (build_plan(d, *plan, B, T, static_cast<uint8_t*>(ws))) return 1;
+      d->plans.emplace_front(key, plan);
+      if (d->plans.size() > 16) d->plans.pop_back();
+    }
+    d->last_plan = plan;
+  }
+
+  int launches = 0;
+  if (launch_pack_z(z, zsb, zsc, plan->a0, B, d->hp.initial_channel, T, st)) return 1;
+  ++launches;
+  if (g) {
+    const Layer& lc = d->layers[d->l_cond];
+    if (launch_cond(lc.wf32, lc.bias, g, plan->cb, B, lc.c_out, lc.c_in, st)) return 1;
+    ++launches;
+  }
+  for (size_t i = 0; i < plan->steps.size(); ++i) {
+    Step s = plan->steps[i];  // copy: per-call epilogue fields, re-entrant across threads
+    if (i == 0) s.ep.bias_b = g ? plan->cb : nullptr;
+    if (run_conv(d, s, st)) return 1;
+    ++launches;
+    if (s.dbg_dst) VD_CUDA(cudaMemcpyAsync(s.dbg_dst, s.ep.out, s.dbg_bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  if (launch_conv_post(plan->x_final, d->layers[d->l_post].wf32, out, B, plan->L_final, plan->C_final, st)) return 1;
+  ++launches;
+  d->last_launches = launches;
+  return 0;
+}
+
+int vitsdec_decode_host(vitsdec_decoder* d, const float* z, const float* g, float* out, int B, int T) {
+  VD_CHECK(d && z && out, "vitsdec_decode_host: null argument");
+  DeviceGuard guard(d->device);
+  if (!d->hstream) VD_CUDA(cudaStreamCreateWithFlags(&d->hstream, cudaStreamNonBlocking));
+  const size_t zb = align_up((size_t)B * d->hp.initial_channel * T * 4, 1024);
+  const size_t gb = align_up((size_t)B * std::max(1, d->hp.gin_channels) * 4, 1024);
+  const size_t ob = align_up((size_t)B * T * d->hop * 4, 1024);
+  const size_t wb = vitsdec_workspace_bytes(d, B, T);
+  const size_t need = zb + gb + ob + wb;
+  if (need > d->hbuf_bytes) {
+    VD_CUDA(cudaStreamSynchronize(d->hstream));
+    if (d->hbuf) VD_CUDA(cudaFree(d->hbuf));
+    d->hbuf = nullptr; d->hbuf_bytes = 0;
+    {
+      std::lock_guard<std::mutex> lock(d->mu);
+      d->plans.clear();
+    }
+    VD_CUDA(cudaMalloc(&d->hbuf, need));
+    d->hbuf_bytes = need;
+  }
+  uint8_t* base = static_cast<uint8_t*>(d->hbuf);
+  float* zd = reinterpret_cast<float*>(base);
+  float* gd = reinterpret_cast<float*>(base + zb);
+  float* od = reinterpret_cast<float*>(base + zb + gb);
+  void* ws = base + zb + gb + ob;
+  VD_CUDA(cudaMemcpyAsync(zd, z, (size_t)B * d->hp.initial_channel * T * 4, cudaMemcpyHostToDevice, d->hstream));
+  if (g) VD_CUDA(cudaMemcpyAsync(gd, g, (size_t)B * d->hp.gin_channels * 4, cudaMemcpyHostToDevice, d->hstream));
+  if (vitsdec_decode(d, zd, (int64_t)d->hp.initial_channel * T, T, g ? gd : nullptr, od, B, T, ws, wb, d->hstream))
+    return 1;
+  VD_CUDA(cudaMemcpyAsync(out, od, (size_t)B * T * d->hop * 4, cudaMemcpyDeviceToHost, d->hstream));
+  VD_CUDA(cudaStreamSynchronize(d->hstream));
+  return 0;
+}
+
+int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
+  VD_CHECK(d && key, "vitsdec_set_option: null argument");
+  std::lock_guard<std::mutex> lock(d->mu);
+  if (!strcmp(key, "impl")) { VD_CHECK(value == 0 || value == 1, "impl: 0 (tcgen05) or 1 (simt)"); d->impl = value; }
+  else if (!strcmp(key, "desc_mode")) d->desc_mode = value;
+  else if (!strcmp(key, "debug_keep")) d->debug_keep = value ? 1 : 0;
+  else { set_error(std::string("unknown option ") + key); return 1; }
+  return 0;
+}
+
+int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
+  VD_CHECK(d && key && value, "vitsdec_get_option: null argument");
+  if (!strcmp(key, "impl")) *value = d->impl;
+  else if (!strcmp(key, "desc_mode")) *value = d->desc_mode;
+  else if (!strcmp(key, "debug_keep")) *value = d->debug_keep;
+  else if (!strcmp(key, "hop")) *value = d->hop;
+  else if (!strcmp(key, "num_sms")) *value = d->num_sms;
+  else { set_error(std::string("unknown option ") + key); return 1; }
+  return 0;
+}
+
+int vitsdec_last_launch_count(const vitsdec_decoder* d) { return d ? d->last_launches : 0; }
+
+int vitsdec_debug_read(vitsdec_decoder* d, const char* name, float* out, size_t out_elems, int* channels, int* length,
+                       void* stream) {
+  VD_CHECK(d && name && out, "vitsdec_debug_read: null argument");
+  std::shared_ptr<Plan> plan;
+  {
+    std::lock_guard<std::mutex> lock(d->mu);
+    plan = d->last_plan;
+  }
+  VD_CHECK(plan != nullptr, "vitsdec_debug_read: no decode has run");
+  DeviceGuard guard(d->device);
+  for (auto& e : plan->debug) {
+    if (e.first == name) {
+      const int C = std::get<1>(e.second), L = std::get<2>(e.second);
+      const int B = plan->steps[0].tc.p.g.B;
+      VD_CHECK(out_elems >= (size_t)B * C * L, "vitsdec_debug_read: output too small");
+      if (channels) *channels = C;
+      if (length) *length = L;
+      return launch_unpack_debug(std::get<0>(e.second), std::get<3>(e.second), out, B, L, C,
+                                 static_cast<cudaStream_t>(stream));
+    }
+  }
+  set_error(std::string("vitsdec_debug_read: unknown or not-kept tensor ") + name + " (set option debug_keep=1)");
+  return 1;
+}
+
+static int op_conv_common(int device, Layer& l, const void* x, const float* w, const float* bias, const void* res,
+                          float res_gain, float out_slope, void* y, int B, int L, int impl, int desc_mode,
+                          cudaStream_t st) {
+  DeviceGuard guard(device);
+  VD_CHECK(guard.ok, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  VD_CUDA(cudaGetDeviceProperties(&prop, device));
+  VD_CHECK(prop.major == 10, "vitsdec needs an sm_100 (B200) device");
+  if (alloc_layer(l)) return 1;
+  float* scale = nullptr;
+  VD_CUDA(cudaMalloc(&scale, 4096 * sizeof(float)));
+  int rc = 0;
+  if (l.kind == kConv) {
+    rc = launch_wn_scale(w, nullptr, scale, l.c_out, l.c_in * l.k, st) ||
+         launch_pack_conv(w, scale, l.w, l.c_out, l.c_in, l.k, st) ||
+         launch_replicate_bias(bias, l.bias, l.c_out, 1, st);
+  } else {
+    rc = launch_wn_scale(w, nullptr, scale, l.c_in, l.c_out * l.k, st) ||
+         launch_pack_convT(w, scale, l.w, l.c_in, l.c_out, l.k, l.stride, (l.k - l.stride) / 2, l.geom.ntaps,
+                           l.geom.tap_off[0], st) ||
+         launch_replicate_bias(bias, l.bias, l.c_out, l.stride, st);
+  }
+  if (!rc) {
+    ConvGeom g = l.geom;
+    g.B = B; g.L = L;
+    ConvEpilogue e{};
+    e.bias = l.bias;
+    e.res = static_cast<const bf16*>(res);
+    e.res_gain = res_gain;
+    e.out_slope = out_slope;
+    e.mrf_scale = 1.f;
+    e.out = static_cast<bf16*>(y);
+    if (impl == 0) {
+      ConvTcPlan pl{};
+      rc = plan_conv_tc(&pl, g, static_cast<const bf16*>(x), l.w, prop.multiProcessorCount, desc_mode) ||
+           launch_conv_tc(pl, e, st);
+    } else {
+      rc = launch_conv_simt(g, e, static_cast<const bf16*>(x), l.w, st);
+    }
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(scale); cudaFree(l.w); cudaFree(l.bias);
+  if (!rc && se != cudaSuccess) { set_error(std::string("op_conv: ") + cudaGetErrorString(se)); rc = 1; }
+  return rc;
+}
+
+int vitsdec_op_conv1d(int device, const void* x, const float* w, const float* bias, const void* res, float res_gain,
+                      float out_slope, void* y, int B, int L, int c_in, int c_out, int k, int dilation, int impl,
+                      int desc_mode, void* stream) {
+  VD_CHECK(x && w && y, "vitsdec_op_conv1d: null argument");
+  VD_CHECK(k % 2 == 1 && k <= kMaxTaps && k >= 1, "k must be odd and <= 16");
+  Layer l;
+  l.kind = kConv; l.c_in = c_in; l.c_out = c_out; l.k = k; l.dil = dilation;
+  conv_geom(l);
+  return op_conv_common(device, l, x, w, bias, res, res_gain, out_slope, y, B, L, impl, desc_mode,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int vitsdec_op_conv_transpose1d(int device, const void* x, const float* w, const float* bias, float out_slope, void* y,
+                                int B, int L, int c_in, int c_out, int k, int stride, int impl, void* stream) {
+  VD_CHECK(x && w && y, "vitsdec_op_conv_transpose1d: null argument");
+  VD_CHECK(k >= stride && (k - stride) % 2 == 0, "need k >= stride and (k - stride) even");
+  Layer l;
+  l.kind = kConvT; l.c_in = c_in; l.c_out = c_out; l.k = k; l.stride = stride;
+  convT_geom(l);
+  VD_CHECK(l.geom.ntaps <= kMaxTaps, "kernel too large");
+  return op_conv_common(device, l, x, w, bias, nullptr, 1.f, out_slope, y, B, L, impl, 0,
+                        static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

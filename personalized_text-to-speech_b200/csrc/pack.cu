@@ -1,0 +1,206 @@
+// Load-time and boundary kernels: weight-norm fold + operand packing, latent transposition,
+// speaker-conditioning GEMV, conv_post + tanh, debug read-back.
+#include "common.cuh"
+#include "pack.h"
+
+namespace vd {
+
+// scale[r] = g[r] / ||v[r, :]||_2  (torch.nn.utils.weight_norm, dim=0; reference models.py:254, modules.py:191-206)
+__global__ void wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ scale,
+                                int inner) {
+  const int r = blockIdx.x;
+  float s = 0.f;
+  if (g != nullptr) {
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+      const float x = v[(long)r * inner + i];
+      s = fmaf(x, x, s);
+    }
+  }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
+    scale[r] = g != nullptr ? g[r] / sqrtf(t) : 1.f;
+  }
+}
+
+// Conv1d weight [co][ci][k] -> packed [tap][co][ci] bf16 (B operand rows = co, K = ci contiguous)
+__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                 __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int k) {
+  const long total = (long)k * c_out * c_in;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ci = i % c_in;
+    const int co = (i / c_in) % c_out;
+    const int j = i / ((long)c_in * c_out);
+    wp[i] = __float2bfloat16_rn(w[((long)co * c_in + ci) * k + j] * scale[co]);
+  }
+}
+
+// ConvTranspose1d weight [ci][co][k] (stride s, padding p) -> polyphase packed [tap][r*c_out+co][ci]:
+// output sample s*i + r takes input rows i + off; the contributing kernel index is j = r + p - s*off.
+__global__ void pack_convT_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                  __nv_bfloat16* __restrict__ wp, int c_in, int c_out, int k, int s, int p,
+                                  int ntaps, int off0) {
+  const long total = (long)ntaps * s * c_out * c_in;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ci = i % c_in;
+    const long rest = i / c_in;
+    const int n = rest % (s * c_out);
+    const int tap = rest / (s * c_out);
+    const int r = n / c_out, co = n % c_out;
+    const int j = r + p - s * (off0 + tap);
+    float val = 0.f;
+    if (j >= 0 && j < k) val = w[((long)ci * c_out + co) * k + j] * scale[ci];
+    wp[i] = __float2bfloat16_rn(val);
+  }
+}
+
+__global__ void replicate_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int c_out, int reps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c_out * reps) out[i] = b ? b[i % c_out] : 0.f;
+}
+
+// z fp32 [B][C][T] (strided) -> bf16 [B][T][C]
+__global__ void pack_z_kernel(const float* __restrict__ z, long sb, long sc, __nv_bfloat16* __restrict__ out, int C,
+                              int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? z[b * sb + c * sc + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) out[((long)b * T + t) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// cb[b][co] = cond.bias[co] + sum_ci cond.weight[co][ci] * g[b][ci]   (models.py:272-273; one warp per output)
+__global__ void cond_kernel(const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ g,
+                            float* __restrict__ cb, int c_out, int gin) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= c_out) return;
+  float s = 0.f;
+  for (int i = lane; i < gin; i += 32) s = fmaf(wc[(long)warp * gin + i], g[(long)b * gin + i], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) cb[(long)b * c_out + warp] = s + bc[warp];
+}
+
+// out[b][t] = tanh( sum_j sum_c w[c][j] * x[b][t + j - 3][c] ), x already leaky-relu'ed (models.py:285-287)
+constexpr int kPostT = 256;
+__global__ void __launch_bounds__(kPostT) conv_post_kernel(const __nv_bfloat16* __restrict__ x,
+                                                           const float* __restrict__ w, float* __restrict__ out,
+                                                           int L, int C) {
+  extern __shared__ uint8_t sm[];
+  float* ws = reinterpret_cast<float*>(sm);                                  // [7][C]
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(sm + 7 * C * 4);     // [kPostT + 6][C + 8] (padded rows)
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kPostT;
+  const int pitch = C + 8;
+  for (int i = threadIdx.x; i < 7 * C; i += kPostT) ws[i] = w[(i % C) * 7 + i / C];  // conv_post.weight [1][C][7]
+  const int vec_per_row = C / 8;
+  for (int i = threadIdx.x; i < (kPostT + 6) * vec_per_row; i += kPostT) {
+    const int r = i / vec_per_row, v = i % vec_per_row;
+    const int t = t0 + r - 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (t >= 0 && t < L) val = __ldg(reinterpret_cast<const uint4*>(x + ((long)b * L + t) * C) + v);
+    *reinterpret_cast<uint4*>(xs + r * pitch + v * 8) = val;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
+  float acc = 0.f;
+  for (int j = 0; j < 7; ++j) {
+    const __nv_bfloat16* xr = xs + (threadIdx.x + j) * pitch;
+    const float* wr = ws + j * C;
+    for (int c = 0; c < C; c += 8) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(xr + c);
+      const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(x2[e]);
+        acc = fmaf(f.x, wr[c + 2 * e], acc);
+        acc = fmaf(f.y, wr[c + 2 * e + 1], acc);
+      }
+    }
+  }
+  out[(long)b * L + t] = tanhf(acc);
+}
+
+// a-form bf16 [B][L][C] -> residual-stream fp32 NCL [B][C][L]
+__global__ void unpack_debug_kernel(const __nv_bfloat16* __restrict__ a, float gain, float* __restrict__ out, int L,
+                                    int C) {
+  const long total = (long)gridDim.y * L * C;
+  (void)total;
+  const int b = blockIdx.y;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)L * C; i += (long)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const long t = i / C;
+    const float v = __bfloat162float(a[(long)b * L * C + i]);
+    out[((long)b * C + c) * L + t] = v >= 0.f ? v : v * gain;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+int launch_wn_scale(const float* v, const float* g, float* scale, int rows, int inner, cudaStream_t st) {
+  wn_scale_kernel<<<rows, 256, 0, st>>>(v, g, scale, inner);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int c_out, int c_in, int k,
+                     cudaStream_t st) {
+  const long total = (long)k * c_out * c_in;
+  pack_conv_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_out, c_in, k);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int c_in, int c_out, int k, int s, int p,
+                      int ntaps, int off0, cudaStream_t st) {
+  const long total = (long)ntaps * s * c_out * c_in;
+  pack_convT_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_in, c_out, k, s, p,
+                                                                                   ntaps, off0);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaStream_t st) {
+  replicate_bias_kernel<<<(c_out * reps + 255) / 256, 256, 0, st>>>(b, out, c_out, reps);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_pack_z(const float* z, long sb, long sc, __nv_bfloat16* out, int B, int C, int T, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  pack_z_kernel<<<grid, block, 0, st>>>(z, sb, sc, out, C, T);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_cond(const float* wc, const float* bc, const float* g, float* cb, int B, int c_out, int gin,
+                cudaStream_t st) {
+  dim3 grid((c_out * 32 + 255) / 256, B);
+  cond_kernel<<<grid, 256, 0, st>>>(wc, bc, g, cb, c_out, gin);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_conv_post(const __nv_bfloat16* x, const float* w, float* out, int B, int L, int C, cudaStream_t st) {
+  VD_CHECK(C % 8 == 0, "conv_post: channels must be a multiple of 8");
+  const size_t smem = 7 * C * 4 + (size_t)(kPostT + 6) * (C + 8) * 2;
+  VD_CHECK(smem <= 48 * 1024, "conv_post: too many channels");
+  dim3 grid((L + kPostT - 1) / kPostT, B);
+  conv_post_kernel<<<grid, kPostT, smem, st>>>(x, w, out, L, C);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_unpack_debug(const __nv_bfloat16* a, float gain, float* out, int B, int L, int C, cudaStream_t st) {
+  dim3 grid((unsigned)std::min<long>(((long)L * C + 255) / 256, 8192), B);
+  unpack_debug_kernel<<<grid, 256, 0, st>>>(a, gain, out, L, C);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vd

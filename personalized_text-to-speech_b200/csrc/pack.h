@@ -1,0 +1,20 @@
+// Launchers for the load-time / boundary kernels in pack.cu.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+namespace vd {
+int launch_wn_scale(const float* v, const float* g, float* scale, int rows, int inner, cudaStream_t st);
+int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int c_out, int c_in, int k,
+                     cudaStream_t st);
+int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int c_in, int c_out, int k, int s, int p,
+                      int ntaps, int off0, cudaStream_t st);
+int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaStream_t st);
+int launch_pack_z(const float* z, long sb, long sc, __nv_bfloat16* out, int B, int C, int T, cudaStream_t st);
+int launch_cond(const float* wc, const float* bc, const float* g, float* cb, int B, int c_out, int gin,
+                cudaStream_t st);
+int launch_conv_post(const __nv_bfloat16* x, const float* w, float* out, int B, int L, int C, cudaStream_t st);
+int launch_unpack_debug(const __nv_bfloat16* a, float gain, float* out, int B, int L, int C, cudaStream_t st);
+}  // namespace vd

@@ -1,0 +1,42 @@
+"""Python wrappers of the single-op C-ABI entries (per-kernel parity tests)."""
+import torch
+
+from . import _capi
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def conv1d_cl(x, w, bias=None, dilation=1, res=None, res_gain=10.0, out_slope=1.0, impl=0, desc_mode=0):
+    """Fused conv on channels-last bf16 activations.  x: bf16 [B, L, C_in]; w: fp32 [C_out, C_in, k] (rounded to
+    bf16 inside); bias fp32 [C_out]; res: bf16 [B, L, C_out] stored post-leaky-relu(1/res_gain).  -> bf16 [B, L, C_out]."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
+    B, L, c_in = x.shape
+    c_out, c_in2, k = w.shape
+    assert c_in2 == c_in
+    w = w.float().contiguous()
+    bias = None if bias is None else bias.float().contiguous()
+    y = torch.empty((B, L, c_out), dtype=torch.bfloat16, device=x.device)
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    _capi.check(_capi.lib().vitsdec_op_conv1d(x.device.index or 0, _ptr(x), _ptr(w), _ptr(bias), _ptr(res),
+                                              float(res_gain), float(out_slope), _ptr(y), B, L, c_in, c_out, k,
+                                              int(dilation), int(impl), int(desc_mode), st), "vitsdec_op_conv1d")
+    return y
+
+
+def conv_transpose1d_cl(x, w, bias=None, stride=2, out_slope=1.0, impl=0):
+    """Polyphase ConvTranspose1d(k, stride, padding=(k-stride)//2).  x: bf16 [B, L, C_in]; w: fp32 [C_in, C_out, k].
+    -> bf16 [B, L*stride, C_out]."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
+    B, L, c_in = x.shape
+    c_in2, c_out, k = w.shape
+    assert c_in2 == c_in
+    w = w.float().contiguous()
+    bias = None if bias is None else bias.float().contiguous()
+    y = torch.empty((B, L * stride, c_out), dtype=torch.bfloat16, device=x.device)
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    _capi.check(_capi.lib().vitsdec_op_conv_transpose1d(x.device.index or 0, _ptr(x), _ptr(w), _ptr(bias),
+                                                        float(out_slope), _ptr(y), B, L, c_in, c_out, k, int(stride),
+                                                        int(impl), st), "vitsdec_op_conv_transpose1d")
+    return y
