@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Headline benchmark: decoded audio-seconds per second of the VITS waveform decoder (HiFi-GAN Generator).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a decoder
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (torch eager port)
+
+One "step" = one decode of a batch of synthetic latents (BASELINE.json config 3: 16 utterances x 10 s,
+T = 862 frames, hop 256, 22.05 kHz, random-init weights of configs/finetune_speaker.json).  N > 1: one
+process per GPU (torchrun), every rank decodes its own 16 utterances (utterance sharding, no collective
+on the data path; "weak" scaling), time = max over ranks.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, HOP = 22050, 256
+FLOP_PER_FRAME = 614907904       # SURVEY.md section 8d / BASELINE.md section 3 (2 x 307 453 952 MAC)
+FLOP_PER_UTT = 262144            # cond(g)
+CONV_POST_FLOP_PER_FRAME = 2 * 57344  # conv_post runs on CUDA cores, not in the tcgen05 kernel
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference(batch, frames, steps, warmup, threads=None):
+    """The reference's CPU implementation of the path: torch eager conv1d/conv_transpose1d/leaky_relu/tanh with the
+    weight-norm recompute per forward (oracle/generator_torch.py restates models.py:270-289 op for op)."""
+    import numpy as np
+    import torch
+    import oracle
+    from oracle.generator_torch import generator_forward_torch, to_torch_state_dict
+    if threads:
+        torch.set_num_threads(threads)
+    hp = oracle.FINETUNE_SPEAKER
+    sd = to_torch_state_dict(oracle.synth_state_dict(hp, 0, gain=2.0))
+    rs = np.random.RandomState(1)
+    z = torch.from_numpy(rs.standard_normal((batch, hp.initial_channel, frames)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((batch, hp.gin_channels, 1)).astype(np.float32))
+    for _ in range(warmup):
+        generator_forward_torch(hp, sd, z, g)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        generator_forward_torch(hp, sd, z, g)
+    dt = (time.perf_counter() - t0) / steps
+    return batch * frames * HOP / SR / dt, dt, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    frames = -(-int(round(args.seconds * SR)) // HOP)  # ceil(sec * 22050 / 256): 10 s -> 862
+    B = args.batch
+    workload = "Generator decode, batch %d x %.0f s synthetic latents per GPU (T=%d frames, hop 256, 22.05 kHz), " \
+               "finetune_speaker.json hyper-parameters" % (B, args.seconds, frames)
+    config = {"workload": workload, "batch_per_gpu": B, "frames": frames,
+              "l2": "working set ~%.1f GB of activations per step >> 126 MB L2; no explicit flush" %
+                    (7 * B * frames * 16384 / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample: ONE utterance of the same workload per step (the CPU needs seconds per utterance)
+        steps = max(1, min(args.steps, 3))
+        val, dt, cores = cpu_reference(1, frames, steps, 1)
+        line = {"impl": "reference", "metric": "decoded audio-sec/sec, VITS Generator", "value": val,
+                "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                 "sample": "1 of the %d utterances (B=1, T=%d) per step, torch CPU eager fp32, "
+                                           "weight-norm recomputed per forward like the reference" % (B, frames)},
+                "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import oracle
+    import vitsdec
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    hp = oracle.FINETUNE_SPEAKER  # hyper-parameters only; the oracle never decodes on this arm
+    cargs, ckw = hp.ctor_args()
+    G = vitsdec.Generator(*cargs, **ckw)
+    G.load_state_dict({k: torch.from_numpy(v) for k, v in oracle.synth_state_dict(hp, 0, gain=2.0).items()})
+    G = G.to(dev).eval()
+    G.assume_frozen = True
+    rs = np.random.RandomState(1 + rank)
+    z_host = torch.from_numpy(rs.standard_normal((B, hp.initial_channel, frames)).astype(np.float32)).pin_memory()
+    g_host = torch.from_numpy(rs.standard_normal((B, hp.gin_channels, 1)).astype(np.float32)).pin_memory()
+    z = z_host.to(dev)
+    g = g_host.to(dev)
+    out_host = torch.empty((B, 1, frames * HOP), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            y = G(z, g)
+        barrier()
+        # ---- device-resident timing (value) + live conv-kernel timing (roofline)
+        G.set_option("profile", 1)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            y = G(z, g)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        conv_ms, conv_launches = G.profile_read()
+        G.set_option("profile", 0)
+        launches = G.last_launch_count() * args.steps
+
+        # ---- end to end through the public API with HOST buffers (pinned): H2D + decode + D2H every step
+        for _ in range(2):
+            out_host.copy_(G(z_host.to(dev, non_blocking=True), g_host.to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            zz = z_host.to(dev, non_blocking=True)
+            gg = g_host.to(dev, non_blocking=True)
+            out_host.copy_(G(zz, gg), non_blocking=True)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+        gather_ms = None
+        if world > 1:  # the optional final waveform gather (north_star): timed separately, not on the data path
+            full = torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(full, y)
+            barrier()
+            e0.record()
+            dist.all_gather_into_tensor(full, y)
+            e1.record()
+            barrier()
+            gather_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    audio_s = world * B * frames * HOP / SR
+    ms_step = ms_total / args.steps
+    value = audio_s / (ms_step / 1e3)
+    e2e_val = audio_s / (ms_e2e / args.steps / 1e3)
+    burst, sustained, peak_src = load_peaks()
+    conv_flops_step = B * (frames * (FLOP_PER_FRAME - CONV_POST_FLOP_PER_FRAME))  # per rank, tcgen05 kernel only
+    conv_ms_step = conv_ms / args.steps
+    achieved = conv_flops_step / (conv_ms_step / 1e3) / 1e12
+    line = {
+        "metric": "decoded audio-sec/sec, VITS Generator", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+        "tflops": (world * B * (frames * FLOP_PER_FRAME + FLOP_PER_UTT)) / (ms_step / 1e3) / 1e12,
+        "e2e": {"value": e2e_val, "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(z_host.numel() * 4 + g_host.numel() * 4),
+                "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)"
+                     % (conv_launches // max(1, args.steps)),
+                     "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                     "frac_of_sustained": achieved / sustained, "peak_source": peak_src + ", bf16 dense burst",
+                     "conv_ms_per_step": conv_ms_step, "traffic": None},
+        "clocks": clocks,
+    }
+    if gather_ms is not None:
+        line["waveform_gather_ms"] = gather_ms
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            val, dt, cores = cpu_reference(1, frames, 2, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                    "sample": "1 of the %d utterances (B=1, T=%d), 2 timed passes after 1 warm-up, "
+                                              "torch CPU eager fp32 (oracle/generator_torch.py)" % (B, frames)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

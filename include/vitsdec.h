@@ -94,9 +94,15 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
                         int frames);
 
 /* Options: "impl" = 0 tcgen05 tensor-core kernels (default), 1 CUDA-core cross-check kernels (tests only);
- *          "desc_mode" = debug knob of the UMMA descriptor; "graph" = 1 capture the decode into a CUDA graph. */
+ *          "desc_mode" = debug knob of the UMMA descriptor (0 is the correct setting);
+ *          "debug_keep" = 1 keep named intermediates for vitsdec_debug_read; "profile" = 1 see below. */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
+
+/* Option "profile"=1 brackets the convolution launches (the tcgen05 kernel) of every decode with CUDA
+ * events on the launching stream; this returns the accumulated device time and launch count since the
+ * option was set (synchronises on the last event only).  Used by bench.py's roofline figure. */
+VITSDEC_API int vitsdec_profile_read(vitsdec_decoder* dec, double* conv_ms, int64_t* conv_launches);
 
 /* Kernel launches issued by the last vitsdec_decode on this decoder (for bench.py's gpu_launches). */
 VITSDEC_API int vitsdec_last_launch_count(const vitsdec_decoder* dec);

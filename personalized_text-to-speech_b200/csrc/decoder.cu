@@ -130,8 +130,13 @@ struct vitsdec_decoder {
   std::vector<int> stage_ch;
   int hop = 1;
   float* scale_scratch = nullptr;
-  int impl = 0, desc_mode = 0, debug_keep = 0;
+  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0;
   int last_launches = 0;
+  // profile=1: CUDA events around the convolution launches of every decode, accumulated on read
+  cudaEvent_t ev_conv0 = nullptr, ev_conv1 = nullptr;
+  bool ev_pending = false;
+  double prof_conv_ms = 0.0;
+  long prof_conv_launches = 0;
   std::mutex mu;
   std::list<std::pair<PlanKey, std::shared_ptr<Plan>>> plans;  // small LRU
   std::shared_ptr<Plan> last_plan;
@@ -411,6 +416,8 @@ void vitsdec_destroy(vitsdec_decoder* d) {
   cudaFree(d->scale_scratch);
   if (d->hbuf) cudaFree(d->hbuf);
   if (d->hstream) cudaStreamDestroy(d->hstream);
+  if (d->ev_conv0) cudaEventDestroy(d->ev_conv0);
+  if (d->ev_conv1) cudaEventDestroy(d->ev_conv1);
   delete d;
 }
 
@@ -499,12 +506,31 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     if (launch_cond(lc.wf32, lc.bias, g, plan->cb, B, lc.c_out, lc.c_in, st)) return 1;
     ++launches;
   }
+  if (d->profile) {
+    if (!d->ev_conv0) {
+      VD_CUDA(cudaEventCreate(&d->ev_conv0));
+      VD_CUDA(cudaEventCreate(&d->ev_conv1));
+    }
+    if (d->ev_pending) {  // fold the previous decode's interval in before re-recording
+      float ms = 0.f;
+      VD_CUDA(cudaEventSynchronize(d->ev_conv1));
+      VD_CUDA(cudaEventElapsedTime(&ms, d->ev_conv0, d->ev_conv1));
+      d->prof_conv_ms += ms;
+      d->ev_pending = false;
+    }
+    VD_CUDA(cudaEventRecord(d->ev_conv0, st));
+  }
   for (size_t i = 0; i < plan->steps.size(); ++i) {
     Step s = plan->steps[i];  // copy: per-call epilogue fields, re-entrant across threads
     if (i == 0) s.ep.bias_b = g ? plan->cb : nullptr;
     if (run_conv(d, s, st)) return 1;
     ++launches;
     if (s.dbg_dst) VD_CUDA(cudaMemcpyAsync(s.dbg_dst, s.ep.out, s.dbg_bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  if (d->profile) {
+    VD_CUDA(cudaEventRecord(d->ev_conv1, st));
+    d->ev_pending = true;
+    d->prof_conv_launches += (long)plan->steps.size();
   }
   if (launch_conv_post(plan->x_final, d->layers[d->l_post].wf32, out, B, plan->L_final, plan->C_final, st)) return 1;
   ++launches;
@@ -552,7 +578,28 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   if (!strcmp(key, "impl")) { VD_CHECK(value == 0 || value == 1, "impl: 0 (tcgen05) or 1 (simt)"); d->impl = value; }
   else if (!strcmp(key, "desc_mode")) d->desc_mode = value;
   else if (!strcmp(key, "debug_keep")) d->debug_keep = value ? 1 : 0;
+  else if (!strcmp(key, "profile")) {
+    d->profile = value ? 1 : 0;
+    d->prof_conv_ms = 0.0;
+    d->prof_conv_launches = 0;
+    d->ev_pending = false;
+  }
   else { set_error(std::string("unknown option ") + key); return 1; }
+  return 0;
+}
+
+int vitsdec_profile_read(vitsdec_decoder* d, double* conv_ms, int64_t* conv_launches) {
+  VD_CHECK(d && conv_ms && conv_launches, "vitsdec_profile_read: null argument");
+  DeviceGuard guard(d->device);
+  if (d->ev_pending) {
+    float ms = 0.f;
+    VD_CUDA(cudaEventSynchronize(d->ev_conv1));
+    VD_CUDA(cudaEventElapsedTime(&ms, d->ev_conv0, d->ev_conv1));
+    d->prof_conv_ms += ms;
+    d->ev_pending = false;
+  }
+  *conv_ms = d->prof_conv_ms;
+  *conv_launches = d->prof_conv_launches;
   return 0;
 }
 

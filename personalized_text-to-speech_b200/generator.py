@@ -241,6 +241,13 @@ class Generator(nn.Module):
         p = next(ref_generator.parameters())
         return new.to(p.device).train(ref_generator.training)
 
+    def profile_read(self):
+        """(accumulated conv-kernel device ms, conv launches) since set_option('profile', 1)."""
+        import ctypes
+        ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+        _capi.check(_capi.lib().vitsdec_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(n)), "profile_read")
+        return ms.value, n.value
+
     def last_launch_count(self):
         return 0 if self._handle is None else _capi.lib().vitsdec_last_launch_count(self._handle)
 

@@ -1,0 +1,82 @@
+"""CPU: the C-ABI library loads, exports every symbol include/vitsdec.h declares, and fails loudly without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+import vitsdec
+from vitsdec import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vitsdec.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"VITSDEC_API\s+[\w\s\*]+?\b(vitsdec_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.lib()
+    names = declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), "libvitsdec.so does not export %s" % n
+    # and the ctypes prototypes cover the whole header (no silently unbound entry point)
+    assert sorted(_capi.SIGNATURES) == names
+    assert lib.vitsdec_abi_version() == 1
+
+
+def test_hparams_struct_layout_matches_header():
+    prog = '#include <stdio.h>\n#include "vitsdec.h"\nint main(){printf("%zu %zu %zu", sizeof(vitsdec_hparams),' \
+           ' __builtin_offsetof(vitsdec_hparams, num_upsamples), __builtin_offsetof(vitsdec_hparams, gin_channels));}'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        size, off_nu, off_gin = map(int, subprocess.check_output([exe]).split())
+    assert size == ctypes.sizeof(_capi.HParams)
+    assert off_nu == _capi.HParams.num_upsamples.offset
+    assert off_gin == _capi.HParams.gin_channels.offset
+
+
+def test_header_is_plain_c():
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write('#include "vitsdec.h"\nint main(void){return VITSDEC_ABI_VERSION - 1;}\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o",
+                               os.path.join(d, "t")])
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    lib = _capi.lib()
+    hp = _capi.make_hparams(192, "1", [3, 7, 11], [[1, 3, 5]] * 3, [8, 8, 2, 2], 512, [16, 16, 4, 4], gin_channels=256)
+    h = ctypes.c_void_p()
+    rc = lib.vitsdec_create(ctypes.byref(hp), 0, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert lib.vitsdec_last_error()  # a message, not a silent fallback
+
+
+def test_make_hparams_rejects_bad_lists():
+    with pytest.raises(ValueError):
+        _capi.make_hparams(192, "1", [3, 7], [[1, 3, 5]] * 3, [8, 8], 512, [16, 16])
+    hp = _capi.make_hparams(192, "2", [3, 7], [[1, 3], [1, 2]], [8, 8], 512, [16, 16])
+    assert hp.resblock == 2 and hp.num_kernels == 2 and hp.num_dilations[1] == 2
+    assert hp.resblock_dilation_sizes[1][1] == 2 and hp.gin_channels == 0
+
+
+def test_no_oracle_import_in_product():
+    """The product package must never route through the CPU oracle (it would void the parity claim)."""
+    pkg = os.path.join(ROOT, "personalized_text-to-speech_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f

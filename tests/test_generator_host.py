@@ -1,0 +1,138 @@
+"""CPU: host-side mirror of the reference interface (state_dict contract, error behaviour, launcher, helpers)."""
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import vitsdec
+from vitsdec import Generator
+
+chunked = __import__("importlib").import_module("personalized_text-to-speech_b200.chunked")
+
+
+def make(hp=oracle.FINETUNE_SPEAKER):
+    args, kw = hp.ctor_args()
+    return Generator(*args, **kw)
+
+
+def test_state_dict_keys_match_reference_tree():
+    G = make()
+    ref = oracle.state_dict_keys(oracle.FINETUNE_SPEAKER)
+    sd = G.state_dict()
+    assert list(sd.keys()) == [k for k, _ in ref]          # 233 keys, same order (utils.py:155-177 walks them)
+    assert all(tuple(sd[k].shape) == tuple(s) for k, s in ref)
+    assert len(sd) == 233
+
+
+def test_strict_load_of_reference_state_dict_and_folded_form():
+    hp = oracle.TINY
+    G = make(hp)
+    sd = oracle.synth_state_dict(hp, 3)
+    G.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    for k, v in G.state_dict().items():
+        assert np.array_equal(v.numpy(), sd[k])
+    # the 157-key style (remove_weight_norm) form is accepted too and reproduces the same effective weights
+    folded = oracle.weights.fold_state_dict(sd)
+    G2 = make(hp)
+    G2.load_state_dict({k: torch.from_numpy(v) for k, v in folded.items()}, strict=True)
+    w = torch._weight_norm(G2.ups[0].weight_v, G2.ups[0].weight_g, 0).detach().numpy()
+    assert np.allclose(w, folded["ups.0.weight"], rtol=1e-5, atol=1e-7)
+
+
+def test_remove_weight_norm_changes_keys_like_reference(capsys):
+    G = make(oracle.TINY)
+    n_wn = len(G.state_dict())
+    G.remove_weight_norm()
+    assert "Removing weight norm" in capsys.readouterr().out      # models.py:292 prints this
+    keys = list(G.state_dict().keys())
+    assert len(keys) == len(oracle.state_dict_keys(oracle.TINY, weight_norm=False)) < n_wn
+    assert not any(k.endswith("weight_g") for k in keys)
+
+
+def test_resblock2_tree():
+    G = make(oracle.TINY_RB2)
+    assert [k for k, _ in oracle.state_dict_keys(oracle.TINY_RB2)] == list(G.state_dict().keys())
+    assert not hasattr(G, "cond")                                   # gin_channels == 0, models.py:267
+
+
+def test_forward_errors_are_loud_not_fallbacks():
+    G = make(oracle.TINY).eval()
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            G(torch.zeros(1, 64, 4))
+        with pytest.raises(RuntimeError, match="expected x of shape"):
+            G(torch.zeros(1, 63, 4))
+
+
+def test_patch_reference_replaces_generator_symbol():
+    fake = types.ModuleType("models")
+    fake.Generator = object
+    sys.modules["models"] = fake
+    try:
+        done = vitsdec.patch_reference(("models",))
+        assert done == ["models"] and fake.Generator is Generator
+        vitsdec.unpatch_reference()
+        assert fake.Generator is object
+    finally:
+        del sys.modules["models"]
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 16, 256):
+        for world in (1, 2, 3, 8):
+            spans = [vitsdec.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_chunk_plan_covers_once_and_clips_halos():
+    for T, c, h in ((5168, 512, 12), (100, 32, 12), (33, 32, 12), (40, 10, 3)):
+        plan = chunked.chunk_plan(T, c, h)
+        covered = []
+        for lo, hi, klo, khi in plan:
+            assert 0 <= lo < hi <= T and 0 <= klo < khi <= hi - lo
+            covered += list(range(lo + klo, lo + khi))
+            assert lo == max(0, lo + klo - h) and hi == min(T, lo + khi + h)
+        assert covered == list(range(T))
+
+
+def test_decode_chunked_with_oracle_decode_fn():
+    hp = oracle.TINY
+    sd = oracle.synth_state_dict(hp, 5, gain=2.0)
+    z = torch.from_numpy(np.random.RandomState(2).standard_normal((1, hp.initial_channel, 50)).astype(np.float32))
+
+    def fn(zz, gg):
+        return torch.from_numpy(oracle.generator_forward_np(hp, sd, zz.numpy(), None, dtype=np.float64)).float()
+
+    full = fn(z, None)
+    got = vitsdec.decode_chunked(fn, z, None, chunk_frames=10, halo=12, hop=hp.hop)
+    assert got.shape == full.shape and float((got - full).abs().max()) < 1e-6
+
+
+def test_polyphase_transposed_conv_derivation():
+    """The packing rule used by pack_convT_kernel (csrc/pack.cu): output sample s*i + r reads input rows i + off with
+    kernel index j = r + p - s*off.  Restated in numpy and checked against the oracle's conv_transpose1d."""
+    from oracle.generator_np import conv_transpose1d
+    rs = np.random.RandomState(0)
+    for (ci, co, k, s) in ((6, 4, 16, 8), (5, 3, 4, 2), (4, 2, 8, 4), (3, 2, 6, 2), (3, 2, 3, 1)):
+        p = (k - s) // 2
+        L = 11
+        x = rs.standard_normal((1, ci, L))
+        w = rs.standard_normal((ci, co, k))
+        ref = conv_transpose1d(x, w, None, stride=s, padding=p)
+        off_min = -((k - 1 - p) // s)
+        off_max = (s - 1 + p) // s
+        y = np.zeros((1, co, L * s))
+        for off in range(off_min, off_max + 1):
+            for r in range(s):
+                j = r + p - s * off
+                if 0 <= j < k:
+                    for i in range(L):
+                        if 0 <= i + off < L:
+                            y[0, :, s * i + r] += w[:, :, j].T @ x[0, :, i + off]
+        assert ref.shape == y.shape and np.abs(ref - y).max() < 1e-12

@@ -1,0 +1,97 @@
+"""GPU: per-kernel parity of the fused convolution primitives against torch functional ops on bf16-rounded
+operands (SURVEY.md section 4 'per-kernel').  Calls go through the C ABI (vitsdec_op_*)."""
+import importlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ops = importlib.import_module("personalized_text-to-speech_b200.ops")
+
+# bf16 output rounding is 2^-9 relative; operands are identical bf16 values on both sides
+REL_TOL = 1e-2
+
+
+def ref_conv(x, w, bias, dilation, res, res_gain, out_slope):
+    k = w.shape[2]
+    y = F.conv1d(x.float().transpose(1, 2), w.bfloat16().float(), bias, dilation=dilation,
+                 padding=(k - 1) // 2 * dilation)
+    if res is not None:
+        r = res.float().transpose(1, 2)
+        y = y + torch.where(r >= 0, r, r * res_gain)
+    return torch.where(y >= 0, y, y * out_slope).transpose(1, 2)
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+CASES = [
+    # B, L, c_in, c_out, k, dil, residual
+    (1, 128, 64, 32, 1, 1, False),      # plain GEMM tile, every BN instance
+    (1, 128, 64, 64, 1, 1, False),
+    (1, 256, 64, 128, 1, 1, False),
+    (1, 128, 64, 256, 1, 1, False),
+    (1, 128, 32, 32, 1, 1, False),      # 64-byte rows (SWIZZLE_64B)
+    (1, 128, 64, 64, 3, 8, False),      # tap shift = whole swizzle atoms
+    (1, 128, 64, 64, 3, 1, False),      # tap shift inside a swizzle atom
+    (2, 300, 128, 128, 7, 5, True),     # stage-1 shape, dilation 5, residual
+    (2, 1000, 256, 256, 11, 5, True),   # stage-0 shape, widest halo (50 rows)
+    (3, 777, 32, 32, 11, 3, True),      # stage-3 shape, ragged length
+    (2, 517, 64, 64, 7, 3, True),       # stage-2 shape
+    (2, 50, 192, 512, 7, 1, False),     # conv_pre shape (3 K-chunks, 2 N-tiles)
+    (1, 5, 64, 64, 7, 1, True),         # shorter than the kernel's halo
+    (1, 1, 64, 64, 11, 5, True),        # single row
+    (1, 4000, 64, 64, 11, 5, True),     # many M-tiles on one utterance
+    (5, 130, 96, 96, 3, 1, False),      # channels not a power of two (BN=32, KC=32)
+]
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_L%d_ci%d_co%d_k%d_d%d_r%d" % c)
+def test_conv1d_matches_torch(case, impl):
+    B, L, ci, co, k, d, use_res = case
+    torch.manual_seed(B * 1000 + L)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, L, ci, device=dev).bfloat16()
+    w = torch.randn(co, ci, k, device=dev) / (ci * k) ** 0.5
+    b = torch.randn(co, device=dev) * 0.1
+    res = torch.randn(B, L, co, device=dev).bfloat16() if use_res else None
+    y = ops.conv1d_cl(x, w, b, dilation=d, res=res, res_gain=10.0, out_slope=0.1, impl=impl)
+    torch.cuda.synchronize()
+    assert rel_err(y, ref_conv(x, w, b, d, res, 10.0, 0.1)) < REL_TOL
+
+
+def test_tcgen05_equals_simt_up_to_accumulation_order():
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    x = torch.randn(2, 700, 128, device=dev).bfloat16()
+    w = torch.randn(128, 128, 7, device=dev) / 30
+    b = torch.randn(128, device=dev) * 0.1
+    a = ops.conv1d_cl(x, w, b, dilation=3, out_slope=0.1, impl=0).float()
+    c = ops.conv1d_cl(x, w, b, dilation=3, out_slope=0.1, impl=1).float()
+    # identical bf16 operands, fp32 accumulation in a different order: at most one bf16 ulp apart
+    assert float(((a - c).abs() / (c.abs() + 1e-3)).max()) < 2 ** -7
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("case", [(2, 50, 64, 32, 4, 2), (1, 37, 128, 64, 4, 2), (2, 33, 512, 256, 16, 8),
+                                  (1, 130, 256, 128, 16, 8), (1, 9, 64, 32, 8, 4), (1, 1, 64, 32, 4, 2),
+                                  (2, 21, 64, 32, 6, 2)],
+                         ids=lambda c: "B%d_L%d_ci%d_co%d_k%d_s%d" % c)
+def test_conv_transpose1d_matches_torch(case, impl):
+    B, L, ci, co, k, s = case
+    torch.manual_seed(L)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, L, ci, device=dev).bfloat16()
+    w = torch.randn(ci, co, k, device=dev) / (ci * k / s) ** 0.5
+    b = torch.randn(co, device=dev) * 0.1
+    y = ops.conv_transpose1d_cl(x, w, b, stride=s, out_slope=0.1, impl=impl)
+    torch.cuda.synchronize()
+    r = F.conv_transpose1d(x.float().transpose(1, 2), w.bfloat16().float(), b, stride=s, padding=(k - s) // 2)
+    r = torch.where(r >= 0, r, r * 0.1).transpose(1, 2)
+    assert y.shape == r.shape
+    assert rel_err(y, r) < REL_TOL
