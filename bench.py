@@ -47,7 +47,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -108,7 +108,7 @@ def cpu_reference(batch, frames, steps, warmup, threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="utterances per GPU")
@@ -147,7 +147,6 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    import oracle
     import vitsdec
 
     torch.cuda.set_device(local_rank)
@@ -155,15 +154,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    hp = oracle.FINETUNE_SPEAKER  # hyper-parameters only; the oracle never decodes on this arm
-    cargs, ckw = hp.ctor_args()
+    # random-init weights of the shipped architecture (no network for checkpoints): torch default init like the
+    # reference's constructor, with weight_g perturbed so the weight-norm fold is exercised
+    cargs, ckw = vitsdec.generator_args()  # configs/finetune_speaker.json model block
+    torch.manual_seed(1234)
     G = vitsdec.Generator(*cargs, **ckw)
-    G.load_state_dict({k: torch.from_numpy(v) for k, v in oracle.synth_state_dict(hp, 0, gain=2.0).items()})
+    with torch.no_grad():
+        for name, p in G.named_parameters():
+            if name.endswith("weight_g"):
+                p.mul_(torch.empty_like(p).uniform_(0.5, 1.5))
     G = G.to(dev).eval()
     G.assume_frozen = True
     rs = np.random.RandomState(1 + rank)
-    z_host = torch.from_numpy(rs.standard_normal((B, hp.initial_channel, frames)).astype(np.float32)).pin_memory()
-    g_host = torch.from_numpy(rs.standard_normal((B, hp.gin_channels, 1)).astype(np.float32)).pin_memory()
+    z_host = torch.from_numpy(rs.standard_normal((B, cargs[0], frames)).astype(np.float32)).pin_memory()
+    g_host = torch.from_numpy(rs.standard_normal((B, ckw["gin_channels"], 1)).astype(np.float32)).pin_memory()
     z = z_host.to(dev)
     g = g_host.to(dev)
     out_host = torch.empty((B, 1, frames * HOP), dtype=torch.float32).pin_memory()

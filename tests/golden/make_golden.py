@@ -33,22 +33,7 @@ import models_infer  # noqa: E402  (the reference)
 import oracle  # noqa: E402
 from oracle.generator_torch import generator_forward_torch, to_torch_state_dict  # noqa: E402
 
-CASES = [
-    # name, hparams, seed, B, T, use_g
-    ("tiny_b2_t9", oracle.TINY, 11, 2, 9, True),
-    ("tiny_b1_t1", oracle.TINY, 12, 1, 1, True),
-    ("tiny_rb2_b2_t13", oracle.TINY_RB2, 13, 2, 13, False),
-    ("full_b2_t32", oracle.FINETUNE_SPEAKER, 21, 2, 32, True),
-    ("full_b1_t7_nog", oracle.FINETUNE_SPEAKER, 22, 1, 7, False),
-]
-
-
-def weight_checksum(sd):
-    acc = 0.0
-    for k in sorted(sd):
-        v = sd[k].astype(np.float64).ravel()
-        acc += float((v * np.cos(np.arange(v.size) % 97)).sum())
-    return np.float64(acc)
+from tests.golden.cases import CASES, weight_checksum  # noqa: E402
 
 
 def main():

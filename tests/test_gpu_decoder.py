@@ -16,7 +16,7 @@ import torch
 import oracle
 import vitsdec
 from oracle.generator_torch import generator_forward_torch, to_torch_state_dict
-from tests.golden.make_golden import CASES
+from tests.golden.cases import CASES
 
 pytestmark = pytest.mark.gpu
 

@@ -9,7 +9,7 @@ import torch
 import oracle
 from oracle import generator_np as gnp
 from oracle.generator_torch import generator_forward_torch, to_torch_state_dict
-from tests.golden.make_golden import CASES, weight_checksum
+from tests.golden.cases import CASES, weight_checksum
 
 
 def _load(golden_dir, name):

@@ -15,5 +15,7 @@ shard_range = _pkg.shard_range
 decode_sharded = _pkg.decode_sharded
 decode_chunked = _pkg.decode_chunked
 build = _pkg.build
+generator_args = _pkg.generator_args
+generator_args_from_config = _pkg.generator_args_from_config
 _capi = _pkg._capi
 __all__ = list(_pkg.__all__)
