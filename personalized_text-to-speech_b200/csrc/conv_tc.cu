@@ -20,15 +20,16 @@
 
 namespace vd {
 
-constexpr int kNA = 2;         // activation-chunk stages
+constexpr int kMaxNA = 4;      // activation-chunk stages (runtime count <= this)
+constexpr int kMaxNB = 8;      // weight-tile stages when weights are streamed
 constexpr int kTcThreads = 192;
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
 
 template <int BN, int KC>
 struct TcCfg {
   static constexpr int NACC = BN >= 256 ? 1 : 2;
   static constexpr int ROWB = KC * 2;
   static constexpr int B_STAGE = BN * ROWB;
-  static constexpr int NB = 4;
   static constexpr int ACC_COLS = NACC * BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
@@ -112,22 +113,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ ConvTcParams p) {
   using C = TcCfg<BN, KC>;
-  constexpr int NACC = C::NACC, ROWB = C::ROWB, B_STAGE = C::B_STAGE, NB = C::NB, ACC_COLS = C::ACC_COLS;
+  constexpr int NACC = C::NACC, ROWB = C::ROWB, B_STAGE = C::B_STAGE, ACC_COLS = C::ACC_COLS;
   constexpr int BM = 128 * NACC;
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern is a function of the shared-memory address bits
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smemA = smem;
-  uint8_t* smemB = smem + kNA * p.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + NB * B_STAGE);
+  const int NA = p.na_stages, NB = p.nb_stages;
+  uint8_t* smemB = smem + NA * p.a_stage_bytes;   // streamed ring, or the whole [tap][kc] weight set (stationary)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + p.b_region_bytes);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + kNA;
-  uint64_t* b_full = a_empty + kNA;
-  uint64_t* b_empty = b_full + NB;
-  uint64_t* acc_full = b_empty + NB;
+  uint64_t* a_empty = a_full + kMaxNA;
+  uint64_t* b_full = a_empty + kMaxNA;
+  uint64_t* b_empty = b_full + kMaxNB;
+  uint64_t* acc_full = b_empty + kMaxNB;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,9 +138,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
-    for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < kMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kMaxNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(w_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -155,6 +159,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t ita = 0, itb = 0;
+      if (p.stationary) {
+        // all taps x K-chunks of this layer's weights stay resident: one bulk load per CTA, no per-tap handshake
+        mbar_expect_tx(w_full, p.g.ntaps * nkc * B_STAGE);
+        for (int tap = 0; tap < p.g.ntaps; ++tap)
+          for (int kc = 0; kc < nkc; ++kc)
+            tma_load_3d(&tmW, w_full, smemB + (tap * nkc + kc) * B_STAGE, kc * KC, 0, tap);
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         const int mb = tile / p.n_tiles;
@@ -162,13 +173,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int t0 = (mb % p.m_tiles) * BM;
         const int n0 = nt * BN;
         for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t sa = ita % kNA, pa = (ita / kNA) & 1;
+          const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_expect_tx(&a_full[sa], p.a_stage_bytes);
           for (int bx = 0; bx < p.nboxes; ++bx)
             tma_load_3d(&tmA, &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, kc * KC,
                         t0 + p.halo_lo + bx * 64, b);
           ++ita;
+          if (p.stationary) continue;
           for (int tap = 0; tap < p.g.ntaps; ++tap) {
             if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0) continue;
             const uint32_t sb = itb % NB, pb = (itb / NB) & 1;
@@ -186,6 +198,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = umma_idesc_f16(BN, false);
       const uint32_t a_addr0 = smem_u32(smemA), b_addr0 = smem_u32(smemB);
       uint32_t ita = 0, itb = 0, itt = 0;
+      if (p.stationary) {
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
         const int n0 = (tile % p.n_tiles) * BN;
         const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
@@ -194,15 +210,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_base = tmem_base + as * ACC_COLS;
         bool first = true;
         for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t sa = ita % kNA, pa = (ita / kNA) & 1;
+          const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
           mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
           for (int tap = 0; tap < p.g.ntaps; ++tap) {
             if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0) continue;
-            const uint32_t sb = itb % NB, pb = (itb / NB) & 1;
-            mbar_wait(&b_full[sb], pb);
-            tc_fence_after();
+            uint32_t sb = 0;
+            if (!p.stationary) {
+              sb = itb % NB;
+              mbar_wait(&b_full[sb], (itb / NB) & 1);
+              tc_fence_after();
+            }
             const uint32_t a_tap = a_addr0 + sa * p.a_stage_bytes + (p.g.tap_off[tap] - p.halo_lo) * ROWB;
-            const uint32_t b_tap = b_addr0 + sb * B_STAGE;
+            const uint32_t b_tap = b_addr0 + (p.stationary ? (tap * nkc + kc) : (int)sb) * B_STAGE;
 #pragma unroll
             for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll
@@ -214,8 +234,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             first = false;
-            umma_commit(&b_empty[sb]);  // weights stage free once these MMAs retire
-            ++itb;
+            if (!p.stationary) {
+              umma_commit(&b_empty[sb]);  // weights stage free once these MMAs retire
+              ++itb;
+            }
           }
           umma_commit(&a_empty[sa]);
           ++ita;
@@ -319,6 +341,8 @@ static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
 
 int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, int num_sms,
                  int desc_mode) {
+  const bool force_streaming = (desc_mode & 2) != 0;  // test knob: exercise the streamed-weights path everywhere
+  desc_mode &= 1;
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
   VD_CHECK(g.n_total % 32 == 0, "conv_tc: output columns must be a multiple of 32");
   VD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, "conv_tc: 1..16 taps supported");
@@ -343,8 +367,22 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, cons
   pl->bn = bn;
   pl->kc = kc;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  pl->smem = 1024 + (size_t)kNA * p.a_stage_bytes + 4 * (size_t)bn * kc * 2 + 256;
-  VD_CHECK(pl->smem <= 227 * 1024, "conv_tc: dilation halo too large for shared memory");
+  const int b_stage = bn * kc * 2;
+  const int w_all = g.ntaps * (g.c_in / kc) * b_stage;
+  // weights stay resident in shared memory when the whole layer fits next to >= 2 activation stages
+  p.stationary = (p.n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= kSmemBudget) ? 1 : 0;
+  if (force_streaming) p.stationary = 0;
+  if (p.stationary) {
+    p.b_region_bytes = w_all;
+    p.nb_stages = 0;
+    p.na_stages = std::min(kMaxNA, (kSmemBudget - w_all) / p.a_stage_bytes);
+  } else {
+    p.na_stages = 2;
+    VD_CHECK(2 * p.a_stage_bytes + 2 * b_stage <= kSmemBudget, "conv_tc: dilation halo too large for shared memory");
+    p.nb_stages = std::min(kMaxNB, (kSmemBudget - 2 * p.a_stage_bytes) / b_stage);
+    p.b_region_bytes = p.nb_stages * b_stage;
+  }
+  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512;
   if (encode_3d(&pl->tmA, x, g.c_in, g.L, g.B, kc, 64)) return 1;
   if (encode_3d(&pl->tmW, w, g.c_in, g.n_total, g.ntaps, kc, bn)) return 1;
   return 0;

@@ -13,6 +13,10 @@ struct ConvTcParams {
   int halo_lo;        // min tap offset
   int nboxes;         // 64-row TMA boxes per A stage
   int a_stage_bytes;  // nboxes * 64 * KC * 2
+  int na_stages;      // activation stages in flight
+  int nb_stages;      // streamed weight stages (0 when stationary)
+  int b_region_bytes; // bytes of the weight region (ring or resident set)
+  int stationary;     // 1: the layer's whole weight set stays resident in shared memory
   int m_tiles;        // per utterance
   int n_tiles;
   int total_tiles;

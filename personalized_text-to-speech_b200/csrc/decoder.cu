@@ -470,7 +470,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   VD_CHECK(d && z && out && ws, "vitsdec_decode: null argument");
   VD_CHECK(B > 0 && T > 0, "vitsdec_decode: empty batch or zero frames");
   VD_CHECK(B <= 65535, "vitsdec_decode: batch too large");
-  VD_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+  VD_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
   VD_CHECK(g == nullptr || d->l_cond >= 0, "g given but the decoder was built with gin_channels=0 (models.py:267)");
   for (const Layer& l : d->layers)
     VD_CHECK(l.loaded, "vitsdec_decode: layer " + l.name + " has no weights loaded");

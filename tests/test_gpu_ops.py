@@ -95,3 +95,16 @@ def test_conv_transpose1d_matches_torch(case, impl):
     r = torch.where(r >= 0, r, r * 0.1).transpose(1, 2)
     assert y.shape == r.shape
     assert rel_err(y, r) < REL_TOL
+
+
+def test_streamed_and_resident_weight_paths_agree_bitwise():
+    """desc_mode bit 1 forces the streamed-weights pipeline where the planner would keep weights resident."""
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    for (ci, co, k, d) in ((32, 32, 11, 5), (64, 64, 7, 3), (128, 128, 3, 1)):
+        x = torch.randn(2, 1500, ci, device=dev).bfloat16()
+        w = torch.randn(co, ci, k, device=dev) / (ci * k) ** 0.5
+        b = torch.randn(co, device=dev) * 0.1
+        a = ops.conv1d_cl(x, w, b, dilation=d, out_slope=0.1, impl=0, desc_mode=0)
+        c = ops.conv1d_cl(x, w, b, dilation=d, out_slope=0.1, impl=0, desc_mode=2)
+        assert torch.equal(a, c)
