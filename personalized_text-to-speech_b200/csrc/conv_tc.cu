@@ -20,7 +20,7 @@
 
 namespace vd {
 
-constexpr int kMaxNA = 4;      // activation-chunk stages (runtime count <= this)
+constexpr int kMaxNA = 8;      // activation-chunk stages (runtime count <= this)
 constexpr int kMaxNB = 8;      // weight-tile stages when weights are streamed
 constexpr int kTcThreads = 192;
 constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
@@ -31,6 +31,7 @@ struct TcCfg {
   static constexpr int ROWB = KC * 2;
   static constexpr int B_STAGE = BN * ROWB;
   static constexpr int ACC_COLS = NACC * BN;
+  static constexpr int RBOXC = BN < 64 ? BN : 64;   // residual prefetch box: RBOXC columns x 64 rows
   static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
@@ -111,7 +112,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvEpilogue& ep, int b, lo
 template <int BN, int KC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ ConvTcParams p) {
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvTcParams p) {
   using C = TcCfg<BN, KC>;
   constexpr int NACC = C::NACC, ROWB = C::ROWB, B_STAGE = C::B_STAGE, ACC_COLS = C::ACC_COLS;
   constexpr int BM = 128 * NACC;
@@ -172,6 +173,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int b = mb / p.m_tiles;
         const int t0 = (mb % p.m_tiles) * BM;
         const int n0 = nt * BN;
+        if (p.res_prefetch) {
+          // the residual tile this tile's epilogue will read: start it towards L2 now (the producer runs NA
+          // activation stages ahead of the MMAs, so this is early enough to hide the DRAM latency)
+          for (int r = 0; r < BM; r += 64)
+            for (int c = 0; c < BN; c += C::RBOXC) tma_prefetch_3d(&tmR, n0 + c, t0 + r, b);
+        }
         for (int kc = 0; kc < nkc; ++kc) {
           const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
           mbar_wait(&a_empty[sa], pa ^ 1);
@@ -193,58 +200,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BN, false);
-      const uint32_t a_addr0 = smem_u32(smemA), b_addr0 = smem_u32(smemB);
-      uint32_t ita = 0, itb = 0, itt = 0;
-      if (p.stationary) {
-        mbar_wait(w_full, 0);
+    // ------------------------------------------------------------ MMA issuer
+    // The whole warp runs this (warp-uniform) control flow; only the elected lane issues tcgen05.mma / commit.
+    // Descriptors are (lo, hi) pairs: hi is a constant, lo advances by precomputed 16-byte-unit deltas, so the
+    // issue loop is a handful of uniform-register adds per MMA.
+    constexpr uint32_t idesc = umma_idesc_f16(BN, false);
+    constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
+    const uint32_t leader = elect_one();
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), b_lo0 = umma_desc_lo(smem_u32(smemB));
+    const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+    uint32_t ita = 0, itb = 0, itt = 0;
+    if (p.stationary) {
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
+      const int n0 = (tile % p.n_tiles) * BN;
+      uint32_t tapmask = 0;
+      for (int tap = 0; tap < p.g.ntaps; ++tap)
+        if (p.g.tap_nlo[tap] < n0 + BN && p.g.tap_nhi[tap] > n0) tapmask |= 1u << tap;
+      const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
+      mbar_wait(&acc_empty[as], pacc ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + as * ACC_COLS;
+      uint32_t accum = 0;  // 0 for the first MMA of each accumulator of this tile
+      for (int kc = 0; kc < nkc; ++kc) {
+        const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
+        mbar_wait(&a_full[sa], pa);
         tc_fence_after();
-      }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
-        const int n0 = (tile % p.n_tiles) * BN;
-        const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
-        mbar_wait(&acc_empty[as], pacc ^ 1);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + as * ACC_COLS;
-        bool first = true;
-        for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
-          mbar_wait(&a_full[sa], pa);
-          tc_fence_after();
-          for (int tap = 0; tap < p.g.ntaps; ++tap) {
-            if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0) continue;
-            uint32_t sb = 0;
-            if (!p.stationary) {
-              sb = itb % NB;
-              mbar_wait(&b_full[sb], (itb / NB) & 1);
-              tc_fence_after();
-            }
-            const uint32_t a_tap = a_addr0 + sa * p.a_stage_bytes + (p.g.tap_off[tap] - p.halo_lo) * ROWB;
-            const uint32_t b_tap = b_addr0 + (p.stationary ? (tap * nkc + kc) : (int)sb) * B_STAGE;
+        const uint32_t a_lo_stage = a_lo0 + sa * a_stage16;
+        for (int tap = 0; tap < p.g.ntaps; ++tap) {
+          if (!((tapmask >> tap) & 1u)) continue;
+          uint32_t sb = 0;
+          uint32_t b_lo;
+          if (p.stationary) {
+            b_lo = b_lo0 + (uint32_t)(tap * nkc + kc) * (B_STAGE >> 4);
+          } else {
+            sb = itb % NB;
+            mbar_wait(&b_full[sb], (itb / NB) & 1);
+            tc_fence_after();
+            b_lo = b_lo0 + sb * (B_STAGE >> 4);
+          }
+          const uint32_t a_lo = a_lo_stage + p.tap_delta16[tap];
 #pragma unroll
-            for (int acc = 0; acc < NACC; ++acc) {
+          for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                const uint32_t aaddr = a_tap + acc * 128 * ROWB + k * 32;
-                const uint32_t boff = p.desc_mode == 1 ? ((aaddr >> 7) & 7u) : 0u;
-                umma_f16(d_base + acc * BN, umma_desc_kmajor(aaddr, ROWB, boff),
-                         umma_desc_kmajor(b_tap + k * 32, ROWB, 0), idesc, (first && k == 0) ? 0u : 1u);
-              }
-            }
-            first = false;
-            if (!p.stationary) {
-              umma_commit(&b_empty[sb]);  // weights stage free once these MMAs retire
-              ++itb;
+            for (int k = 0; k < KC / 16; ++k) {
+              umma_f16_lohi(d_base + acc * BN, a_lo + ((acc * 128 * ROWB + k * 32) >> 4), desc_hi, b_lo + ((k * 32) >> 4),
+                            desc_hi, idesc, k == 0 ? accum : 1u, leader);
             }
           }
-          umma_commit(&a_empty[sa]);
-          ++ita;
+          accum = 1;
+          if (!p.stationary) {
+            if (leader) umma_commit(&b_empty[sb]);  // weights stage free once these MMAs retire
+            ++itb;
+          }
         }
-        umma_commit(&acc_full[as]);
+        if (leader) umma_commit(&a_empty[sa]);
+        ++ita;
       }
+      if (leader) umma_commit(&acc_full[as]);
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
     const int q = warp & 3;
@@ -305,15 +322,16 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 tensor [d2][d1][d0] (d0 contiguous), box {b0, b1, 1}, swizzle span = b0*2 bytes
 static int encode_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
-                     uint32_t b1) {
+                     uint32_t b1, bool swizzle = true) {
   EncodeTiledFn fn = get_encode_fn();
   VD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUtensorMapSwizzle sw = b0 * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                        : (b0 * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMapSwizzle sw = !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                          : b0 * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                          : (b0 * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -334,7 +352,7 @@ static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
     VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KC><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
+  conv_tc_kernel<BN, KC><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.tmR, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -364,6 +382,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, cons
   p.n_tiles = g.n_total / bn;
   p.total_tiles = g.B * p.m_tiles * p.n_tiles;
   p.desc_mode = desc_mode;
+  for (int i = 0; i < g.ntaps; ++i) p.tap_delta16[i] = (uint32_t)((g.tap_off[i] - lo) * kc * 2) >> 4;
   pl->bn = bn;
   pl->kc = kc;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
@@ -376,6 +395,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, cons
     p.b_region_bytes = w_all;
     p.nb_stages = 0;
     p.na_stages = std::min(kMaxNA, (kSmemBudget - w_all) / p.a_stage_bytes);
+    p.na_stages = std::min(p.na_stages, std::max(2, (96 * 1024) / p.a_stage_bytes));  // ~96 KB in flight is plenty
   } else {
     p.na_stages = 2;
     VD_CHECK(2 * p.a_stage_bytes + 2 * b_stage <= kSmemBudget, "conv_tc: dilation halo too large for shared memory");
@@ -385,11 +405,23 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, cons
   pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512;
   if (encode_3d(&pl->tmA, x, g.c_in, g.L, g.B, kc, 64)) return 1;
   if (encode_3d(&pl->tmW, w, g.c_in, g.n_total, g.ntaps, kc, bn)) return 1;
+  pl->tmR = pl->tmA;  // placeholder until a residual is bound
+  pl->res_bound = nullptr;
+  return 0;
+}
+
+int bind_residual_tc(ConvTcPlan& pl, const __nv_bfloat16* res) {
+  if (res != nullptr && pl.res_bound != res) {
+    if (encode_3d(&pl.tmR, res, pl.p.g.n_total, pl.p.g.L, pl.p.g.B, pl.bn < 64 ? pl.bn : 64, 64, false)) return 1;
+    pl.res_bound = res;
+  }
   return 0;
 }
 
 int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) {
   pl.p.ep = ep;
+  if (bind_residual_tc(pl, ep.res)) return 1;  // no-op when the plan was built with this residual
+  pl.p.res_prefetch = ep.res != nullptr ? 1 : 0;
   switch (pl.bn * 100 + pl.kc) {
     case 25664: return launch_inst<256, 64>(pl, stream);
     case 12864: return launch_inst<128, 64>(pl, stream);

@@ -20,11 +20,14 @@ struct ConvTcParams {
   int m_tiles;        // per utterance
   int n_tiles;
   int total_tiles;
+  uint32_t tap_delta16[kMaxTaps];  // (tap_off - halo_lo) * row_bytes >> 4: descriptor start-address delta per tap
+  int res_prefetch;   // 1: the producer prefetches the residual tile (tmR) into L2
   int desc_mode;      // debug knob for the A descriptor base-offset field (0 = none)
 };
 
 struct ConvTcPlan {
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmR;
+  const void* res_bound;
   ConvTcParams p;
   int bn, kc;
   int grid;
@@ -34,6 +37,7 @@ struct ConvTcPlan {
 // Encodes the TMA descriptors for activations `x` [B][L][c_in] and packed weights `w` [ntaps][n_total][c_in].
 int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, int num_sms,
                  int desc_mode);
+int bind_residual_tc(ConvTcPlan& pl, const __nv_bfloat16* res);
 int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream);
 int launch_conv_simt(const ConvGeom& g, const ConvEpilogue& ep, const __nv_bfloat16* x, const __nv_bfloat16* w,
                      cudaStream_t stream);

@@ -238,6 +238,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     s.tc.p.g = g;
     if (d->impl == 0) {
       if (plan_conv_tc(&s.tc, g, x, ly.w, d->num_sms, d->desc_mode)) return 1;
+      if (bind_residual_tc(s.tc, ep.res)) return 1;
     }
     pl.steps.push_back(s);
     return 0;
