@@ -22,8 +22,9 @@ namespace vd {
 
 constexpr int kMaxNA = 8;      // activation-chunk stages (runtime count <= this)
 constexpr int kMaxNB = 8;      // weight-tile stages when weights are streamed
-constexpr int kTcThreads = 192;
-constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
+constexpr int kEpiWarps = 8;   // two warps per TMEM lane quadrant
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - 8192 /*bias*/;
 
 template <int BN, int KC>
 struct TcCfg {
@@ -36,13 +37,47 @@ struct TcCfg {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
-// 32 consecutive output columns of one row
-__device__ __forceinline__ void epilogue_chunk(const ConvEpilogue& ep, int b, long row, int n, int n_total,
-                                               const uint32_t (&acc)[32], bool valid) {
+// Epilogue work item = 32 consecutive output columns of one row per thread.  Global reads (residual, MRF
+// accumulator) are issued one item AHEAD of their use so their DRAM/L2 latency overlaps the TMEM load, the math
+// and the stores of the current item (the epilogue is otherwise latency-bound: one 64-byte load per thread).
+struct EpiLoads {
+  uint4 res[4];
+  float4 mrf[8];
+};
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, long idx, bool valid, EpiLoads& ld) {
+  if (!valid) return;
+  if (ep.res) {
+    const uint4* rp = reinterpret_cast<const uint4*>(ep.res + idx);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ld.res[q] = ld_stream_u4(rp + q);
+  }
+  if (ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) {
+    const float4* mp = reinterpret_cast<const float4*>(ep.mrf + idx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ld.mrf[j] = ld_stream_f4(mp + j);
+  }
+}
+
+__device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const float* sbias, int b, long idx, int n,
+                                           int n_total, const uint32_t (&acc)[32], bool valid, const EpiLoads& ld) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
+    const float4 bv = *reinterpret_cast<const float4*>(sbias + n + j);
     v[j + 0] = __uint_as_float(acc[j + 0]) + bv.x;
     v[j + 1] = __uint_as_float(acc[j + 1]) + bv.y;
     v[j + 2] = __uint_as_float(acc[j + 2]) + bv.z;
@@ -57,13 +92,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvEpilogue& ep, int b, lo
     }
   }
   if (!valid) return;
-  const long idx = row * n_total + n;
   if (ep.res) {
-    const uint4* rp = reinterpret_cast<const uint4*>(ep.res + idx);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 rv = __ldg(rp + q);
-      const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+      const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&ld.res[q]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 a = __bfloat1622float2(r2[e]);
@@ -78,8 +110,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvEpilogue& ep, int b, lo
     for (int j = 0; j < 8; ++j) {
       float4 m = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       if (ep.mrf_mode == 2) {
-        const float4 o = mp[j];
-        m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+        m.x += ld.mrf[j].x; m.y += ld.mrf[j].y; m.z += ld.mrf[j].z; m.w += ld.mrf[j].w;
       }
       mp[j] = m;
     }
@@ -87,11 +118,9 @@ __device__ __forceinline__ void epilogue_chunk(const ConvEpilogue& ep, int b, lo
   }
   if (ep.mrf_mode == 3) {
     if (ep.mrf) {
-      const float4* mp = reinterpret_cast<const float4*>(ep.mrf + idx);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 o = mp[j];
-        v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+        v[4 * j] += ld.mrf[j].x; v[4 * j + 1] += ld.mrf[j].y; v[4 * j + 2] += ld.mrf[j].z; v[4 * j + 3] += ld.mrf[j].w;
       }
     }
 #pragma unroll
@@ -132,6 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_full = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  float* sbias = reinterpret_cast<float*>(bars + 64);  // 512 bytes of barrier space, then the bias vector
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < kMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kMaxNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -149,6 +179,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.g.n_total; i += kTcThreads) sbias[i] = p.ep.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -263,35 +294,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+    // ------------------------------------------------------------ epilogue warps
+    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split a tile's items by parity.
+    constexpr int CHUNKS = BN / 32, NITEMS = NACC * CHUNKS;
     const int q = warp & 3;
-    uint32_t itt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
+    const int hsel = (warp - 2) >> 2;
+    auto coords = [&](int tile, int it, int& b, int& n, long& idx, bool& valid, uint32_t& tcol) {
       const int nt = tile % p.n_tiles;
       const int mb = tile / p.n_tiles;
-      const int b = mb / p.m_tiles;
-      const int t0 = (mb % p.m_tiles) * BM;
-      const int n0 = nt * BN;
-      const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
-      mbar_wait(&acc_full[as], pacc);
-      tc_fence_after();
-#pragma unroll 1
-      for (int acc = 0; acc < NACC; ++acc) {
-        const int t = t0 + acc * 128 + q * 32 + lane;
-        const bool valid = t < p.g.L;
-        const long row = (long)b * p.g.L + t;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + acc * BN + c0, v);
-          tmem_ld_wait();
-          epilogue_chunk(p.ep, b, row, n0 + c0, p.g.n_total, v, valid);
-        }
+      b = mb / p.m_tiles;
+      const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 32;
+      const int t = (mb % p.m_tiles) * BM + acc * 128 + q * 32 + lane;
+      n = nt * BN + c0;
+      valid = t < p.g.L;
+      idx = ((long)b * p.g.L + t) * p.g.n_total + n;
+      tcol = acc * BN + c0;
+    };
+    int tile = blockIdx.x, it = hsel < NITEMS ? hsel : NITEMS;  // NITEMS == 1: the second warp of a quadrant idles
+    uint32_t itt = 0;
+    EpiLoads ld_next;
+    int nb = 0, nn = 0; long nidx = 0; bool nvalid = false; uint32_t ncol = 0;
+    const bool active = it < NITEMS;
+    if (active && tile < p.total_tiles) {
+      coords(tile, it, nb, nn, nidx, nvalid, ncol);
+      epi_issue_loads(p.ep, nidx, nvalid, ld_next);
+    }
+    while (active && tile < p.total_tiles) {
+      const EpiLoads ld = ld_next;
+      const int b = nb, n = nn; const long idx = nidx; const bool valid = nvalid; const uint32_t tcol = ncol;
+      const bool first = it < 2, last = it + 2 >= NITEMS;
+      int ntile = tile, nit = it + 2;
+      if (nit >= NITEMS) { nit = hsel; ntile += gridDim.x; }
+      if (ntile < p.total_tiles) {
+        coords(ntile, nit, nb, nn, nidx, nvalid, ncol);
+        epi_issue_loads(p.ep, nidx, nvalid, ld_next);
       }
-      tc_fence_before();
+      const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
+      if (first) {
+        mbar_wait(&acc_full[as], pacc);
+        tc_fence_after();
+      }
+      uint32_t v[32];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + tcol, v);
+      tmem_ld_wait();
+      epi_finish(p.ep, sbias, b, idx, n, p.g.n_total, v, valid, ld);
+      if (last) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        ++itt;
+      }
+      tile = ntile; it = nit;
+    }
+    if (!active) {  // idle second warp still has to release the accumulator buffers it never reads
+      for (; tile < p.total_tiles; tile += gridDim.x, ++itt) {
+        if (lane == 0) mbar_arrive(&acc_empty[itt & 1]);
+      }
     }
   }
 
@@ -364,6 +423,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, cons
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
   VD_CHECK(g.n_total % 32 == 0, "conv_tc: output columns must be a multiple of 32");
   VD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, "conv_tc: 1..16 taps supported");
+  VD_CHECK(g.n_total <= 2048, "conv_tc: at most 2048 output columns per row");
   const int kc = (g.c_in % 64 == 0) ? 64 : 32;
   int bn = 32;
   for (int c : {256, 128, 64}) {
@@ -402,7 +462,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, cons
     p.nb_stages = std::min(kMaxNB, (kSmemBudget - 2 * p.a_stage_bytes) / b_stage);
     p.b_region_bytes = p.nb_stages * b_stage;
   }
-  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512;
+  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + (size_t)g.n_total * 4;
   if (encode_3d(&pl->tmA, x, g.c_in, g.L, g.B, kc, 64)) return 1;
   if (encode_3d(&pl->tmW, w, g.c_in, g.n_total, g.ntaps, kc, bn)) return 1;
   pl->tmR = pl->tmA;  // placeholder until a residual is bound
