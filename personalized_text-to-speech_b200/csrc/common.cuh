@@ -36,8 +36,8 @@ __device__ __forceinline__ void epilogue_scalar(const ConvEpilogue& ep, int b, l
   const long idx = row * n_total + n;  // row = b*L + t
   float v = acc + ep.bias[n];
   if (ep.bias_b) v += ep.bias_b[(long)b * n_total + n];
-  if (ep.res) {
-    float a = __bfloat162float(ep.res[idx]);
+  for (int i = 0; i < ep.nres; ++i) {
+    float a = __bfloat162float(ep.res[i][idx]);
     v += a >= 0.f ? a : a * ep.res_gain;
   }
   if (ep.mrf_mode == 1) {

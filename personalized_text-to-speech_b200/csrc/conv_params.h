@@ -11,7 +11,8 @@
 
 namespace vd {
 
-constexpr int kMaxTaps = 16;
+constexpr int kMaxTaps = 32;
+constexpr int kMaxSeg = 4;  // input tensors whose convolutions accumulate into one output (MRF fusion)
 
 struct ConvGeom {
   int B;        // utterances
@@ -22,20 +23,27 @@ struct ConvGeom {
   int tap_off[kMaxTaps];  // input-row offset of each tap
   int tap_nlo[kMaxTaps];  // tap contributes only to columns [nlo, nhi) (polyphase zero blocks)
   int tap_nhi[kMaxTaps];
+  // Segments: taps [seg_tap_end[s-1], seg_tap_end[s]) read input tensor s.  One segment for an ordinary conv; the
+  // last convs of the MRF branches (models.py:279-284) run as ONE launch with one segment per branch, so the branch
+  // sum is formed in the accumulator instead of in HBM.
+  int nseg;
+  int seg_tap_end[kMaxSeg];
 };
 
-// Epilogue:  v = acc + bias[n] (+ bias_b[b][n]) (+ unlrelu(res[b,t,n]))
+// Epilogue:  v = acc + bias[n] (+ bias_b[b][n]) (+ sum_i unlrelu(res[i][b,t,n]))
 //   mrf_mode 0: out = lrelu(v, out_slope)
 //   mrf_mode 1: mrf  = v                       (first MRF branch)          no bf16 output
 //   mrf_mode 2: mrf += v                       (middle MRF branches)       no bf16 output
-//   mrf_mode 3: out = lrelu((mrf + v) * mrf_scale, out_slope)  (last branch; mrf may be null)
+//   mrf_mode 3: out = lrelu((mrf + v) * mrf_scale, out_slope)  (last branch; mrf may be null -- it is when the
+//               branches were accumulated in TMEM by a multi-segment launch)
 // Activations are stored post-leaky-relu ("a-form"): the next conv's tensor-core operand.  The
 // residual stream x is recovered exactly (up to the bf16 rounding of a) as x = a >= 0 ? a : a * res_gain
 // with res_gain = 1/slope, which is what lets one bf16 tensor serve as both operand and residual.
 struct ConvEpilogue {
   const float* bias;           // [n_total]
   const float* bias_b;         // [B][n_total] or null
-  const __nv_bfloat16* res;    // [B][L][n_total] a-form or null
+  const __nv_bfloat16* res[kMaxSeg];  // nres residual tensors [B][L][n_total] in a-form
+  int nres;
   float res_gain;              // 1/slope of the a-form stored in `res`
   float* mrf;                  // [B][L][n_total] fp32 or null
   int mrf_mode;

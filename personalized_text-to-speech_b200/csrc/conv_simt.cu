@@ -7,7 +7,11 @@ namespace vd {
 
 constexpr int kSimtRows = 4;
 
-__global__ void __launch_bounds__(128) conv_simt_kernel(ConvGeom g, ConvEpilogue ep, const __nv_bfloat16* __restrict__ x,
+struct SimtInputs {
+  const __nv_bfloat16* x[kMaxSeg];
+};
+
+__global__ void __launch_bounds__(128) conv_simt_kernel(ConvGeom g, ConvEpilogue ep, SimtInputs in,
                                                         const __nv_bfloat16* __restrict__ w) {
   const int n = blockIdx.y * 32 + (threadIdx.x & 31);
   const int tgroup = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -17,7 +21,10 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvGeom g, ConvEpilogue
   float acc[kSimtRows];
 #pragma unroll
   for (int r = 0; r < kSimtRows; ++r) acc[r] = 0.f;
+  int seg = 0;
   for (int tap = 0; tap < g.ntaps; ++tap) {
+    while (tap >= g.seg_tap_end[seg]) ++seg;
+    const __nv_bfloat16* __restrict__ x = in.x[seg];
     if (n < g.tap_nlo[tap] || n >= g.tap_nhi[tap]) continue;
     const uint4* wr = reinterpret_cast<const uint4*>(w + ((long)tap * g.n_total + n) * g.c_in);
     for (int c8 = 0; c8 < g.c_in / 8; ++c8) {
@@ -46,11 +53,13 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvGeom g, ConvEpilogue
   }
 }
 
-int launch_conv_simt(const ConvGeom& g, const ConvEpilogue& ep, const __nv_bfloat16* x, const __nv_bfloat16* w,
+int launch_conv_simt(const ConvGeom& g, const ConvEpilogue& ep, const __nv_bfloat16* const* xs, const __nv_bfloat16* w,
                      cudaStream_t stream) {
+  SimtInputs in{};
+  for (int s = 0; s < g.nseg; ++s) in.x[s] = xs[s];
   VD_CHECK(g.c_in % 8 == 0, "conv_simt: c_in must be a multiple of 8");
   dim3 grid((g.L + 4 * kSimtRows - 1) / (4 * kSimtRows), (g.n_total + 31) / 32, g.B);
-  conv_simt_kernel<<<grid, 128, 0, stream>>>(g, ep, x, w);
+  conv_simt_kernel<<<grid, 128, 0, stream>>>(g, ep, in, w);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

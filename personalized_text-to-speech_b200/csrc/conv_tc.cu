@@ -41,9 +41,10 @@ struct TcCfg {
 // accumulator) are issued one item AHEAD of their use so their DRAM/L2 latency overlaps the TMEM load, the math
 // and the stores of the current item (the epilogue is otherwise latency-bound: one 64-byte load per thread).
 struct EpiLoads {
-  uint4 res[4];
+  uint4 res[kMaxSeg - 1][4];  // up to 3 residual tensors in flight (MRF fusion of up to 3 branches + ... see plan)
   float4 mrf[8];
 };
+constexpr int kMaxRes = kMaxSeg - 1;
 
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
   uint4 r;
@@ -60,10 +61,13 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
 
 __device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, long idx, bool valid, EpiLoads& ld) {
   if (!valid) return;
-  if (ep.res) {
-    const uint4* rp = reinterpret_cast<const uint4*>(ep.res + idx);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) ld.res[q] = ld_stream_u4(rp + q);
+  for (int i = 0; i < kMaxRes; ++i) {
+    if (i < ep.nres) {
+      const uint4* rp = reinterpret_cast<const uint4*>(ep.res[i] + idx);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ld.res[i][q] = ld_stream_u4(rp + q);
+    }
   }
   if (ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) {
     const float4* mp = reinterpret_cast<const float4*>(ep.mrf + idx);
@@ -72,9 +76,10 @@ __device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, long idx
   }
 }
 
-__device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const float* sbias, int b, long idx, int n,
-                                           int n_total, const uint32_t (&acc)[32], bool valid, const EpiLoads& ld) {
-  float v[32];
+// v = acc + bias (+ per-utterance bias) (+ residuals) (+ MRF accumulator): everything that consumes `ld`
+__device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const float* sbias, int b, int n, int n_total,
+                                               const uint32_t (&acc)[32], bool valid, const EpiLoads& ld,
+                                               float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 bv = *reinterpret_cast<const float4*>(sbias + n + j);
@@ -92,37 +97,38 @@ __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const float* 
     }
   }
   if (!valid) return;
-  if (ep.res) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&ld.res[q]);
+  for (int i = 0; i < kMaxRes; ++i) {
+    if (i < ep.nres) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 a = __bfloat1622float2(r2[e]);
-        v[q * 8 + e * 2 + 0] += a.x >= 0.f ? a.x : a.x * ep.res_gain;
-        v[q * 8 + e * 2 + 1] += a.y >= 0.f ? a.y : a.y * ep.res_gain;
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&ld.res[i][q]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __bfloat1622float2(r2[e]);
+          v[q * 8 + e * 2 + 0] += a.x >= 0.f ? a.x : a.x * ep.res_gain;
+          v[q * 8 + e * 2 + 1] += a.y >= 0.f ? a.y : a.y * ep.res_gain;
+        }
       }
     }
   }
+  if (ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] += ld.mrf[j].x; v[4 * j + 1] += ld.mrf[j].y; v[4 * j + 2] += ld.mrf[j].z; v[4 * j + 3] += ld.mrf[j].w;
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_store(const ConvEpilogue& ep, long idx, bool valid, float (&v)[32]) {
+  if (!valid) return;
   if (ep.mrf_mode == 1 || ep.mrf_mode == 2) {
     float4* mp = reinterpret_cast<float4*>(ep.mrf + idx);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 m = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      if (ep.mrf_mode == 2) {
-        m.x += ld.mrf[j].x; m.y += ld.mrf[j].y; m.z += ld.mrf[j].z; m.w += ld.mrf[j].w;
-      }
-      mp[j] = m;
-    }
+    for (int j = 0; j < 8; ++j) mp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     return;
   }
   if (ep.mrf_mode == 3) {
-    if (ep.mrf) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[4 * j] += ld.mrf[j].x; v[4 * j + 1] += ld.mrf[j].y; v[4 * j + 2] += ld.mrf[j].z; v[4 * j + 3] += ld.mrf[j].w;
-      }
-    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= ep.mrf_scale;
   }
@@ -140,8 +146,8 @@ __device__ __forceinline__ void epi_finish(const ConvEpilogue& ep, const float* 
 
 template <int BN, int KC>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ ConvTcParams p) {
+conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ ConvTcParams p) {
   using C = TcCfg<BN, KC>;
   constexpr int NACC = C::NACC, ROWB = C::ROWB, B_STAGE = C::B_STAGE, ACC_COLS = C::ACC_COLS;
   constexpr int BM = 128 * NACC;
@@ -167,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
+    for (int sg = 0; sg < p.g.nseg; ++sg) tma_prefetch_desc(&tm.a[sg]);
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < kMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kMaxNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -205,28 +211,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int t0 = (mb % p.m_tiles) * BM;
         const int n0 = nt * BN;
         if (p.res_prefetch) {
-          // the residual tile this tile's epilogue will read: start it towards L2 now (the producer runs NA
+          // the residual tiles this tile's epilogue will read: start them towards L2 now (the producer runs NA
           // activation stages ahead of the MMAs, so this is early enough to hide the DRAM latency)
-          for (int r = 0; r < BM; r += 64)
-            for (int c = 0; c < BN; c += C::RBOXC) tma_prefetch_3d(&tmR, n0 + c, t0 + r, b);
+          for (int i = 0; i < p.ep.nres; ++i)
+            for (int r = 0; r < BM; r += 64)
+              for (int c = 0; c < BN; c += C::RBOXC) tma_prefetch_3d(&tm.r[i], n0 + c, t0 + r, b);
         }
-        for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
-          mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_expect_tx(&a_full[sa], p.a_stage_bytes);
-          for (int bx = 0; bx < p.nboxes; ++bx)
-            tma_load_3d(&tmA, &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, kc * KC,
-                        t0 + p.halo_lo + bx * 64, b);
-          ++ita;
-          if (p.stationary) continue;
-          for (int tap = 0; tap < p.g.ntaps; ++tap) {
-            if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0) continue;
-            const uint32_t sb = itb % NB, pb = (itb / NB) & 1;
-            mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_expect_tx(&b_full[sb], B_STAGE);
-            tma_load_3d(&tmW, &b_full[sb], smemB + sb * B_STAGE, kc * KC, n0, tap);
-            ++itb;
+        int tap0 = 0;
+        for (int sg = 0; sg < p.g.nseg; ++sg) {
+          const int tap1 = p.g.seg_tap_end[sg];
+          const int nbx = p.seg_nboxes[sg];
+          for (int kc = 0; kc < nkc; ++kc) {
+            const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            mbar_expect_tx(&a_full[sa], nbx * 64 * ROWB);
+            for (int bx = 0; bx < nbx; ++bx)
+              tma_load_3d(&tm.a[sg], &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, kc * KC,
+                          t0 + p.seg_halo_lo[sg] + bx * 64, b);
+            ++ita;
+            if (p.stationary) continue;
+            for (int tap = tap0; tap < tap1; ++tap) {
+              if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0) continue;
+              const uint32_t sb = itb % NB, pb = (itb / NB) & 1;
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx(&b_full[sb], B_STAGE);
+              tma_load_3d(&tmW, &b_full[sb], smemB + sb * B_STAGE, kc * KC, n0, tap);
+              ++itb;
+            }
           }
+          tap0 = tap1;
         }
       }
     }
@@ -255,12 +268,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t d_base = tmem_base + as * ACC_COLS;
       uint32_t accum = 0;  // 0 for the first MMA of each accumulator of this tile
+      int tap0 = 0;
+      for (int sg = 0; sg < p.g.nseg; ++sg) {
+      const int tap1 = p.g.seg_tap_end[sg];
       for (int kc = 0; kc < nkc; ++kc) {
         const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
         const uint32_t a_lo_stage = a_lo0 + sa * a_stage16;
-        for (int tap = 0; tap < p.g.ntaps; ++tap) {
+        for (int tap = tap0; tap < tap1; ++tap) {
           if (!((tapmask >> tap) & 1u)) continue;
           uint32_t sb = 0;
           uint32_t b_lo;
@@ -290,6 +306,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (leader) umma_commit(&a_empty[sa]);
         ++ita;
       }
+      tap0 = tap1;
+      }
       if (leader) umma_commit(&acc_full[as]);
     }
     __syncwarp();
@@ -312,39 +330,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     int tile = blockIdx.x, it = hsel < NITEMS ? hsel : NITEMS;  // NITEMS == 1: the second warp of a quadrant idles
     uint32_t itt = 0;
-    EpiLoads ld_next;
-    int nb = 0, nn = 0; long nidx = 0; bool nvalid = false; uint32_t ncol = 0;
+    EpiLoads ld;
+    int b = 0, n = 0; long idx = 0; bool valid = false; uint32_t tcol = 0;
     const bool active = it < NITEMS;
     if (active && tile < p.total_tiles) {
-      coords(tile, it, nb, nn, nidx, nvalid, ncol);
-      epi_issue_loads(p.ep, nidx, nvalid, ld_next);
+      coords(tile, it, b, n, idx, valid, tcol);
+      epi_issue_loads(p.ep, idx, valid, ld);
     }
     while (active && tile < p.total_tiles) {
-      const EpiLoads ld = ld_next;
-      const int b = nb, n = nn; const long idx = nidx; const bool valid = nvalid; const uint32_t tcol = ncol;
       const bool first = it < 2, last = it + 2 >= NITEMS;
-      int ntile = tile, nit = it + 2;
-      if (nit >= NITEMS) { nit = hsel; ntile += gridDim.x; }
-      if (ntile < p.total_tiles) {
-        coords(ntile, nit, nb, nn, nidx, nvalid, ncol);
-        epi_issue_loads(p.ep, nidx, nvalid, ld_next);
-      }
       const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
       if (first) {
         mbar_wait(&acc_full[as], pacc);
         tc_fence_after();
       }
-      uint32_t v[32];
+      uint32_t acc[32];
+      float v[32];
       __syncwarp();
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + tcol, v);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + tcol, acc);
       tmem_ld_wait();
-      epi_finish(p.ep, sbias, b, idx, n, p.g.n_total, v, valid, ld);
-      if (last) {
+      epi_accumulate(p.ep, sbias, b, n, p.g.n_total, acc, valid, ld, v);
+      if (last) {  // accumulator fully read: hand the TMEM buffer back before the stores
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);
         ++itt;
       }
+      const long idx_cur = idx; const bool valid_cur = valid;
+      // next item: its global reads go out now and land while this item is stored and the next accumulator is awaited
+      int ntile = tile, nit = it + 2;
+      if (nit >= NITEMS) { nit = hsel; ntile += gridDim.x; }
+      if (ntile < p.total_tiles) {
+        coords(ntile, nit, b, n, idx, valid, tcol);
+        epi_issue_loads(p.ep, idx, valid, ld);
+      }
+      epi_store(p.ep, idx_cur, valid_cur, v);
       tile = ntile; it = nit;
     }
     if (!active) {  // idle second warp still has to release the accumulator buffers it never reads
@@ -411,18 +431,19 @@ static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
     VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KC><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.tmR, pl.p);
+  conv_tc_kernel<BN, KC><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
 
-int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, int num_sms,
-                 int desc_mode) {
+int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* xs, const __nv_bfloat16* w,
+                 int num_sms, int desc_mode) {
   const bool force_streaming = (desc_mode & 2) != 0;  // test knob: exercise the streamed-weights path everywhere
   desc_mode &= 1;
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
   VD_CHECK(g.n_total % 32 == 0, "conv_tc: output columns must be a multiple of 32");
-  VD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, "conv_tc: 1..16 taps supported");
+  VD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, "conv_tc: 1..32 taps supported");
+  VD_CHECK(g.nseg >= 1 && g.nseg <= kMaxSeg && g.seg_tap_end[g.nseg - 1] == g.ntaps, "conv_tc: bad segment table");
   VD_CHECK(g.n_total <= 2048, "conv_tc: at most 2048 output columns per row");
   const int kc = (g.c_in % 64 == 0) ? 64 : 32;
   int bn = 32;
@@ -431,18 +452,26 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, cons
   }
   const int nacc = bn >= 256 ? 1 : 2;
   const int bm = 128 * nacc;
-  int lo = g.tap_off[0], hi = g.tap_off[0];
-  for (int i = 1; i < g.ntaps; ++i) { lo = std::min(lo, g.tap_off[i]); hi = std::max(hi, g.tap_off[i]); }
   ConvTcParams& p = pl->p;
   p.g = g;
-  p.halo_lo = lo;
-  p.nboxes = (bm + (hi - lo) + 63) / 64;
-  p.a_stage_bytes = p.nboxes * 64 * kc * 2;
+  p.a_stage_bytes = 0;
+  int tap0 = 0;
+  for (int sg = 0; sg < g.nseg; ++sg) {
+    const int tap1 = g.seg_tap_end[sg];
+    VD_CHECK(tap1 > tap0, "conv_tc: empty segment");
+    int lo = g.tap_off[tap0], hi = g.tap_off[tap0];
+    for (int i = tap0 + 1; i < tap1; ++i) { lo = std::min(lo, g.tap_off[i]); hi = std::max(hi, g.tap_off[i]); }
+    p.seg_halo_lo[sg] = lo;
+    p.seg_nboxes[sg] = (bm + (hi - lo) + 63) / 64;
+    p.a_stage_bytes = std::max(p.a_stage_bytes, p.seg_nboxes[sg] * 64 * kc * 2);
+    for (int i = tap0; i < tap1; ++i) p.tap_delta16[i] = (uint32_t)((g.tap_off[i] - lo) * kc * 2) >> 4;
+    tap0 = tap1;
+  }
   p.m_tiles = (g.L + bm - 1) / bm;
   p.n_tiles = g.n_total / bn;
   p.total_tiles = g.B * p.m_tiles * p.n_tiles;
   p.desc_mode = desc_mode;
-  for (int i = 0; i < g.ntaps; ++i) p.tap_delta16[i] = (uint32_t)((g.tap_off[i] - lo) * kc * 2) >> 4;
+  p.res_prefetch = 0;
   pl->bn = bn;
   pl->kc = kc;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
@@ -463,25 +492,31 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* x, cons
     p.b_region_bytes = p.nb_stages * b_stage;
   }
   pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + (size_t)g.n_total * 4;
-  if (encode_3d(&pl->tmA, x, g.c_in, g.L, g.B, kc, 64)) return 1;
+  for (int sg = 0; sg < kMaxSeg; ++sg) {
+    if (encode_3d(&pl->tm.a[sg], xs[sg < g.nseg ? sg : 0], g.c_in, g.L, g.B, kc, 64)) return 1;
+    pl->tm.r[sg] = pl->tm.a[sg];  // placeholder until a residual is bound
+    pl->res_bound[sg] = nullptr;
+  }
   if (encode_3d(&pl->tmW, w, g.c_in, g.n_total, g.ntaps, kc, bn)) return 1;
-  pl->tmR = pl->tmA;  // placeholder until a residual is bound
-  pl->res_bound = nullptr;
   return 0;
 }
 
-int bind_residual_tc(ConvTcPlan& pl, const __nv_bfloat16* res) {
-  if (res != nullptr && pl.res_bound != res) {
-    if (encode_3d(&pl.tmR, res, pl.p.g.n_total, pl.p.g.L, pl.p.g.B, pl.bn < 64 ? pl.bn : 64, 64, false)) return 1;
-    pl.res_bound = res;
+int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep) {
+  VD_CHECK(ep.nres >= 0 && ep.nres <= kMaxSeg - 1, "conv_tc: at most 3 residual tensors");
+  for (int i = 0; i < ep.nres; ++i) {
+    if (pl.res_bound[i] != ep.res[i]) {
+      if (encode_3d(&pl.tm.r[i], ep.res[i], pl.p.g.n_total, pl.p.g.L, pl.p.g.B, pl.bn < 64 ? pl.bn : 64, 64, false))
+        return 1;
+      pl.res_bound[i] = ep.res[i];
+    }
   }
   return 0;
 }
 
 int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) {
   pl.p.ep = ep;
-  if (bind_residual_tc(pl, ep.res)) return 1;  // no-op when the plan was built with this residual
-  pl.p.res_prefetch = ep.res != nullptr ? 1 : 0;
+  if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
+  pl.p.res_prefetch = ep.nres > 0 ? 1 : 0;
   switch (pl.bn * 100 + pl.kc) {
     case 25664: return launch_inst<256, 64>(pl, stream);
     case 12864: return launch_inst<128, 64>(pl, stream);

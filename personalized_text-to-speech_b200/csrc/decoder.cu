@@ -45,7 +45,7 @@ constexpr float kPostSlope = 0.01f;  // F.leaky_relu default, models.py:285
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int ceildiv(int a, int b) { return -floordiv(-a, b); }
 
-enum LayerKind { kConv = 0, kConvT = 1, kPost = 2, kCond = 3 };
+enum LayerKind { kConv = 0, kConvT = 1, kPost = 2, kCond = 3, kMrf = 4 };
 
 struct Layer {
   std::string name;
@@ -56,6 +56,11 @@ struct Layer {
   float* bias = nullptr;  // [n_total] (zero when the layer has no bias)
   float* wf32 = nullptr;  // conv_post / cond keep fp32 weights
   bool loaded = false;
+  // kMrf (virtual layer): the last convs of one stage's MRF branches, accumulated in one launch
+  std::vector<int> members;      // real layer ids, one per branch
+  bool bias_dirty = false;       // combined bias = sum of member biases, rebuilt lazily
+  int mrf_group = -1;            // real layers: id of the virtual layer they also feed, and their tap base in it
+  int mrf_tap_base = 0;
 };
 
 static void conv_geom(Layer& l) {
@@ -68,6 +73,8 @@ static void conv_geom(Layer& l) {
     g.tap_nlo[j] = 0;
     g.tap_nhi[j] = l.c_out;
   }
+  g.nseg = 1;
+  g.seg_tap_end[0] = g.ntaps;
 }
 
 // ConvTranspose1d(k, s, p=(k-s)/2): output sample s*i + r reads input rows i + off, kernel index j = r + p - s*off
@@ -85,6 +92,8 @@ static void convT_geom(Layer& l) {
     g.tap_nlo[i] = rlo * l.c_out;
     g.tap_nhi[i] = rhi * l.c_out;
   }
+  g.nseg = 1;
+  g.seg_tap_end[0] = g.ntaps;
 }
 
 struct PlanKey {
@@ -97,7 +106,7 @@ struct PlanKey {
 
 struct Step {           // one launch of the conv primitive
   int layer;
-  const bf16* x;
+  const bf16* xs[kMaxSeg];
   ConvEpilogue ep;
   int L;
   ConvTcPlan tc;
@@ -126,6 +135,8 @@ struct vitsdec_decoder {
   std::map<std::string, int> by_name;
   int l_pre = -1, l_post = -1, l_cond = -1;
   std::vector<int> l_ups;
+  std::vector<int> l_mrf;              // per stage: virtual fused-MRF layer id, or -1 (fp32 accumulator path)
+  int num_real_layers = 0;
   std::vector<std::vector<int>> l_rb;  // per resblock: conv layer ids in forward order
   std::vector<int> stage_ch;
   int hop = 1;
@@ -170,7 +181,7 @@ static int add_layer(vitsdec_decoder* d, const std::string& name, LayerKind kind
 }
 
 static int alloc_layer(Layer& l) {
-  if (l.kind == kConv || l.kind == kConvT) {
+  if (l.kind == kConv || l.kind == kConvT || l.kind == kMrf) {
     const size_t wn = (size_t)l.geom.ntaps * l.geom.n_total * l.geom.c_in;
     VD_CUDA(cudaMalloc(&l.w, wn * sizeof(bf16)));
     VD_CUDA(cudaMalloc(&l.bias, (size_t)l.geom.n_total * sizeof(float)));
@@ -186,8 +197,18 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
   size_t slot;      // bytes of one bf16 activation slot
-  size_t off_a0, off_cb, off_x, off_u, off_h, off_p, off_q, off_s, off_dbg, total;
+  size_t off_a0, off_cb, off_slots, off_dbg, total;
+  int nslots;
 };
+
+// Slot map.  0: X (stage in/out)  1: U (upsampled)  2: T1 (c1 output of non-final pairs)  3: T2 (pair ping-pong)
+//   fused MRF:  4+j: P_j (input + residual of branch j's last pair)   4+nk+j: H_j (c1 output of that last pair)
+//   fp32-accumulator MRF (fallback):  4: P   5,6: S (one fp32 tensor)
+static bool all_fused(const vitsdec_decoder* d) {
+  for (int id : d->l_mrf)
+    if (id < 0) return false;
+  return true;
+}
 
 static WsLayout ws_layout(const vitsdec_decoder* d, int B, int T) {
   WsLayout w{};
@@ -205,12 +226,8 @@ static WsLayout ws_layout(const vitsdec_decoder* d, int B, int T) {
   w.slot = slot;
   w.off_a0 = o; o += align_up((size_t)B * T * d->hp.initial_channel * 2, 1024);
   w.off_cb = o; o += align_up((size_t)B * d->hp.upsample_initial_channel * 4, 1024);
-  w.off_x = o; o += slot;
-  w.off_u = o; o += slot;
-  w.off_h = o; o += slot;
-  w.off_p = o; o += slot;
-  w.off_q = o; o += slot;
-  w.off_s = o; o += 2 * slot;
+  w.nslots = all_fused(d) ? 4 + 2 * d->hp.num_kernels : std::max(7, 4 + 2 * d->hp.num_kernels);
+  w.off_slots = o; o += (size_t)w.nslots * slot;
   w.off_dbg = o;
   if (d->debug_keep) o += align_up(dbg, 1024);
   w.total = o;
@@ -219,30 +236,32 @@ static WsLayout ws_layout(const vitsdec_decoder* d, int B, int T) {
 
 static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   const WsLayout w = ws_layout(d, B, T);
-  bf16* X = reinterpret_cast<bf16*>(ws + w.off_x);
-  bf16* U = reinterpret_cast<bf16*>(ws + w.off_u);
-  bf16* H = reinterpret_cast<bf16*>(ws + w.off_h);
-  bf16* P = reinterpret_cast<bf16*>(ws + w.off_p);
-  bf16* Q = reinterpret_cast<bf16*>(ws + w.off_q);
-  float* S = reinterpret_cast<float*>(ws + w.off_s);
+  auto slot = [&](int i) { return reinterpret_cast<bf16*>(ws + w.off_slots + (size_t)i * w.slot); };
+  bf16* X = slot(0);
+  bf16* U = slot(1);
+  bf16* T1 = slot(2);
+  bf16* T2 = slot(3);
+  const int nk = d->hp.num_kernels;
   pl.a0 = reinterpret_cast<bf16*>(ws + w.off_a0);
   pl.cb = reinterpret_cast<float*>(ws + w.off_cb);
   uint8_t* dbg = ws + w.off_dbg;
 
-  auto push = [&](int layer, const bf16* x, int L, const ConvEpilogue& ep) -> int {
+  auto push = [&](int layer, const bf16* const* xs, int L, const ConvEpilogue& ep) -> int {
     Step s{};
-    s.layer = layer; s.x = x; s.ep = ep; s.L = L;
+    s.layer = layer; s.ep = ep; s.L = L;
     Layer& ly = d->layers[layer];
     ConvGeom g = ly.geom;
     g.B = B; g.L = L;
+    for (int i = 0; i < g.nseg; ++i) s.xs[i] = xs[i];
     s.tc.p.g = g;
     if (d->impl == 0) {
-      if (plan_conv_tc(&s.tc, g, x, ly.w, d->num_sms, d->desc_mode)) return 1;
-      if (bind_residual_tc(s.tc, ep.res)) return 1;
+      if (plan_conv_tc(&s.tc, g, s.xs, ly.w, d->num_sms, d->desc_mode)) return 1;
+      if (bind_residual_tc(s.tc, ep)) return 1;
     }
     pl.steps.push_back(s);
     return 0;
   };
+  auto push1 = [&](int layer, const bf16* x, int L, const ConvEpilogue& ep) -> int { return push(layer, &x, L, ep); };
   auto keep = [&](const std::string& name, int C, int Lr, float gain) {
     if (!d->debug_keep) return;
     Step& s = pl.steps.back();
@@ -264,10 +283,9 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   {
     ConvEpilogue e = ep0(d->l_pre);
     e.out = X;
-    if (push(d->l_pre, pl.a0, T, e)) return 1;
+    if (push1(d->l_pre, pl.a0, T, e)) return 1;
     keep("conv_pre", d->hp.upsample_initial_channel, T, 1.f / kSlope);
   }
-  const int nk = d->hp.num_kernels;
   const int nstage = d->hp.num_upsamples;
   int L = T;
   for (int i = 0; i < nstage; ++i) {
@@ -276,32 +294,46 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     {  // ups[i]: rows = input rows, columns = s * ch  ==  [B][L*s][ch]
       ConvEpilogue e = ep0(d->l_ups[i]);
       e.out = U;
-      if (push(d->l_ups[i], X, L, e)) return 1;
+      if (push1(d->l_ups[i], X, L, e)) return 1;
     }
     L *= s;
     keep("ups." + std::to_string(i), ch, L, 1.f / kSlope);
     const float next_slope = (i == nstage - 1) ? kPostSlope : kSlope;
+    const bool fused = d->l_mrf[i] >= 0;
+    float* S = reinterpret_cast<float*>(slot(5));
+    const bf16* seg_in[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
+    const bf16* seg_res[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
     for (int j = 0; j < nk; ++j) {
       const std::vector<int>& convs = d->l_rb[i * nk + j];
-      const bf16* cur = U;
       const int nconv = (int)convs.size();
       const int npairs = d->hp.resblock == 1 ? nconv / 2 : nconv;
+      bf16* Pj = fused ? slot(4 + j) : slot(4);
+      bf16* Hj = fused ? slot(4 + nk + j) : T1;
+      const bf16* cur = U;
       for (int m = 0; m < npairs; ++m) {
+        const bool last = m == npairs - 1;
         const bf16* conv_in = cur;
         int lid;
         if (d->hp.resblock == 1) {
           ConvEpilogue e1 = ep0(convs[2 * m]);
-          e1.out = H;
-          if (push(convs[2 * m], cur, L, e1)) return 1;
-          conv_in = H;
+          e1.out = last ? Hj : T1;
+          if (push1(convs[2 * m], cur, L, e1)) return 1;
+          conv_in = e1.out;
           lid = convs[2 * m + 1];
         } else {
           lid = convs[m];
         }
+        if (last && fused) {  // deferred: runs as segment j of the stage's fused MRF launch
+          seg_in[j] = conv_in;
+          seg_res[j] = cur;
+          break;
+        }
         ConvEpilogue e = ep0(lid);
-        e.res = cur;
-        bf16* dst = (m & 1) ? Q : P;
-        if (m < npairs - 1) {
+        e.res[0] = cur;
+        e.nres = 1;
+        // ping-pong so that the input of the last pair lands in P_j
+        bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2;
+        if (!last) {
           e.out = dst;
         } else {
           e.mrf = S;
@@ -313,9 +345,21 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
           e.out = X;
           e.out_slope = next_slope;
         }
-        if (push(lid, conv_in, L, e)) return 1;
+        if (push1(lid, conv_in, L, e)) return 1;
         cur = dst;
       }
+    }
+    if (fused) {
+      // models.py:279-284: x = (rb0(x) + rb1(x) + rb2(x)) / nk -- the three last convs accumulate in one TMEM tile
+      ConvEpilogue e = ep0(d->l_mrf[i]);
+      for (int j = 0; j < nk; ++j) e.res[j] = seg_res[j];
+      e.nres = nk;
+      e.mrf_mode = 3;
+      e.mrf = nullptr;
+      e.mrf_scale = 1.f / nk;
+      e.out = X;
+      e.out_slope = next_slope;
+      if (push(d->l_mrf[i], seg_in, L, e)) return 1;
     }
     keep("mrf." + std::to_string(i), ch, L, 1.f / next_slope);
   }
@@ -328,7 +372,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
 static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
   Layer& ly = d->layers[s.layer];
   if (d->impl == 0) return launch_conv_tc(s.tc, s.ep, st);
-  return launch_conv_simt(s.tc.p.g, s.ep, s.x, ly.w, st);
+  return launch_conv_simt(s.tc.p.g, s.ep, s.xs, ly.w, st);
 }
 
 }  // namespace vd
@@ -400,6 +444,41 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
   }
   d->l_post = add_layer(d.get(), "conv_post", kPost, d->stage_ch.back(), 1, 7, 1, 1);
   if (hp->gin_channels > 0) d->l_cond = add_layer(d.get(), "cond", kCond, hp->gin_channels, c0, 1, 1, 1);
+  d->num_real_layers = (int)d->layers.size();
+  // Fused MRF: one virtual layer per stage whose segments are the LAST conv of every branch (weights concatenated
+  // along taps, biases summed); possible when the residual count fits the epilogue (<= 3) and the taps fit the table.
+  {
+    int ksum = 0;
+    for (int j = 0; j < hp->num_kernels; ++j) ksum += hp->resblock_kernel_sizes[j];
+    const bool fusable = hp->num_kernels <= kMaxSeg - 1 && ksum <= kMaxTaps;
+    for (int i = 0; i < hp->num_upsamples; ++i) {
+      if (!fusable) { d->l_mrf.push_back(-1); continue; }
+      Layer v;
+      v.name = "mrf." + std::to_string(i);
+      v.kind = kMrf;
+      v.c_in = v.c_out = d->stage_ch[i];
+      ConvGeom& g = v.geom;
+      g.c_in = g.n_total = v.c_in;
+      g.ntaps = 0;
+      g.nseg = hp->num_kernels;
+      const int vid = (int)d->layers.size();
+      for (int j = 0; j < hp->num_kernels; ++j) {
+        const int lid = d->l_rb[i * hp->num_kernels + j].back();
+        Layer& m = d->layers[lid];
+        m.mrf_group = vid;
+        m.mrf_tap_base = g.ntaps;
+        for (int t = 0; t < m.geom.ntaps; ++t, ++g.ntaps) {
+          g.tap_off[g.ntaps] = m.geom.tap_off[t];
+          g.tap_nlo[g.ntaps] = 0;
+          g.tap_nhi[g.ntaps] = v.c_out;
+        }
+        g.seg_tap_end[j] = g.ntaps;
+        v.members.push_back(lid);
+      }
+      d->layers.push_back(v);
+      d->l_mrf.push_back(vid);
+    }
+  }
   for (Layer& l : d->layers)
     if (alloc_layer(l)) return 1;
   VD_CUDA(cudaMalloc(&d->scale_scratch, 4096 * sizeof(float)));
@@ -422,9 +501,9 @@ void vitsdec_destroy(vitsdec_decoder* d) {
   delete d;
 }
 
-int vitsdec_num_layers(const vitsdec_decoder* d) { return d ? (int)d->layers.size() : 0; }
+int vitsdec_num_layers(const vitsdec_decoder* d) { return d ? d->num_real_layers : 0; }
 const char* vitsdec_layer_name(const vitsdec_decoder* d, int i) {
-  if (!d || i < 0 || i >= (int)d->layers.size()) return nullptr;
+  if (!d || i < 0 || i >= d->num_real_layers) return nullptr;
   return d->layers[i].name.c_str();
 }
 
@@ -442,6 +521,13 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
     if (launch_wn_scale(w, wg, d->scale_scratch, l.c_out, l.c_in * l.k, st)) return 1;
     if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st)) return 1;
     if (launch_replicate_bias(bias, l.bias, l.c_out, 1, st)) return 1;
+    if (l.mrf_group >= 0) {
+      Layer& v = d->layers[l.mrf_group];
+      if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.mrf_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
+                           st))
+        return 1;
+      v.bias_dirty = true;
+    }
   } else if (l.kind == kConvT) {
     VD_CHECK(l.c_in <= 4096, "too many channels");
     if (launch_wn_scale(w, wg, d->scale_scratch, l.c_in, l.c_out * l.k, st)) return 1;  // dim 0 of [C_in,C_out,k]
@@ -473,10 +559,21 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   VD_CHECK(B <= 65535, "vitsdec_decode: batch too large");
   VD_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
   VD_CHECK(g == nullptr || d->l_cond >= 0, "g given but the decoder was built with gin_channels=0 (models.py:267)");
-  for (const Layer& l : d->layers)
-    VD_CHECK(l.loaded, "vitsdec_decode: layer " + l.name + " has no weights loaded");
+  for (int i = 0; i < d->num_real_layers; ++i)
+    VD_CHECK(d->layers[i].loaded, "vitsdec_decode: layer " + d->layers[i].name + " has no weights loaded");
   DeviceGuard guard(d->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    std::lock_guard<std::mutex> lock(d->mu);
+    for (size_t i = d->num_real_layers; i < d->layers.size(); ++i) {
+      Layer& v = d->layers[i];
+      if (!v.bias_dirty) continue;
+      const float* bs[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
+      for (size_t j = 0; j < v.members.size(); ++j) bs[j] = d->layers[v.members[j]].bias;
+      if (launch_sum_bias(bs[0], bs[1], bs[2], bs[3], v.bias, v.c_out, st)) return 1;
+      v.bias_dirty = false;
+    }
+  }
 
   std::shared_ptr<Plan> plan;
   {
@@ -669,17 +766,19 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
     g.B = B; g.L = L;
     ConvEpilogue e{};
     e.bias = l.bias;
-    e.res = static_cast<const bf16*>(res);
+    e.res[0] = static_cast<const bf16*>(res);
+    e.nres = res ? 1 : 0;
     e.res_gain = res_gain;
     e.out_slope = out_slope;
     e.mrf_scale = 1.f;
     e.out = static_cast<bf16*>(y);
     if (impl == 0) {
       ConvTcPlan pl{};
-      rc = plan_conv_tc(&pl, g, static_cast<const bf16*>(x), l.w, prop.multiProcessorCount, desc_mode) ||
-           launch_conv_tc(pl, e, st);
+      const bf16* xs[kMaxSeg] = {static_cast<const bf16*>(x), nullptr, nullptr, nullptr};
+      rc = plan_conv_tc(&pl, g, xs, l.w, prop.multiProcessorCount, desc_mode) || launch_conv_tc(pl, e, st);
     } else {
-      rc = launch_conv_simt(g, e, static_cast<const bf16*>(x), l.w, st);
+      const bf16* xs[kMaxSeg] = {static_cast<const bf16*>(x), nullptr, nullptr, nullptr};
+      rc = launch_conv_simt(g, e, xs, l.w, st);
     }
   }
   cudaError_t se = cudaStreamSynchronize(st);

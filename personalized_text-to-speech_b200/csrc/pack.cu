@@ -63,6 +63,19 @@ __global__ void replicate_bias_kernel(const float* __restrict__ b, float* __rest
   if (i < c_out * reps) out[i] = b ? b[i % c_out] : 0.f;
 }
 
+// combined bias of a fused MRF launch: sum of the member layers' biases
+__global__ void sum_bias_kernel(const float* __restrict__ b0, const float* __restrict__ b1,
+                                const float* __restrict__ b2, const float* __restrict__ b3, float* __restrict__ out,
+                                int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = b0[i];
+  if (b1) s += b1[i];
+  if (b2) s += b2[i];
+  if (b3) s += b3[i];
+  out[i] = s;
+}
+
 // z fp32 [B][C][T] (strided) -> bf16 [B][T][C]
 __global__ void pack_z_kernel(const float* __restrict__ z, long sb, long sc, __nv_bfloat16* __restrict__ out, int C,
                               int T) {
@@ -171,6 +184,12 @@ int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int
 }
 int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaStream_t st) {
   replicate_bias_kernel<<<(c_out * reps + 255) / 256, 256, 0, st>>>(b, out, c_out, reps);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_sum_bias(const float* b0, const float* b1, const float* b2, const float* b3, float* out, int n,
+                    cudaStream_t st) {
+  sum_bias_kernel<<<(n + 255) / 256, 256, 0, st>>>(b0, b1, b2, b3, out, n);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -12,6 +12,8 @@ int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int 
 int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int c_in, int c_out, int k, int s, int p,
                       int ntaps, int off0, cudaStream_t st);
 int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaStream_t st);
+int launch_sum_bias(const float* b0, const float* b1, const float* b2, const float* b3, float* out, int n,
+                    cudaStream_t st);
 int launch_pack_z(const float* z, long sb, long sc, __nv_bfloat16* out, int B, int C, int T, cudaStream_t st);
 int launch_cond(const float* wc, const float* bc, const float* g, float* cb, int B, int c_out, int gin,
                 cudaStream_t st);
