@@ -33,7 +33,8 @@ struct TcCfg {
   static constexpr int B_STAGE = BN * ROWB;
   static constexpr int ACC_COLS = NACC * BN;
   static constexpr int RBOXC = BN < 64 ? BN : 64;   // residual prefetch box: RBOXC columns x 64 rows
-  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  static constexpr int NBUF = 512 / ACC_COLS > 8 ? 8 : 512 / ACC_COLS;  // accumulator buffers in TMEM (2..8)
+  static constexpr int TMEM_COLS = NBUF * ACC_COLS;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
@@ -164,8 +165,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
   uint64_t* b_full = a_empty + kMaxNA;
   uint64_t* b_empty = b_full + kMaxNB;
   uint64_t* acc_full = b_empty + kMaxNB;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* w_full = acc_empty + 2;
+  uint64_t* acc_empty = acc_full + 8;
+  uint64_t* w_full = acc_empty + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   float* sbias = reinterpret_cast<float*>(bars + 64);  // 512 bytes of barrier space, then the bias vector
 
@@ -177,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < kMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kMaxNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -263,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       uint32_t tapmask = 0;
       for (int tap = 0; tap < p.g.ntaps; ++tap)
         if (p.g.tap_nlo[tap] < n0 + BN && p.g.tap_nhi[tap] > n0) tapmask |= 1u << tap;
-      const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
+      const uint32_t as = itt % C::NBUF, pacc = (itt / C::NBUF) & 1;
       mbar_wait(&acc_empty[as], pacc ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + as * ACC_COLS;
@@ -339,7 +340,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     }
     while (active && tile < p.total_tiles) {
       const bool first = it < 2, last = it + 2 >= NITEMS;
-      const uint32_t as = itt & 1, pacc = (itt >> 1) & 1;
+      const uint32_t as = itt % C::NBUF, pacc = (itt / C::NBUF) & 1;
       if (first) {
         mbar_wait(&acc_full[as], pacc);
         tc_fence_after();
@@ -369,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     }
     if (!active) {  // idle second warp still has to release the accumulator buffers it never reads
       for (; tile < p.total_tiles; tile += gridDim.x, ++itt) {
-        if (lane == 0) mbar_arrive(&acc_empty[itt & 1]);
+        if (lane == 0) mbar_arrive(&acc_empty[itt % C::NBUF]);
       }
     }
   }
@@ -484,7 +485,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
     p.b_region_bytes = w_all;
     p.nb_stages = 0;
     p.na_stages = std::min(kMaxNA, (kSmemBudget - w_all) / p.a_stage_bytes);
-    p.na_stages = std::min(p.na_stages, std::max(2, (96 * 1024) / p.a_stage_bytes));  // ~96 KB in flight is plenty
+    p.na_stages = std::min(p.na_stages, std::max(2, (96 * 1024) / p.a_stage_bytes));  // deeper did not help (r1f)
   } else {
     p.na_stages = 2;
     VD_CHECK(2 * p.a_stage_bytes + 2 * b_stage <= kSmemBudget, "conv_tc: dilation halo too large for shared memory");
