@@ -113,6 +113,10 @@ VITSDEC_API int vitsdec_last_launch_count(const vitsdec_decoder* dec);
 VITSDEC_API int vitsdec_debug_read(vitsdec_decoder* dec, const char* name, float* out_dev, size_t out_elems, int* channels,
                        int* length, void* stream);
 
+/* Profiling hook for vitsdec_op_*: device buffer of 256 x 12 uint64 that CTA 0 of the tcgen05 kernel fills with
+ * clock64() stamps per tile (producer / MMA issuer / epilogue hand-offs); NULL disables.  tools/trace_probe.py. */
+VITSDEC_API int vitsdec_debug_set_trace(void* trace_dev);
+
 /* Single fused convolution on channels-last bf16 activations (per-kernel parity tests):
  *   y[b,t,co] = lrelu( bias[co] + sum_j sum_ci w[co,ci,j] * x[b, t + (j-(k-1)/2)*dilation, ci] (+ res), out_slope )
  *   x_dev / res_dev / y_dev: bf16 [batch, length, channels]; w_dev fp32 [c_out, c_in, k]; bias fp32 [c_out].

@@ -59,6 +59,7 @@ SIGNATURES = {
     "vitsdec_last_launch_count": (_i, [_vp]),
     "vitsdec_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
     "vitsdec_debug_read": (_i, [_vp, _cp, _vp, _sz, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp]),
+    "vitsdec_debug_set_trace": (_i, [_vp]),
     "vitsdec_op_conv1d": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vitsdec_op_conv_transpose1d": (_i, [_i, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }

@@ -24,7 +24,7 @@ constexpr int kMaxNA = 8;      // activation-chunk stages (runtime count <= this
 constexpr int kMaxNB = 8;      // weight-tile stages when weights are streamed
 constexpr int kEpiWarps = 8;   // two warps per TMEM lane quadrant
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
-constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - 8192 /*bias*/;
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - 8192 /*bias*/ - 16384 /*scratch*/;
 
 template <int BN, int KC>
 struct TcCfg {
@@ -41,9 +41,16 @@ struct TcCfg {
 // Epilogue work item = 32 consecutive output columns of one row per thread.  Global reads (residual, MRF
 // accumulator) are issued one item AHEAD of their use so their DRAM/L2 latency overlaps the TMEM load, the math
 // and the stores of the current item (the epilogue is otherwise latency-bound: one 64-byte load per thread).
+// Per-warp 2 KB transpose scratch: a 32-row x 64-byte item, 16-byte chunks XOR-swizzled so that both access patterns
+// below are bank-conflict free.  Threads OWN rows for the math (TMEM lane == row), but global memory wants each warp
+// instruction to cover contiguous 64-byte row segments (8 rows x 64 B per LDG/STG.128 instead of 32 rows x 16 B):
+// with the row-owner mapping every instruction touched 32 different 128-byte lines and the LSU, not HBM, set the
+// streaming ceiling (~4.4 TB/s; profiles/r01_stream_probe.txt).
+__device__ __forceinline__ uint32_t scr_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+
 struct EpiLoads {
-  uint4 res[kMaxSeg - 1][4];  // up to 3 residual tensors in flight (MRF fusion of up to 3 branches + ... see plan)
-  float4 mrf[8];
+  uint4 res[kMaxSeg - 1][4];  // residual tensors, COALESCED mapping: element i = row 8*i + lane/4, chunk lane%4
+  float4 mrf[8];              // fp32 MRF accumulator (fallback path only), row-owner mapping
 };
 constexpr int kMaxRes = kMaxSeg - 1;
 
@@ -60,50 +67,69 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   return r;
 }
 
-__device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, long idx, bool valid, EpiLoads& ld) {
-  if (!valid) return;
+// One epilogue work item: rows [row0, row0+32) x columns [n, n+32) of utterance b; rows_valid of them exist.
+struct EpiItem {
+  int b, n, rows_valid;
+  long row0;       // b*L + t of lane 0's row
+  uint32_t tcol;   // TMEM column of the item inside its accumulator buffer
+};
+
+__device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, const EpiItem& it, int n_total, int lane,
+                                                EpiLoads& ld) {
 #pragma unroll
   for (int i = 0; i < kMaxRes; ++i) {
     if (i < ep.nres) {
-      const uint4* rp = reinterpret_cast<const uint4*>(ep.res[i] + idx);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ld.res[i][q] = ld_stream_u4(rp + q);
+      for (int j = 0; j < 4; ++j) {
+        const int row = 8 * j + (lane >> 2);
+        if (row < it.rows_valid)
+          ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + (it.row0 + row) * n_total + it.n) +
+                                      (lane & 3));
+      }
     }
   }
-  if (ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) {
-    const float4* mp = reinterpret_cast<const float4*>(ep.mrf + idx);
+  if ((ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) && lane < it.rows_valid) {
+    const float4* mp = reinterpret_cast<const float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
 #pragma unroll
     for (int j = 0; j < 8; ++j) ld.mrf[j] = ld_stream_f4(mp + j);
   }
 }
 
 // v = acc + bias (+ per-utterance bias) (+ residuals) (+ MRF accumulator): everything that consumes `ld`
-__device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const float* sbias, int b, int n, int n_total,
-                                               const uint32_t (&acc)[32], bool valid, const EpiLoads& ld,
-                                               float (&v)[32]) {
+__device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const float4 (&bias)[8], uint8_t* scratch,
+                                               const EpiItem& it, int n_total, int lane, const uint32_t (&acc)[32],
+                                               const EpiLoads& ld, float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 bv = *reinterpret_cast<const float4*>(sbias + n + j);
+    const float4 bv = bias[j >> 2];
     v[j + 0] = __uint_as_float(acc[j + 0]) + bv.x;
     v[j + 1] = __uint_as_float(acc[j + 1]) + bv.y;
     v[j + 2] = __uint_as_float(acc[j + 2]) + bv.z;
     v[j + 3] = __uint_as_float(acc[j + 3]) + bv.w;
   }
   if (ep.bias_b) {
-    const float* bb = ep.bias_b + (long)b * n_total + n;
+    const float* bb = ep.bias_b + (long)it.b * n_total + it.n;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 bv = __ldg(reinterpret_cast<const float4*>(bb + j));
       v[j + 0] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
     }
   }
-  if (!valid) return;
 #pragma unroll
   for (int i = 0; i < kMaxRes; ++i) {
     if (i < ep.nres) {
+      // coalesced registers -> scratch -> row-owner registers
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(scratch + scr_off(8 * j + (lane >> 2), lane & 3)) = ld.res[i][j];
+      __syncwarp();
+      uint4 mine[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mine[c] = *reinterpret_cast<const uint4*>(scratch + scr_off(lane, c));
+      __syncwarp();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&ld.res[i][q]);
+        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&mine[q]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 a = __bfloat1622float2(r2[e]);
@@ -121,28 +147,40 @@ __device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const flo
   }
 }
 
-__device__ __forceinline__ void epi_store(const ConvEpilogue& ep, long idx, bool valid, float (&v)[32]) {
-  if (!valid) return;
+__device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int n_total,
+                                          int lane, float (&v)[32]) {
   if (ep.mrf_mode == 1 || ep.mrf_mode == 2) {
-    float4* mp = reinterpret_cast<float4*>(ep.mrf + idx);
+    if (lane < it.rows_valid) {
+      float4* mp = reinterpret_cast<float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 8; ++j) mp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
     return;
   }
   if (ep.mrf_mode == 3) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= ep.mrf_scale;
   }
-  uint4* op = reinterpret_cast<uint4*>(ep.out + idx);
+  // row-owner registers -> scratch -> coalesced 64-byte row segments
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint4 ov;
     __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      o2[e] = __floats2bfloat162_rn(lrelu(v[q * 8 + e * 2], ep.out_slope), lrelu(v[q * 8 + e * 2 + 1], ep.out_slope));
-    op[q] = ov;
+      o2[e] = __floats2bfloat162_rn(fmaxf(v[q * 8 + e * 2], v[q * 8 + e * 2] * ep.out_slope),
+                                    fmaxf(v[q * 8 + e * 2 + 1], v[q * 8 + e * 2 + 1] * ep.out_slope));  // slope in (0,1]
+    *reinterpret_cast<uint4*>(scratch + scr_off(lane, q)) = ov;
   }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = 8 * j + (lane >> 2);
+    const uint4 ov = *reinterpret_cast<const uint4*>(scratch + scr_off(row, lane & 3));
+    if (row < it.rows_valid)
+      *(reinterpret_cast<uint4*>(ep.out + (it.row0 + row) * n_total + it.n) + (lane & 3)) = ov;
+  }
+  __syncwarp();
 }
 
 template <int BN, int KC>
@@ -206,10 +244,11 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
             tma_load_3d(&tmW, w_full, smemB + (tap * nkc + kc) * B_STAGE, kc * KC, 0, tap);
       }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mb = tile / p.n_tiles;
-        const int b = mb / p.m_tiles;
-        const int t0 = (mb % p.m_tiles) * BM;
+        uint32_t mb, nt, bq, mt;
+        p.div_n.divmod(tile, mb, nt);
+        p.div_m.divmod(mb, bq, mt);
+        const int b = bq;
+        const int t0 = mt * BM;
         const int n0 = nt * BN;
         if (p.res_prefetch) {
           // the residual tiles this tile's epilogue will read: start them towards L2 now (the producer runs NA
@@ -225,6 +264,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
           for (int kc = 0; kc < nkc; ++kc) {
             const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
             mbar_wait(&a_empty[sa], pa ^ 1);
+            if (p.trace && blockIdx.x == 0 && sg == 0 && kc == 0 && tile / gridDim.x < 256)
+              p.trace[(tile / gridDim.x) * 12 + 0] = clock64();
             mbar_expect_tx(&a_full[sa], nbx * 64 * ROWB);
             for (int bx = 0; bx < nbx; ++bx)
               tma_load_3d(&tm.a[sg], &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, kc * KC,
@@ -260,13 +301,15 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       tc_fence_after();
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
-      const int n0 = (tile % p.n_tiles) * BN;
+      const int n0 = (tile - p.div_n.quot(tile) * p.n_tiles) * BN;
       uint32_t tapmask = 0;
       for (int tap = 0; tap < p.g.ntaps; ++tap)
         if (p.g.tap_nlo[tap] < n0 + BN && p.g.tap_nhi[tap] > n0) tapmask |= 1u << tap;
       const uint32_t as = itt % C::NBUF, pacc = (itt / C::NBUF) & 1;
       mbar_wait(&acc_empty[as], pacc ^ 1);
       tc_fence_after();
+      const bool tr = p.trace && blockIdx.x == 0 && itt < 256 && lane == 0;
+      if (tr) p.trace[itt * 12 + 1] = clock64();
       const uint32_t d_base = tmem_base + as * ACC_COLS;
       uint32_t accum = 0;  // 0 for the first MMA of each accumulator of this tile
       int tap0 = 0;
@@ -276,6 +319,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
+        if (tr && sg == 0 && kc == 0) p.trace[itt * 12 + 2] = clock64();
         const uint32_t a_lo_stage = a_lo0 + sa * a_stage16;
         for (int tap = tap0; tap < tap1; ++tap) {
           if (!((tapmask >> tap) & 1u)) continue;
@@ -310,6 +354,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       tap0 = tap1;
       }
       if (leader) umma_commit(&acc_full[as]);
+      if (tr) p.trace[itt * 12 + 3] = clock64();
     }
     __syncwarp();
   } else {
@@ -318,25 +363,27 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     constexpr int CHUNKS = BN / 32, NITEMS = NACC * CHUNKS;
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
-    auto coords = [&](int tile, int it, int& b, int& n, long& idx, bool& valid, uint32_t& tcol) {
-      const int nt = tile % p.n_tiles;
-      const int mb = tile / p.n_tiles;
-      b = mb / p.m_tiles;
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(sbias) + 8192 + (warp - 2) * 2048;
+    auto coords = [&](int tile, int it, EpiItem& e) {
+      uint32_t mb, nt, bq, mt;
+      p.div_n.divmod(tile, mb, nt);
+      p.div_m.divmod(mb, bq, mt);
+      e.b = bq;
       const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 32;
-      const int t = (mb % p.m_tiles) * BM + acc * 128 + q * 32 + lane;
-      n = nt * BN + c0;
-      valid = t < p.g.L;
-      idx = ((long)b * p.g.L + t) * p.g.n_total + n;
-      tcol = acc * BN + c0;
+      const int t = mt * BM + acc * 128 + q * 32;
+      e.n = nt * BN + c0;
+      e.rows_valid = min(32, max(0, p.g.L - t));
+      e.row0 = (long)e.b * p.g.L + t;
+      e.tcol = acc * BN + c0;
     };
     int tile = blockIdx.x, it = hsel < NITEMS ? hsel : NITEMS;  // NITEMS == 1: the second warp of a quadrant idles
     uint32_t itt = 0;
     EpiLoads ld;
-    int b = 0, n = 0; long idx = 0; bool valid = false; uint32_t tcol = 0;
+    EpiItem cur{};
     const bool active = it < NITEMS;
     if (active && tile < p.total_tiles) {
-      coords(tile, it, b, n, idx, valid, tcol);
-      epi_issue_loads(p.ep, idx, valid, ld);
+      coords(tile, it, cur);
+      epi_issue_loads(p.ep, cur, p.g.n_total, lane, ld);
     }
     while (active && tile < p.total_tiles) {
       const bool first = it < 2, last = it + 2 >= NITEMS;
@@ -345,27 +392,37 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         mbar_wait(&acc_full[as], pacc);
         tc_fence_after();
       }
+      const bool tr = p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && first && itt < 256;
+      if (tr) p.trace[itt * 12 + 4] = clock64();
       uint32_t acc[32];
       float v[32];
       __syncwarp();
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + tcol, acc);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + cur.tcol, acc);
+      float4 bv[8];  // bias for this item's columns: read from smem while the TMEM load is in flight
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + cur.n + 4 * j);
       tmem_ld_wait();
-      epi_accumulate(p.ep, sbias, b, n, p.g.n_total, acc, valid, ld, v);
+      if (tr) p.trace[itt * 12 + 5] = clock64();
+      epi_accumulate(p.ep, bv, scratch, cur, p.g.n_total, lane, acc, ld, v);
+      if (tr) p.trace[itt * 12 + 6] = clock64();
       if (last) {  // accumulator fully read: hand the TMEM buffer back before the stores
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);
         ++itt;
       }
-      const long idx_cur = idx; const bool valid_cur = valid;
+      if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 8] = clock64();
+      const EpiItem done = cur;
       // next item: its global reads go out now and land while this item is stored and the next accumulator is awaited
       int ntile = tile, nit = it + 2;
       if (nit >= NITEMS) { nit = hsel; ntile += gridDim.x; }
       if (ntile < p.total_tiles) {
-        coords(ntile, nit, b, n, idx, valid, tcol);
-        epi_issue_loads(p.ep, idx, valid, ld);
+        coords(ntile, nit, cur);
+        epi_issue_loads(p.ep, cur, p.g.n_total, lane, ld);
       }
-      epi_store(p.ep, idx_cur, valid_cur, v);
+      if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 9] = clock64();
+      epi_store(p.ep, scratch, done, p.g.n_total, lane, v);
+      if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 7] = clock64();
       tile = ntile; it = nit;
     }
     if (!active) {  // idle second warp still has to release the accumulator buffers it never reads
@@ -440,6 +497,7 @@ static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
 int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* xs, const __nv_bfloat16* w,
                  int num_sms, int desc_mode) {
   const bool force_streaming = (desc_mode & 2) != 0;  // test knob: exercise the streamed-weights path everywhere
+  pl->no_res_prefetch = (desc_mode & 4) != 0;        // experiment knob: skip the TMA L2 prefetch of residual tiles
   desc_mode &= 1;
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
   VD_CHECK(g.n_total % 32 == 0, "conv_tc: output columns must be a multiple of 32");
@@ -471,8 +529,11 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   p.m_tiles = (g.L + bm - 1) / bm;
   p.n_tiles = g.n_total / bn;
   p.total_tiles = g.B * p.m_tiles * p.n_tiles;
+  p.div_n.init(p.n_tiles);
+  p.div_m.init(p.m_tiles);
   p.desc_mode = desc_mode;
   p.res_prefetch = 0;
+  p.trace = nullptr;
   pl->bn = bn;
   pl->kc = kc;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
@@ -492,7 +553,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
     p.nb_stages = std::min(kMaxNB, (kSmemBudget - 2 * p.a_stage_bytes) / b_stage);
     p.b_region_bytes = p.nb_stages * b_stage;
   }
-  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + (size_t)g.n_total * 4;
+  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + 8192 + 16384;
   for (int sg = 0; sg < kMaxSeg; ++sg) {
     if (encode_3d(&pl->tm.a[sg], xs[sg < g.nseg ? sg : 0], g.c_in, g.L, g.B, kc, 64)) return 1;
     pl->tm.r[sg] = pl->tm.a[sg];  // placeholder until a residual is bound
@@ -517,7 +578,7 @@ int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep) {
 int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) {
   pl.p.ep = ep;
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
-  pl.p.res_prefetch = ep.nres > 0 ? 1 : 0;
+  pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch) ? 1 : 0;
   switch (pl.bn * 100 + pl.kc) {
     case 25664: return launch_inst<256, 64>(pl, stream);
     case 12864: return launch_inst<128, 64>(pl, stream);

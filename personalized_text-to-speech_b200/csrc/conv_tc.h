@@ -7,6 +7,25 @@
 
 namespace vd {
 
+// Division by a launch-time constant without the ~150-cycle integer-divide sequence (Granlund-Montgomery round-up
+// method; exact for dividends below 2^31, which tile indices always are).
+struct FastDiv {
+  uint32_t mul, shr, div;
+  void init(uint32_t d) {
+    div = d;
+    shr = 0;
+    while ((1u << shr) < d) ++shr;
+    mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << shr) - d)) / d) + 1;
+  }
+#ifdef __CUDACC__
+  __device__ __forceinline__ uint32_t quot(uint32_t n) const { return (__umulhi(mul, n) + n) >> shr; }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = quot(n);
+    r = n - q * div;
+  }
+#endif
+};
+
 struct ConvTcParams {
   ConvGeom g;
   ConvEpilogue ep;
@@ -20,8 +39,10 @@ struct ConvTcParams {
   int m_tiles;                // per utterance
   int n_tiles;
   int total_tiles;
+  FastDiv div_n, div_m;       // tile -> (n-tile, m-block) -> (utterance, m-tile)
   uint32_t tap_delta16[kMaxTaps];  // (tap_off - seg_halo_lo) * row_bytes >> 4: descriptor start-address delta per tap
   int res_prefetch;           // 1: the producer prefetches the residual tiles (tmR) into L2
+  unsigned long long* trace;  // debug: per-tile clock64 stamps of CTA 0 ([tile][8]) or null
   int desc_mode;              // debug knob for the A descriptor base-offset field (0 = none)
 };
 
@@ -37,6 +58,7 @@ struct ConvTcPlan {
   ConvTcParams p;
   int bn, kc;
   int grid;
+  bool no_res_prefetch;
   size_t smem;
 };
 

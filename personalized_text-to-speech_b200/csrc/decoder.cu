@@ -36,6 +36,7 @@
 namespace vd {
 
 static thread_local std::string g_err;
+static unsigned long long* g_trace_buffer = nullptr;  // vitsdec_debug_set_trace: device buffer [256][8] of clock64 stamps
 void set_error(const std::string& msg) { g_err = msg; }
 
 typedef __nv_bfloat16 bf16;
@@ -775,7 +776,9 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
     if (impl == 0) {
       ConvTcPlan pl{};
       const bf16* xs[kMaxSeg] = {static_cast<const bf16*>(x), nullptr, nullptr, nullptr};
-      rc = plan_conv_tc(&pl, g, xs, l.w, prop.multiProcessorCount, desc_mode) || launch_conv_tc(pl, e, st);
+      rc = plan_conv_tc(&pl, g, xs, l.w, prop.multiProcessorCount, desc_mode);
+      pl.p.trace = g_trace_buffer;
+      rc = rc || launch_conv_tc(pl, e, st);
     } else {
       const bf16* xs[kMaxSeg] = {static_cast<const bf16*>(x), nullptr, nullptr, nullptr};
       rc = launch_conv_simt(g, e, xs, l.w, st);
@@ -785,6 +788,11 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
   cudaFree(scale); cudaFree(l.w); cudaFree(l.bias);
   if (!rc && se != cudaSuccess) { set_error(std::string("op_conv: ") + cudaGetErrorString(se)); rc = 1; }
   return rc;
+}
+
+int vitsdec_debug_set_trace(void* trace_dev) {
+  g_trace_buffer = static_cast<unsigned long long*>(trace_dev);
+  return 0;
 }
 
 int vitsdec_op_conv1d(int device, const void* x, const float* w, const float* bias, const void* res, float res_gain,
