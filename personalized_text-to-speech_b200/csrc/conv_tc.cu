@@ -22,7 +22,8 @@ namespace vd {
 
 constexpr int kMaxNA = 8;      // activation-chunk stages (runtime count <= this)
 constexpr int kMaxNB = 8;      // weight-tile stages when weights are streamed
-constexpr int kEpiWarps = 8;   // two warps per TMEM lane quadrant
+constexpr int kEpiWarps = 16;  // four warps per TMEM lane quadrant: the epilogue is instruction-latency bound, TLP hides it
+constexpr int kIW = 16;        // epilogue work item: 32 rows (TMEM lanes of one warp) x kIW output columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - 8192 /*bias*/ - 16384 /*scratch*/;
 
@@ -38,21 +39,21 @@ struct TcCfg {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
-// Epilogue work item = 32 consecutive output columns of one row per thread.  Global reads (residual, MRF
-// accumulator) are issued one item AHEAD of their use so their DRAM/L2 latency overlaps the TMEM load, the math
-// and the stores of the current item (the epilogue is otherwise latency-bound: one 64-byte load per thread).
-// Per-warp 2 KB transpose scratch: a 32-row x 64-byte item, 16-byte chunks XOR-swizzled so that both access patterns
+// Epilogue work item = 32 rows x 16 output columns per warp (one row per thread).  Global reads (residuals) are
+// issued one item AHEAD of their use so their DRAM/L2 latency overlaps the TMEM load, the math and the stores of the
+// current item.  Sixteen epilogue warps (four per scheduler) because the per-item instruction stream is a long
+// dependent chain: with two warps per scheduler it ran at ~7 cycles/instruction and bounded every k=3 layer
+// (profiles/r01_trace_probe.txt).
+//
+// Per-warp 1 KB transpose scratch: a 32-row x 32-byte item, 16-byte chunks XOR-swizzled so that both access patterns
 // below are bank-conflict free.  Threads OWN rows for the math (TMEM lane == row), but global memory wants each warp
-// instruction to cover contiguous 64-byte row segments (8 rows x 64 B per LDG/STG.128 instead of 32 rows x 16 B):
-// with the row-owner mapping every instruction touched 32 different 128-byte lines and the LSU, not HBM, set the
-// streaming ceiling (~4.4 TB/s; profiles/r01_stream_probe.txt).
-__device__ __forceinline__ uint32_t scr_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+// instruction to cover contiguous row segments (16 rows x 32 B per LDG/STG.128 instead of 32 rows x 16 B).
+__device__ __forceinline__ uint32_t scr_off(int row, int chunk) { return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4); }
 
-struct EpiLoads {
-  uint4 res[kMaxSeg - 1][4];  // residual tensors, COALESCED mapping: element i = row 8*i + lane/4, chunk lane%4
-  float4 mrf[8];              // fp32 MRF accumulator (fallback path only), row-owner mapping
-};
 constexpr int kMaxRes = kMaxSeg - 1;
+struct EpiLoads {
+  uint4 res[kMaxRes][2];  // residual tensors, COALESCED mapping: element j = row 16*j + lane/2, chunk lane%2
+};
 
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
   uint4 r;
@@ -60,130 +61,136 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
-__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
-  float4 r;
-  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
 
-// One epilogue work item: rows [row0, row0+32) x columns [n, n+32) of utterance b; rows_valid of them exist.
+// One epilogue work item: rows [row0, row0+32) x columns [n, n+kIW) of utterance b; rows_valid of them exist.
 struct EpiItem {
   int b, n, rows_valid;
   long row0;       // b*L + t of lane 0's row
   uint32_t tcol;   // TMEM column of the item inside its accumulator buffer
 };
 
+// EPI specialisation: straight-line epilogue code for the common cases (the generic path re-tests half a dozen
+// launch constants per item, and a lone warp pays ~20-30 cycles per resolved branch):
+//   0 generic (runtime flags: per-utterance bias, any residual count, fp32 MRF fallback)
+//   1 plain (bias + leaky-relu)      2 one residual      3 three residuals + 1/nk scale (fused MRF)
+template <int EPI>
+__device__ __forceinline__ bool epi_has_res(const ConvEpilogue& ep, int i) {
+  if constexpr (EPI == 0) return i < ep.nres;
+  if constexpr (EPI == 1) return false;
+  if constexpr (EPI == 2) return i < 1;
+  return i < 3;
+}
+
+template <int EPI>
 __device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, const EpiItem& it, int n_total, int lane,
                                                 EpiLoads& ld) {
 #pragma unroll
   for (int i = 0; i < kMaxRes; ++i) {
-    if (i < ep.nres) {
+    if (epi_has_res<EPI>(ep, i)) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int row = 8 * j + (lane >> 2);
+      for (int j = 0; j < 2; ++j) {
+        const int row = 16 * j + (lane >> 1);
         if (row < it.rows_valid)
           ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + (it.row0 + row) * n_total + it.n) +
-                                      (lane & 3));
+                                      (lane & 1));
       }
     }
   }
-  if ((ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) && lane < it.rows_valid) {
-    const float4* mp = reinterpret_cast<const float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ld.mrf[j] = ld_stream_f4(mp + j);
-  }
 }
 
-// v = acc + bias (+ per-utterance bias) (+ residuals) (+ MRF accumulator): everything that consumes `ld`
-__device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const float4 (&bias)[8], uint8_t* scratch,
-                                               const EpiItem& it, int n_total, int lane, const uint32_t (&acc)[32],
-                                               const EpiLoads& ld, float (&v)[32]) {
+// v = acc + bias (+ per-utterance bias) (+ residuals) (+ MRF accumulator)
+template <int EPI>
+__device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const float4 (&bias)[4], uint8_t* scratch,
+                                               const EpiItem& it, int n_total, int lane, float res_gain,
+                                               const uint32_t (&acc)[kIW], const EpiLoads& ld, float (&v)[kIW]) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
+  for (int j = 0; j < kIW; j += 4) {
     const float4 bv = bias[j >> 2];
     v[j + 0] = __uint_as_float(acc[j + 0]) + bv.x;
     v[j + 1] = __uint_as_float(acc[j + 1]) + bv.y;
     v[j + 2] = __uint_as_float(acc[j + 2]) + bv.z;
     v[j + 3] = __uint_as_float(acc[j + 3]) + bv.w;
   }
-  if (ep.bias_b) {
+  if (EPI == 0 && ep.bias_b) {
     const float* bb = ep.bias_b + (long)it.b * n_total + it.n;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < kIW; j += 4) {
       const float4 bv = __ldg(reinterpret_cast<const float4*>(bb + j));
       v[j + 0] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
     }
   }
 #pragma unroll
   for (int i = 0; i < kMaxRes; ++i) {
-    if (i < ep.nres) {
+    if (epi_has_res<EPI>(ep, i)) {
       // coalesced registers -> scratch -> row-owner registers
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(scratch + scr_off(8 * j + (lane >> 2), lane & 3)) = ld.res[i][j];
+      for (int j = 0; j < 2; ++j)
+        *reinterpret_cast<uint4*>(scratch + scr_off(16 * j + (lane >> 1), lane & 1)) = ld.res[i][j];
       __syncwarp();
-      uint4 mine[4];
+      uint4 mine[2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) mine[c] = *reinterpret_cast<const uint4*>(scratch + scr_off(lane, c));
+      for (int c = 0; c < 2; ++c) mine[c] = *reinterpret_cast<const uint4*>(scratch + scr_off(lane, c));
       __syncwarp();
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&mine[q]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 a = __bfloat1622float2(r2[e]);
-          v[q * 8 + e * 2 + 0] += a.x >= 0.f ? a.x : a.x * ep.res_gain;
-          v[q * 8 + e * 2 + 1] += a.y >= 0.f ? a.y : a.y * ep.res_gain;
+          v[q * 8 + e * 2 + 0] += a.x >= 0.f ? a.x : a.x * res_gain;
+          v[q * 8 + e * 2 + 1] += a.y >= 0.f ? a.y : a.y * res_gain;
         }
       }
     }
   }
-  if (ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) {
+  if (EPI == 0 && (ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) && lane < it.rows_valid) {  // fp32 fallback path
+    const float4* mp = reinterpret_cast<const float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[4 * j] += ld.mrf[j].x; v[4 * j + 1] += ld.mrf[j].y; v[4 * j + 2] += ld.mrf[j].z; v[4 * j + 3] += ld.mrf[j].w;
+    for (int j = 0; j < kIW / 4; ++j) {
+      const float4 m = mp[j];
+      v[4 * j] += m.x; v[4 * j + 1] += m.y; v[4 * j + 2] += m.z; v[4 * j + 3] += m.w;
     }
   }
 }
 
+template <int EPI>
 __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int n_total,
-                                          int lane, float (&v)[32]) {
-  if (ep.mrf_mode == 1 || ep.mrf_mode == 2) {
+                                          int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
+  if (EPI == 0 && (ep.mrf_mode == 1 || ep.mrf_mode == 2)) {
     if (lane < it.rows_valid) {
       float4* mp = reinterpret_cast<float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) mp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < kIW / 4; ++j) mp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     return;
   }
-  if (ep.mrf_mode == 3) {
+  if (EPI == 3 || (EPI == 0 && ep.mrf_mode == 3)) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= ep.mrf_scale;
+    for (int j = 0; j < kIW; ++j) v[j] *= mrf_scale;
   }
-  // row-owner registers -> scratch -> coalesced 64-byte row segments
+  // row-owner registers -> scratch -> coalesced 32-byte row segments
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2; ++q) {
     uint4 ov;
     __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      o2[e] = __floats2bfloat162_rn(fmaxf(v[q * 8 + e * 2], v[q * 8 + e * 2] * ep.out_slope),
-                                    fmaxf(v[q * 8 + e * 2 + 1], v[q * 8 + e * 2 + 1] * ep.out_slope));  // slope in (0,1]
+      o2[e] = __floats2bfloat162_rn(fmaxf(v[q * 8 + e * 2], v[q * 8 + e * 2] * out_slope),
+                                    fmaxf(v[q * 8 + e * 2 + 1], v[q * 8 + e * 2 + 1] * out_slope));  // slope in (0,1]
     *reinterpret_cast<uint4*>(scratch + scr_off(lane, q)) = ov;
   }
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int row = 8 * j + (lane >> 2);
-    const uint4 ov = *reinterpret_cast<const uint4*>(scratch + scr_off(row, lane & 3));
+  for (int j = 0; j < 2; ++j) {
+    const int row = 16 * j + (lane >> 1);
+    const uint4 ov = *reinterpret_cast<const uint4*>(scratch + scr_off(row, lane & 1));
     if (row < it.rows_valid)
-      *(reinterpret_cast<uint4*>(ep.out + (it.row0 + row) * n_total + it.n) + (lane & 3)) = ov;
+      *(reinterpret_cast<uint4*>(ep.out + (it.row0 + row) * n_total + it.n) + (lane & 1)) = ov;
   }
   __syncwarp();
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ ConvTcParams p) {
@@ -359,34 +366,39 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
-    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split a tile's items by parity.
-    constexpr int CHUNKS = BN / 32, NITEMS = NACC * CHUNKS;
+    // TMEM lane quadrant = warp % 4 (hardware rule); the four warps of a quadrant take a tile's items round-robin.
+    constexpr int CHUNKS = BN / kIW, NITEMS = NACC * CHUNKS, NW = kEpiWarps / 4;
+    static_assert(NITEMS >= NW, "every epilogue warp needs at least one item per tile");
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
-    uint8_t* scratch = reinterpret_cast<uint8_t*>(sbias) + 8192 + (warp - 2) * 2048;
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(sbias) + 8192 + (warp - 2) * 1024;
+    // launch constants live in registers for the whole loop (each read of the __grid_constant__ block is an LDC)
+    const FastDiv div_n = p.div_n, div_m = p.div_m;
+    const int L = p.g.L, n_total = p.g.n_total, total_tiles = p.total_tiles, tile_step = gridDim.x;
+    const float out_slope = p.ep.out_slope, mrf_scale = p.ep.mrf_scale, res_gain = p.ep.res_gain;
+    ConvEpilogue ep = p.ep;
     auto coords = [&](int tile, int it, EpiItem& e) {
       uint32_t mb, nt, bq, mt;
-      p.div_n.divmod(tile, mb, nt);
-      p.div_m.divmod(mb, bq, mt);
+      div_n.divmod(tile, mb, nt);
+      div_m.divmod(mb, bq, mt);
       e.b = bq;
-      const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 32;
+      const int acc = it / CHUNKS, c0 = (it % CHUNKS) * kIW;
       const int t = mt * BM + acc * 128 + q * 32;
       e.n = nt * BN + c0;
-      e.rows_valid = min(32, max(0, p.g.L - t));
-      e.row0 = (long)e.b * p.g.L + t;
+      e.rows_valid = min(32, max(0, L - t));
+      e.row0 = (long)e.b * L + t;
       e.tcol = acc * BN + c0;
     };
-    int tile = blockIdx.x, it = hsel < NITEMS ? hsel : NITEMS;  // NITEMS == 1: the second warp of a quadrant idles
+    int tile = blockIdx.x, it = hsel;
     uint32_t itt = 0;
     EpiLoads ld;
     EpiItem cur{};
-    const bool active = it < NITEMS;
-    if (active && tile < p.total_tiles) {
+    if (tile < total_tiles) {
       coords(tile, it, cur);
-      epi_issue_loads(p.ep, cur, p.g.n_total, lane, ld);
+      epi_issue_loads<EPI>(ep, cur, n_total, lane, ld);
     }
-    while (active && tile < p.total_tiles) {
-      const bool first = it < 2, last = it + 2 >= NITEMS;
+    while (tile < total_tiles) {
+      const bool first = it < NW, last = it + NW >= NITEMS;
       const uint32_t as = itt % C::NBUF, pacc = (itt / C::NBUF) & 1;
       if (first) {
         mbar_wait(&acc_full[as], pacc);
@@ -394,16 +406,16 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       }
       const bool tr = p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && first && itt < 256;
       if (tr) p.trace[itt * 12 + 4] = clock64();
-      uint32_t acc[32];
-      float v[32];
+      uint32_t acc[kIW];
+      float v[kIW];
       __syncwarp();
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + cur.tcol, acc);
-      float4 bv[8];  // bias for this item's columns: read from smem while the TMEM load is in flight
+      tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + cur.tcol, acc);
+      float4 bv[kIW / 4];  // bias for this item's columns: read from smem while the TMEM load is in flight
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + cur.n + 4 * j);
+      for (int j = 0; j < kIW / 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + cur.n + 4 * j);
       tmem_ld_wait();
       if (tr) p.trace[itt * 12 + 5] = clock64();
-      epi_accumulate(p.ep, bv, scratch, cur, p.g.n_total, lane, acc, ld, v);
+      epi_accumulate<EPI>(ep, bv, scratch, cur, n_total, lane, res_gain, acc, ld, v);
       if (tr) p.trace[itt * 12 + 6] = clock64();
       if (last) {  // accumulator fully read: hand the TMEM buffer back before the stores
         tc_fence_before();
@@ -414,21 +426,16 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 8] = clock64();
       const EpiItem done = cur;
       // next item: its global reads go out now and land while this item is stored and the next accumulator is awaited
-      int ntile = tile, nit = it + 2;
-      if (nit >= NITEMS) { nit = hsel; ntile += gridDim.x; }
-      if (ntile < p.total_tiles) {
+      int ntile = tile, nit = it + NW;
+      if (nit >= NITEMS) { nit = hsel; ntile += tile_step; }
+      if (ntile < total_tiles) {
         coords(ntile, nit, cur);
-        epi_issue_loads(p.ep, cur, p.g.n_total, lane, ld);
+        epi_issue_loads<EPI>(ep, cur, n_total, lane, ld);
       }
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 9] = clock64();
-      epi_store(p.ep, scratch, done, p.g.n_total, lane, v);
+      epi_store<EPI>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 7] = clock64();
       tile = ntile; it = nit;
-    }
-    if (!active) {  // idle second warp still has to release the accumulator buffers it never reads
-      for (; tile < p.total_tiles; tile += gridDim.x, ++itt) {
-        if (lane == 0) mbar_arrive(&acc_empty[itt % C::NBUF]);
-      }
     }
   }
 
@@ -482,16 +489,30 @@ static int encode_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1,
   return 0;
 }
 
-template <int BN, int KC>
-static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
+template <int BN, int KC, int EPI>
+static int launch_one(const ConvTcPlan& pl, cudaStream_t stream) {
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
-    VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KC><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
+  conv_tc_kernel<BN, KC, EPI><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Specialised epilogues exist for the shapes of the shipped configuration; everything else takes the generic one.
+template <int BN, int KC, bool SPECIALISED>
+static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
+  const ConvEpilogue& e = pl.p.ep;
+  if constexpr (SPECIALISED) {
+    const bool simple = e.bias_b == nullptr && (e.mrf_mode == 0 || (e.mrf_mode == 3 && e.mrf == nullptr));
+    if (simple && e.mrf_mode == 0 && e.nres == 0) return launch_one<BN, KC, 1>(pl, stream);
+    if (simple && e.mrf_mode == 0 && e.nres == 1) return launch_one<BN, KC, 2>(pl, stream);
+    if (simple && e.mrf_mode == 3 && e.nres == 3) return launch_one<BN, KC, 3>(pl, stream);
+  }
+  return launch_one<BN, KC, 0>(pl, stream);
 }
 
 int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* xs, const __nv_bfloat16* w,
@@ -580,14 +601,14 @@ int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) 
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
   pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch) ? 1 : 0;
   switch (pl.bn * 100 + pl.kc) {
-    case 25664: return launch_inst<256, 64>(pl, stream);
-    case 12864: return launch_inst<128, 64>(pl, stream);
-    case 6464:  return launch_inst<64, 64>(pl, stream);
-    case 3264:  return launch_inst<32, 64>(pl, stream);
-    case 25632: return launch_inst<256, 32>(pl, stream);
-    case 12832: return launch_inst<128, 32>(pl, stream);
-    case 6432:  return launch_inst<64, 32>(pl, stream);
-    case 3232:  return launch_inst<32, 32>(pl, stream);
+    case 25664: return launch_inst<256, 64, true>(pl, stream);
+    case 12864: return launch_inst<128, 64, true>(pl, stream);
+    case 6464:  return launch_inst<64, 64, true>(pl, stream);
+    case 3264:  return launch_inst<32, 64, false>(pl, stream);
+    case 25632: return launch_inst<256, 32, false>(pl, stream);
+    case 12832: return launch_inst<128, 32, false>(pl, stream);
+    case 6432:  return launch_inst<64, 32, false>(pl, stream);
+    case 3232:  return launch_inst<32, 32, true>(pl, stream);
   }
   set_error("conv_tc: no kernel instance");
   return 1;
