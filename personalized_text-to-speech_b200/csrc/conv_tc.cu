@@ -190,7 +190,80 @@ __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scrat
   __syncwarp();
 }
 
-template <int BN, int KC, int EPI>
+// ---- SWAP epilogue (channels on TMEM lanes, time on TMEM columns) --------------------------------------------------
+// Item = 32 channels (one per thread) x 16 time rows.  Global memory is [time][channel]: the item is 16 rows of 64
+// bytes.  Scratch holds it row-major (64-byte rows, chunk-swizzled); the thread<->time transposition happens in the
+// 2-byte shared-memory accesses, global accesses stay 16 bytes per lane over 8 rows x 64 B per instruction.
+__device__ __forceinline__ uint32_t scrT_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+
+template <int EPI>
+__device__ __forceinline__ void epiT_issue_loads(const ConvEpilogue& ep, const EpiItem& it, int n_total, int lane,
+                                                 EpiLoads& ld) {
+#pragma unroll
+  for (int i = 0; i < kMaxRes; ++i) {
+    if (epi_has_res<EPI>(ep, i)) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int row = 8 * j + (lane >> 2);
+        if (row < it.rows_valid)
+          ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + (it.row0 + row) * n_total + it.n) +
+                                      (lane & 3));
+      }
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epiT_accumulate(const ConvEpilogue& ep, float bias, uint8_t* scratch, const EpiItem& it,
+                                                int n_total, int lane, float res_gain, const uint32_t (&acc)[kIW],
+                                                const EpiLoads& ld, float (&v)[kIW]) {
+  if (EPI == 0 && ep.bias_b) bias += __ldg(ep.bias_b + (long)it.b * n_total + it.n + lane);
+#pragma unroll
+  for (int j = 0; j < kIW; ++j) v[j] = __uint_as_float(acc[j]) + bias;
+  const uint32_t mine = ((lane >> 3) << 4), sub = (lane & 7) * 2;  // my channel inside a 64-byte row
+#pragma unroll
+  for (int i = 0; i < kMaxRes; ++i) {
+    if (epi_has_res<EPI>(ep, i)) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        *reinterpret_cast<uint4*>(scratch + scrT_off(8 * j + (lane >> 2), lane & 3)) = ld.res[i][j];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kIW; ++j) {
+        const uint16_t raw = *reinterpret_cast<const uint16_t*>(scratch + j * 64 + (mine ^ (((j >> 1) & 3) << 4)) + sub);
+        const float a = __uint_as_float((uint32_t)raw << 16);
+        v[j] += a >= 0.f ? a : a * res_gain;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int n_total,
+                                           int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
+  if (EPI == 3 || (EPI == 0 && ep.mrf_mode == 3)) {
+#pragma unroll
+    for (int j = 0; j < kIW; ++j) v[j] *= mrf_scale;
+  }
+  const uint32_t mine = ((lane >> 3) << 4), sub = (lane & 7) * 2;
+#pragma unroll
+  for (int j = 0; j < kIW; ++j) {
+    const __nv_bfloat16 o = __float2bfloat16_rn(fmaxf(v[j], v[j] * out_slope));
+    *reinterpret_cast<__nv_bfloat16*>(scratch + j * 64 + (mine ^ (((j >> 1) & 3) << 4)) + sub) = o;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int row = 8 * j + (lane >> 2);
+    const uint4 ov = *reinterpret_cast<const uint4*>(scratch + scrT_off(row, lane & 3));
+    if (row < it.rows_valid)
+      *(reinterpret_cast<uint4*>(ep.out + (it.row0 + row) * n_total + it.n) + (lane & 3)) = ov;
+  }
+  __syncwarp();
+}
+
+template <int BN, int KC, int EPI, bool SWAP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ ConvTcParams p) {
@@ -297,7 +370,10 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     // The whole warp runs this (warp-uniform) control flow; only the elected lane issues tcgen05.mma / commit.
     // Descriptors are (lo, hi) pairs: hi is a constant, lo advances by precomputed 16-byte-unit deltas, so the
     // issue loop is a handful of uniform-register adds per MMA.
-    constexpr uint32_t idesc = umma_idesc_f16(BN, false);
+    // SWAP: D[channel, time] = W[channel, ci] * X[time, ci]^T -- the 128 output channels are the MMA's M, the 256 time
+    // rows its N, so one instruction reads 4 KB of weights + 8 KB of activations per 128 cycles (96 B/cycle of
+    // shared-memory operand traffic) instead of 2 x (4 KB + 4 KB) per 2 x 64 cycles (128 B/cycle, the smem limit).
+    constexpr uint32_t idesc = umma_idesc_f16(SWAP ? 256 : BN, false);
     constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
     const uint32_t leader = elect_one();
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), b_lo0 = umma_desc_lo(smem_u32(smemB));
@@ -341,12 +417,19 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
             b_lo = b_lo0 + sb * (B_STAGE >> 4);
           }
           const uint32_t a_lo = a_lo_stage + p.tap_delta16[tap];
+          if constexpr (SWAP) {
 #pragma unroll
-          for (int acc = 0; acc < NACC; ++acc) {
+            for (int k = 0; k < KC / 16; ++k)
+              umma_f16_lohi(d_base, b_lo + ((k * 32) >> 4), desc_hi, a_lo + ((k * 32) >> 4), desc_hi, idesc,
+                            k == 0 ? accum : 1u, leader);
+          } else {
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              umma_f16_lohi(d_base + acc * BN, a_lo + ((acc * 128 * ROWB + k * 32) >> 4), desc_hi, b_lo + ((k * 32) >> 4),
-                            desc_hi, idesc, k == 0 ? accum : 1u, leader);
+            for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                umma_f16_lohi(d_base + acc * BN, a_lo + ((acc * 128 * ROWB + k * 32) >> 4), desc_hi,
+                              b_lo + ((k * 32) >> 4), desc_hi, idesc, k == 0 ? accum : 1u, leader);
+              }
             }
           }
           accum = 1;
@@ -367,7 +450,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
   } else {
     // ------------------------------------------------------------ epilogue warps
     // TMEM lane quadrant = warp % 4 (hardware rule); the four warps of a quadrant take a tile's items round-robin.
-    constexpr int CHUNKS = BN / kIW, NITEMS = NACC * CHUNKS, NW = kEpiWarps / 4;
+    static_assert(!SWAP || (BN == 128 && NACC == 2), "SWAP tiles are 128 channels x 256 time rows");
+    constexpr int CHUNKS = BN / kIW, NITEMS = SWAP ? 256 / kIW : NACC * CHUNKS, NW = kEpiWarps / 4;
     static_assert(NITEMS >= NW, "every epilogue warp needs at least one item per tile");
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
@@ -382,12 +466,24 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       div_n.divmod(tile, mb, nt);
       div_m.divmod(mb, bq, mt);
       e.b = bq;
-      const int acc = it / CHUNKS, c0 = (it % CHUNKS) * kIW;
-      const int t = mt * BM + acc * 128 + q * 32;
-      e.n = nt * BN + c0;
-      e.rows_valid = min(32, max(0, L - t));
-      e.row0 = (long)e.b * L + t;
-      e.tcol = acc * BN + c0;
+      if constexpr (SWAP) {
+        const int t = mt * BM + it * kIW;       // item = 16 time rows (TMEM columns) x this warp's 32 channels
+        e.n = nt * BN + q * 32;
+        e.rows_valid = min(kIW, max(0, L - t));
+        e.row0 = (long)e.b * L + t;
+        e.tcol = it * kIW;
+      } else {
+        const int acc = it / CHUNKS, c0 = (it % CHUNKS) * kIW;
+        const int t = mt * BM + acc * 128 + q * 32;
+        e.n = nt * BN + c0;
+        e.rows_valid = min(32, max(0, L - t));
+        e.row0 = (long)e.b * L + t;
+        e.tcol = acc * BN + c0;
+      }
+    };
+    auto issue = [&](const EpiItem& e, EpiLoads& l) {
+      if constexpr (SWAP) epiT_issue_loads<EPI>(ep, e, n_total, lane, l);
+      else epi_issue_loads<EPI>(ep, e, n_total, lane, l);
     };
     int tile = blockIdx.x, it = hsel;
     uint32_t itt = 0;
@@ -395,7 +491,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     EpiItem cur{};
     if (tile < total_tiles) {
       coords(tile, it, cur);
-      epi_issue_loads<EPI>(ep, cur, n_total, lane, ld);
+      issue(cur, ld);
     }
     while (tile < total_tiles) {
       const bool first = it < NW, last = it + NW >= NITEMS;
@@ -411,11 +507,17 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       __syncwarp();
       tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + cur.tcol, acc);
       float4 bv[kIW / 4];  // bias for this item's columns: read from smem while the TMEM load is in flight
+      float bias_lane = 0.f;
+      if constexpr (SWAP) {
+        bias_lane = sbias[cur.n + lane];
+      } else {
 #pragma unroll
-      for (int j = 0; j < kIW / 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + cur.n + 4 * j);
+        for (int j = 0; j < kIW / 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + cur.n + 4 * j);
+      }
       tmem_ld_wait();
       if (tr) p.trace[itt * 12 + 5] = clock64();
-      epi_accumulate<EPI>(ep, bv, scratch, cur, n_total, lane, res_gain, acc, ld, v);
+      if constexpr (SWAP) epiT_accumulate<EPI>(ep, bias_lane, scratch, cur, n_total, lane, res_gain, acc, ld, v);
+      else epi_accumulate<EPI>(ep, bv, scratch, cur, n_total, lane, res_gain, acc, ld, v);
       if (tr) p.trace[itt * 12 + 6] = clock64();
       if (last) {  // accumulator fully read: hand the TMEM buffer back before the stores
         tc_fence_before();
@@ -430,10 +532,11 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       if (nit >= NITEMS) { nit = hsel; ntile += tile_step; }
       if (ntile < total_tiles) {
         coords(ntile, nit, cur);
-        epi_issue_loads<EPI>(ep, cur, n_total, lane, ld);
+        issue(cur, ld);
       }
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 9] = clock64();
-      epi_store<EPI>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
+      if constexpr (SWAP) epiT_store<EPI>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
+      else epi_store<EPI>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 7] = clock64();
       tile = ntile; it = nit;
     }
@@ -489,17 +592,27 @@ static int encode_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1,
   return 0;
 }
 
-template <int BN, int KC, int EPI>
+template <int BN, int KC, int EPI, bool SWAP = false>
 static int launch_one(const ConvTcPlan& pl, cudaStream_t stream) {
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
-    VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, EPI, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KC, EPI><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
+  conv_tc_kernel<BN, KC, EPI, SWAP><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
+}
+
+// channels-as-M variant (128 channels x 256 time rows per tile); never with the fp32 MRF fallback
+static int launch_swapped(const ConvTcPlan& pl, cudaStream_t stream) {
+  const ConvEpilogue& e = pl.p.ep;
+  const bool simple = e.bias_b == nullptr;
+  if (simple && e.mrf_mode == 0 && e.nres == 0) return launch_one<128, 64, 1, true>(pl, stream);
+  if (simple && e.mrf_mode == 0 && e.nres == 1) return launch_one<128, 64, 2, true>(pl, stream);
+  if (simple && e.mrf_mode == 3 && e.nres == 3) return launch_one<128, 64, 3, true>(pl, stream);
+  return launch_one<128, 64, 0, true>(pl, stream);
 }
 
 // Specialised epilogues exist for the shapes of the shipped configuration; everything else takes the generic one.
@@ -516,9 +629,10 @@ static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
 }
 
 int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* xs, const __nv_bfloat16* w,
-                 int num_sms, int desc_mode) {
+                 int num_sms, int desc_mode, bool allow_swap) {
   const bool force_streaming = (desc_mode & 2) != 0;  // test knob: exercise the streamed-weights path everywhere
   pl->no_res_prefetch = (desc_mode & 4) != 0;        // experiment knob: skip the TMA L2 prefetch of residual tiles
+  const bool force_no_swap = (desc_mode & 8) != 0;   // test knob: keep wide layers on the time-as-M form
   desc_mode &= 1;
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
   VD_CHECK(g.n_total % 32 == 0, "conv_tc: output columns must be a multiple of 32");
@@ -530,6 +644,12 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   for (int c : {256, 128, 64}) {
     if (g.n_total % c == 0) { bn = c; break; }
   }
+  // Wide layers whose weights do not stay resident run channels-as-M (128 channels x 256 time rows): at N=128 the
+  // time-as-M form is bound by shared-memory operand bandwidth, at N=256 by L2 weight streaming.
+  const bool want_swap = allow_swap && kc == 64 && g.n_total % 128 == 0 &&
+                         (size_t)g.ntaps * g.c_in * 128 * 2 > 110 * 1024 && !force_no_swap;
+  if (want_swap) bn = 128;
+  pl->swap = want_swap;
   const int nacc = bn >= 256 ? 1 : 2;
   const int bm = 128 * nacc;
   ConvTcParams& p = pl->p;
@@ -600,6 +720,10 @@ int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) 
   pl.p.ep = ep;
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
   pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch) ? 1 : 0;
+  if (pl.swap) {
+    VD_CHECK(ep.mrf == nullptr, "conv_tc: the channels-as-M variant has no fp32 MRF accumulator path");
+    return launch_swapped(pl, stream);
+  }
   switch (pl.bn * 100 + pl.kc) {
     case 25664: return launch_inst<256, 64, true>(pl, stream);
     case 12864: return launch_inst<128, 64, true>(pl, stream);

@@ -59,13 +59,14 @@ struct ConvTcPlan {
   int bn, kc;
   int grid;
   bool no_res_prefetch;
+  bool swap;        // channels-as-M variant (128 channels x 256 time rows per tile)
   size_t smem;
 };
 
 // Encodes the TMA descriptors for the activation tensors xs[0..g.nseg) (each [B][L][c_in]) and the packed weights
 // `w` [ntaps][n_total][c_in].
 int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* xs, const __nv_bfloat16* w,
-                 int num_sms, int desc_mode);
+                 int num_sms, int desc_mode, bool allow_swap = true);
 int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep);
 int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream);
 int launch_conv_simt(const ConvGeom& g, const ConvEpilogue& ep, const __nv_bfloat16* const* xs,

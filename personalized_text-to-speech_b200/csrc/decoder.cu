@@ -256,7 +256,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     for (int i = 0; i < g.nseg; ++i) s.xs[i] = xs[i];
     s.tc.p.g = g;
     if (d->impl == 0) {
-      if (plan_conv_tc(&s.tc, g, s.xs, ly.w, d->num_sms, d->desc_mode)) return 1;
+      if (plan_conv_tc(&s.tc, g, s.xs, ly.w, d->num_sms, d->desc_mode, ep.mrf == nullptr)) return 1;
       if (bind_residual_tc(s.tc, ep)) return 1;
     }
     pl.steps.push_back(s);

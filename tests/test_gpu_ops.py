@@ -108,3 +108,19 @@ def test_streamed_and_resident_weight_paths_agree_bitwise():
         a = ops.conv1d_cl(x, w, b, dilation=d, out_slope=0.1, impl=0, desc_mode=0)
         c = ops.conv1d_cl(x, w, b, dilation=d, out_slope=0.1, impl=0, desc_mode=2)
         assert torch.equal(a, c)
+
+
+def test_channels_as_m_and_time_as_m_forms_agree_bitwise():
+    """desc_mode bit 3 keeps wide layers on the time-as-M tile; the default for them is channels-as-M (SWAP)."""
+    torch.manual_seed(4)
+    dev = torch.device("cuda:0")
+    for (ci, co, k, d, use_res) in ((128, 128, 7, 3, True), (256, 256, 11, 5, True), (192, 512, 7, 1, False),
+                                    (256, 256, 3, 1, False)):
+        x = torch.randn(2, 1111, ci, device=dev).bfloat16()
+        w = torch.randn(co, ci, k, device=dev) / (ci * k) ** 0.5
+        b = torch.randn(co, device=dev) * 0.1
+        res = torch.randn(2, 1111, co, device=dev).bfloat16() if use_res else None
+        a = ops.conv1d_cl(x, w, b, dilation=d, res=res, out_slope=0.1, impl=0, desc_mode=0)
+        c = ops.conv1d_cl(x, w, b, dilation=d, res=res, out_slope=0.1, impl=0, desc_mode=8)
+        assert torch.equal(a, c)
+        assert rel_err(a, ref_conv(x, w, b, d, res, 10.0, 0.1)) < REL_TOL

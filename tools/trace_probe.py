@@ -12,8 +12,11 @@ ops = importlib.import_module("personalized_text-to-speech_b200.ops")
 lib = vitsdec._capi.lib()
 dev = torch.device("cuda:0")
 trace = torch.zeros(256 * 12, dtype=torch.int64, device=dev)
-for (C, L, k, use_res) in ((32, 220672, 1, 0), (32, 220672, 3, 0), (32, 220672, 3, 1), (64, 110336, 3, 0),
-                           (128, 55168, 3, 0), (128, 55168, 7, 0)):
+CASES = ((32, 220672, 1, 0), (32, 220672, 3, 0), (32, 220672, 3, 1), (64, 110336, 3, 0),
+         (128, 55168, 3, 0), (128, 55168, 7, 0))
+if len(sys.argv) > 1 and sys.argv[1] == "wide":
+    CASES = ((128, 55168, 7, 0), (128, 55168, 11, 1), (256, 6896, 3, 0), (256, 6896, 11, 0))
+for (C, L, k, use_res) in CASES:
     x = torch.randn(16, L, C, device=dev).bfloat16()
     r = torch.randn(16, L, C, device=dev).bfloat16() if use_res else None
     w = torch.randn(C, C, k, device=dev) / (C * k) ** 0.5
