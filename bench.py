@@ -56,9 +56,12 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -67,7 +70,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.05):
+                continue  # only samples taken DURING the timed region
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -184,23 +189,25 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~0.2 s to start: launch it before the warm-up, keep only timed-region samples
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             y = G(z, g)
         barrier()
         # ---- device-resident timing (value) + live conv-kernel timing (roofline)
         G.set_option("profile", 1)
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_begin = sampler.mark()
         e0.record()
         for _ in range(args.steps):
             y = G(z, g)
         e1.record()
         barrier()
-        clocks = sampler.stop() if rank == 0 else None
+        t_end = sampler.mark()
+        clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         conv_ms, conv_launches = G.profile_read()
         G.set_option("profile", 0)

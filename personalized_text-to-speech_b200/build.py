@@ -18,6 +18,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
 ]
+if os.environ.get("VITSDEC_TRACE") == "1":   # debug build with per-tile clock64 trace hooks (tools/trace_probe.py)
+    NVCC_FLAGS = NVCC_FLAGS + ["-DVITSDEC_TRACE=1"]
 
 
 def _nvcc():

@@ -22,6 +22,10 @@ namespace vd {
 
 constexpr int kMaxNA = 8;      // activation-chunk stages (runtime count <= this)
 constexpr int kMaxNB = 8;      // weight-tile stages when weights are streamed
+#ifndef VITSDEC_TRACE
+#define VITSDEC_TRACE 0   // 1: build with the per-tile clock64 trace hooks (tools/trace_probe.py); costs ~10 % in the epilogue
+#endif
+constexpr bool kTrace = VITSDEC_TRACE != 0;
 constexpr int kEpiWarps = 16;  // four warps per TMEM lane quadrant: the epilogue is instruction-latency bound, TLP hides it
 constexpr int kIW = 16;        // epilogue work item: 32 rows (TMEM lanes of one warp) x kIW output columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
@@ -344,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
           for (int kc = 0; kc < nkc; ++kc) {
             const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
             mbar_wait(&a_empty[sa], pa ^ 1);
-            if (p.trace && blockIdx.x == 0 && sg == 0 && kc == 0 && tile / gridDim.x < 256)
+            if (kTrace && p.trace && blockIdx.x == 0 && sg == 0 && kc == 0 && tile / gridDim.x < 256)
               p.trace[(tile / gridDim.x) * 12 + 0] = clock64();
             mbar_expect_tx(&a_full[sa], nbx * 64 * ROWB);
             for (int bx = 0; bx < nbx; ++bx)
@@ -391,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       const uint32_t as = itt % C::NBUF, pacc = (itt / C::NBUF) & 1;
       mbar_wait(&acc_empty[as], pacc ^ 1);
       tc_fence_after();
-      const bool tr = p.trace && blockIdx.x == 0 && itt < 256 && lane == 0;
+      const bool tr = kTrace && p.trace && blockIdx.x == 0 && itt < 256 && lane == 0;
       if (tr) p.trace[itt * 12 + 1] = clock64();
       const uint32_t d_base = tmem_base + as * ACC_COLS;
       uint32_t accum = 0;  // 0 for the first MMA of each accumulator of this tile
@@ -500,7 +504,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         mbar_wait(&acc_full[as], pacc);
         tc_fence_after();
       }
-      const bool tr = p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && first && itt < 256;
+      const bool tr = kTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && first && itt < 256;
       if (tr) p.trace[itt * 12 + 4] = clock64();
       uint32_t acc[kIW];
       float v[kIW];
