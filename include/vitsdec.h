@@ -95,7 +95,8 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
 
 /* Options: "impl" = 0 tcgen05 tensor-core kernels (default), 1 CUDA-core cross-check kernels (tests only);
  *          "desc_mode" = debug knob of the UMMA descriptor (0 is the correct setting);
- *          "debug_keep" = 1 keep named intermediates for vitsdec_debug_read; "profile" = 1 see below. */
+ *          "debug_keep" = 1 keep named intermediates for vitsdec_debug_read; "profile" = 1 see below;
+ *          "fuse_pairs" = 0 run every ResBlock conv as its own launch (default 1: fused pairs where they fit). */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
 
@@ -124,6 +125,13 @@ VITSDEC_API int vitsdec_debug_set_trace(void* trace_dev);
 VITSDEC_API int vitsdec_op_conv1d(int device, const void* x_dev, const float* w_dev, const float* bias_dev, const void* res_dev,
                       float res_gain, float out_slope, void* y_dev, int batch, int length, int c_in, int c_out,
                       int k, int dilation, int impl, int desc_mode, void* stream);
+
+/* One fused ResBlock1 iteration (modules.py:211-221) on channels-last bf16 a-form activations:
+ *   y = lrelu( conv(k,1)( lrelu( conv(k,dilation)(x) + b1 ) ) + b2 + unlrelu(x), slope ),  x stored as lrelu(., slope).
+ *   w1/w2 fp32 [C, C, k].  Only shapes for which the fused kernel exists (C in {32, 64}). */
+VITSDEC_API int vitsdec_op_resblock_pair(int device, const void* x_dev, const float* w1_dev, const float* b1_dev,
+                                         const float* w2_dev, const float* b2_dev, void* y_dev, int batch, int length,
+                                         int channels, int k, int dilation, float slope, void* stream);
 
 /* Same for ConvTranspose1d(c_in, c_out, k, stride, padding=(k-stride)/2) in polyphase form:
  *   w_dev fp32 [c_in, c_out, k]; y_dev bf16 [batch, length*stride, c_out]. */

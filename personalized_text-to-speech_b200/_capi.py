@@ -61,6 +61,7 @@ SIGNATURES = {
     "vitsdec_debug_read": (_i, [_vp, _cp, _vp, _sz, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp]),
     "vitsdec_debug_set_trace": (_i, [_vp]),
     "vitsdec_op_conv1d": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "vitsdec_op_resblock_pair": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "vitsdec_op_conv_transpose1d": (_i, [_i, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

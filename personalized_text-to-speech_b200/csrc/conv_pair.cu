@@ -1,0 +1,378 @@
+// Fused ResBlock1 pair on the sm_100a tensor cores:
+//     y = lrelu( c2( lrelu( c1(a) + b1 ) ) + b2 + x(a) )          (modules.py:211-221, one loop iteration)
+// with a = lrelu(x) the stored a-form input, c1 = Conv1d(C, C, k, dilation d), c2 = Conv1d(C, C, k, dilation 1).
+//
+// Why: for the narrow stages (C = 32, 64) one conv per launch is bound by HBM and by the epilogue, not by the tensor
+// pipe: every conv reads and writes a 226 MB tensor (16 x 10 s) for a few hundred MACs per element.  Here the
+// intermediate h never leaves the SM: c1's accumulator goes TMEM -> registers (bias, leaky-relu, zero outside the
+// utterance) -> shared memory in the 128B/64B-swizzled K-major layout, where c2's tcgen05.mma reads it as its A
+// operand; the residual x is recovered from the activation tile that is already resident for c1.  HBM traffic per
+// pair drops from 5 tensor passes to 2, launches from 2 to 1.
+//
+// Tile: 256 rows of h per CTA tile (two 128-row accumulators), of which 256 - (k-1) output rows are valid (c2 needs a
+// (k-1)/2 halo of h on each side), so tiles advance by 256 - (k-1) rows.  Both convs' weights stay resident.
+// Pipeline per CTA (tile i): TMA A(i) -> c1(i) -> epi1(i) [h -> smem] -> c2(i) -> epi2(i) [-> global], with c1(i+1)
+// issued before c2(i) so the tensor pipe works on the next tile while the epilogue warps build h.
+#include <algorithm>
+
+#include "common.cuh"
+#include "conv_pair.h"
+#include "ptx.cuh"
+
+namespace vd {
+
+constexpr int kPairEpiWarps = 16;
+constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
+constexpr int kPairMaxNA = 4;
+constexpr int kPairHRows = 272;  // 256 + (k-1) rounded up, k <= 15
+
+__device__ __forceinline__ uint4 ld_shared_u4(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+
+template <int ROWB>
+__device__ __forceinline__ uint32_t swz_row(int row) {  // chunk XOR term of the TMA/UMMA swizzle for a 1024B-aligned tile
+  return ROWB == 128 ? (row & 7) : ((row >> 1) & 3);
+}
+
+template <int CH, int KC>
+__global__ void __launch_bounds__(kPairThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ PairParams p) {
+  constexpr int ROWB = KC * 2;
+  constexpr int B_STAGE = CH * ROWB;      // one tap's weights [CH][KC]
+  constexpr int ACC_COLS = 2 * CH;        // two 128-row accumulators per conv
+  constexpr int TMEM_COLS = 4 * ACC_COLS; // acc1[2] + acc2[2]
+  constexpr int CHUNKS = CH / 16, NITEMS = 2 * CHUNKS, NW = kPairEpiWarps / 4;
+  static_assert(KC == CH, "pair kernel: one K chunk per tap");
+  static_assert(TMEM_COLS <= 512 && NITEMS >= NW, "pair kernel: C must be 32 or 64");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int NA = p.na_stages;
+  uint8_t* smemA = smem;
+  uint8_t* smemW = smemA + NA * p.a_stage_bytes;
+  uint8_t* smemH = smemW + 2 * p.k * B_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemH + kPairHRows * ROWB);
+  uint64_t* a_full = bars;                 // [kPairMaxNA]
+  uint64_t* a_empty = a_full + kPairMaxNA; // [kPairMaxNA]  1 (c1 retired) + 16 (epilogue warps read the residual)
+  uint64_t* acc1_full = a_empty + kPairMaxNA;
+  uint64_t* acc1_empty = acc1_full + 2;
+  uint64_t* acc2_full = acc1_empty + 2;
+  uint64_t* acc2_empty = acc2_full + 2;
+  uint64_t* h_full = acc2_empty + 2;
+  uint64_t* h_empty = h_full + 1;
+  uint64_t* w_full = h_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  float* sbias = reinterpret_cast<float*>(bars + 32);                 // 256 B of barriers, then 2*CH floats
+  uint8_t* scratch_base = reinterpret_cast<uint8_t*>(sbias) + 1024;   // 16 warps x 1 KB
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < kPairMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kPairEpiWarps); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kPairEpiWarps);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kPairEpiWarps);
+    }
+    mbar_init(h_full, kPairEpiWarps);
+    mbar_init(h_empty, 1);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 2 * CH; i += kPairThreads) sbias[i] = i < CH ? p.bias1[i] : p.bias2[i - CH];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int hk = p.hk;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 2 * p.k * B_STAGE);
+      for (int tap = 0; tap < 2 * p.k; ++tap) tma_load_3d(&tmW, w_full, smemW + tap * B_STAGE, 0, 0, tap);
+      for (int i = 0; i < my_tiles; ++i) {
+        const uint32_t tile = blockIdx.x + i * gridDim.x;
+        uint32_t b, mt;
+        p.div_m.divmod(tile, b, mt);
+        const int t0 = mt * p.bmo;
+        const uint32_t sa = i % NA, pa = (i / NA) & 1;
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        mbar_expect_tx(&a_full[sa], p.nboxes * 64 * ROWB);
+        for (int bx = 0; bx < p.nboxes; ++bx)
+          tma_load_3d(&tmA, &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, 0,
+                      t0 - hk - hk * p.dil + bx * 64, (int)b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform; elected lane issues)
+    constexpr uint32_t idesc = umma_idesc_f16(CH, false);
+    constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
+    const uint32_t leader = elect_one();
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), w_lo0 = umma_desc_lo(smem_u32(smemW));
+    const uint32_t h_lo0 = umma_desc_lo(smem_u32(smemH));
+    const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    auto c1 = [&](int i) {
+      const uint32_t as = i & 1, sa = i % NA;
+      mbar_wait(&acc1_empty[as], ((i >> 1) & 1) ^ 1);
+      mbar_wait(&a_full[sa], (i / NA) & 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + as * ACC_COLS;
+      const uint32_t a_lo = a_lo0 + sa * a_stage16;
+      for (int tap = 0; tap < p.k; ++tap) {
+        const uint32_t at = a_lo + ((uint32_t)(tap * p.dil * ROWB) >> 4);
+        const uint32_t wt = w_lo0 + tap * (B_STAGE >> 4);
+#pragma unroll
+        for (int acc = 0; acc < 2; ++acc)
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk)
+            umma_f16_lohi(d_base + acc * CH, at + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
+                          desc_hi, idesc, (tap > 0 || kk > 0) ? 1u : 0u, leader);
+      }
+      if (leader) {
+        umma_commit(&acc1_full[as]);
+        umma_commit(&a_empty[sa]);
+      }
+    };
+    auto c2 = [&](int i) {
+      const uint32_t as = i & 1;
+      mbar_wait(h_full, i & 1);
+      mbar_wait(&acc2_empty[as], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + 2 * ACC_COLS + as * ACC_COLS;
+      for (int tap = 0; tap < p.k; ++tap) {
+        const uint32_t ht = h_lo0 + ((uint32_t)(tap * ROWB) >> 4);
+        const uint32_t wt = w_lo0 + (p.k + tap) * (B_STAGE >> 4);
+#pragma unroll
+        for (int acc = 0; acc < 2; ++acc)
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk)
+            umma_f16_lohi(d_base + acc * CH, ht + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
+                          desc_hi, idesc, (tap > 0 || kk > 0) ? 1u : 0u, leader);
+      }
+      if (leader) {
+        umma_commit(&acc2_full[as]);
+        umma_commit(h_empty);
+      }
+    };
+    if (my_tiles > 0) c1(0);
+    for (int i = 0; i < my_tiles; ++i) {
+      if (i + 1 < my_tiles) c1(i + 1);
+      c2(i);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    uint8_t* scratch = scratch_base + (warp - 2) * 1024;
+    const int L = p.L, C = CH;
+    const float slope = p.slope, res_gain = p.res_gain;
+    __nv_bfloat16* const out = p.out;
+
+    // h = lrelu(c1 + b1), zero outside the utterance, written as c2's swizzled K-major A operand
+    auto epi1 = [&](int i) {
+      const uint32_t tile = blockIdx.x + i * gridDim.x;
+      uint32_t b, mt;
+      p.div_m.divmod(tile, b, mt);
+      const int t0 = mt * p.bmo;
+      const uint32_t as = i & 1;
+      mbar_wait(&acc1_full[as], (i >> 1) & 1);
+      tc_fence_after();
+      bool h_free = false;
+      for (int it = hsel; it < NITEMS; it += NW) {
+        const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 16;
+        const int r = acc * 128 + q * 32 + lane;
+        const int th = t0 - hk + r;
+        uint32_t a[16];
+        __syncwarp();
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + acc * CH + c0, a);
+        float4 bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+        tmem_ld_wait();
+        const bool inside = th >= 0 && th < L;
+        uint4 o[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o[h2]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = h2 * 8 + e * 2;
+            const float4 bq = bv[j >> 2];
+            float v0 = __uint_as_float(a[j]) + ((j & 3) == 0 ? bq.x : bq.z);
+            float v1 = __uint_as_float(a[j + 1]) + ((j & 3) == 0 ? bq.y : bq.w);
+            v0 = inside ? fmaxf(v0, v0 * slope) : 0.f;
+            v1 = inside ? fmaxf(v1, v1 * slope) : 0.f;
+            o2[e] = __floats2bfloat162_rn(v0, v1);
+          }
+        }
+        if (!h_free) {  // c2 of the previous tile must have finished reading h before it is overwritten
+          mbar_wait(h_empty, (i & 1) ^ 1);
+          h_free = true;
+        }
+        const uint32_t sw = swz_row<ROWB>(r);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+          *reinterpret_cast<uint4*>(smemH + r * ROWB + ((((c0 >> 3) + h2) ^ sw) << 4)) = o[h2];
+      }
+      fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(h_full);
+        mbar_arrive(&acc1_empty[as]);
+      }
+    };
+
+    // y = lrelu(c2 + b2 + x), x recovered from the resident activation tile; coalesced channels-last store
+    auto epi2 = [&](int i) {
+      const uint32_t tile = blockIdx.x + i * gridDim.x;
+      uint32_t b, mt;
+      p.div_m.divmod(tile, b, mt);
+      const int t0 = mt * p.bmo;
+      const uint32_t as = i & 1, sa = i % NA;
+      const uint8_t* atile = smemA + sa * p.a_stage_bytes;
+      mbar_wait(&acc2_full[as], (i >> 1) & 1);
+      tc_fence_after();
+      for (int it = hsel; it < NITEMS; it += NW) {
+        const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 16;
+        const int i0 = acc * 128 + q * 32;            // first output row of this warp's 32
+        const int ra = i0 + lane + hk + hk * p.dil;   // row of x(t0 + i0 + lane) in the activation tile
+        uint32_t a[16];
+        __syncwarp();
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + as * ACC_COLS + acc * CH + c0, a);
+        float4 bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + CH + c0 + 4 * j);
+        const uint32_t sw = swz_row<ROWB>(ra);
+        uint4 rx[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) rx[h2] = ld_shared_u4(atile + ra * ROWB + ((((c0 >> 3) + h2) ^ sw) << 4));
+        tmem_ld_wait();
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rx[h2]);
+          uint4 ov;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = h2 * 8 + e * 2;
+            const float4 bq = bv[j >> 2];
+            const float2 xr = __bfloat1622float2(r2[e]);
+            float v0 = __uint_as_float(a[j]) + ((j & 3) == 0 ? bq.x : bq.z) + (xr.x >= 0.f ? xr.x : xr.x * res_gain);
+            float v1 = __uint_as_float(a[j + 1]) + ((j & 3) == 0 ? bq.y : bq.w) + (xr.y >= 0.f ? xr.y : xr.y * res_gain);
+            o2[e] = __floats2bfloat162_rn(fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope));
+          }
+          *reinterpret_cast<uint4*>(scratch + lane * 32 + ((h2 ^ ((lane >> 2) & 1)) << 4)) = ov;
+        }
+        __syncwarp();
+        const int rows_valid = min(32, max(0, min(p.bmo - i0, L - (t0 + i0))));
+        const long row0 = (long)b * L + t0 + i0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int row = 16 * j + (lane >> 1);
+          const uint4 ov = *reinterpret_cast<const uint4*>(scratch + row * 32 + (((lane & 1) ^ ((row >> 2) & 1)) << 4));
+          if (row < rows_valid) *(reinterpret_cast<uint4*>(out + (row0 + row) * C + c0) + (lane & 1)) = ov;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&acc2_empty[as]);
+        mbar_arrive(&a_empty[sa]);
+      }
+    };
+
+    if (my_tiles > 0) epi1(0);
+    for (int i = 0; i < my_tiles; ++i) {
+      if (i + 1 < my_tiles) epi1(i + 1);
+      epi2(i);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                   bool swizzle);
+
+static constexpr int kPairSmemBudget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 1024 /*bias*/ - 16384 /*scratch*/;
+
+bool pair_supported(int channels, int k, int dil) {
+  if (channels != 32 && channels != 64) return false;
+  if (k % 2 == 0 || k > 15) return false;
+  const int rowb = channels * 2;
+  const int nboxes = (256 + (k - 1) * dil + 63) / 64;
+  const int a_stage = nboxes * 64 * rowb;
+  const int need = 3 * a_stage + 2 * k * channels * rowb + kPairHRows * rowb;
+  return need <= kPairSmemBudget && 256 - (k - 1) >= 128;
+}
+
+int plan_conv_pair(PairPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
+                   const __nv_bfloat16* w_pair, int num_sms) {
+  VD_CHECK(pair_supported(channels, k, dil), "conv_pair: unsupported shape");
+  PairParams& p = pl->p;
+  p.B = B; p.L = L; p.k = k; p.dil = dil; p.hk = (k - 1) / 2;
+  p.bmo = 256 - (k - 1);
+  const int rowb = channels * 2;
+  p.nboxes = (256 + (k - 1) * dil + 63) / 64;
+  p.a_stage_bytes = p.nboxes * 64 * rowb;
+  const int fixed = 2 * k * channels * rowb + kPairHRows * rowb;
+  p.na_stages = std::min(kPairMaxNA, (kPairSmemBudget - fixed) / p.a_stage_bytes);
+  p.m_tiles = (L + p.bmo - 1) / p.bmo;
+  p.total_tiles = B * p.m_tiles;
+  p.div_m.init(p.m_tiles);
+  p.trace = nullptr;
+  pl->channels = channels;
+  pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + fixed + 256 + 1024 + 16384;
+  if (encode_tmap_3d(&pl->tmA, x, channels, L, B, channels, 64, true)) return 1;
+  if (encode_tmap_3d(&pl->tmW, w_pair, channels, channels, 2 * k, channels, channels, true)) return 1;
+  return 0;
+}
+
+template <int CH>
+static int launch_pair_inst(const PairPlan& pl, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VD_CUDA(cudaFuncSetAttribute(conv_pair_kernel<CH, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_pair_kernel<CH, CH><<<pl.grid, kPairThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv_pair(PairPlan& pl, const float* bias1, const float* bias2, float slope, __nv_bfloat16* out,
+                     cudaStream_t stream) {
+  pl.p.bias1 = bias1;
+  pl.p.bias2 = bias2;
+  pl.p.slope = slope;
+  pl.p.res_gain = 1.f / slope;
+  pl.p.out = out;
+  if (pl.channels == 32) return launch_pair_inst<32>(pl, stream);
+  if (pl.channels == 64) return launch_pair_inst<64>(pl, stream);
+  set_error("conv_pair: no kernel instance");
+  return 1;
+}
+
+}  // namespace vd

@@ -596,6 +596,11 @@ static int encode_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1,
   return 0;
 }
 
+int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                   bool swizzle) {
+  return encode_3d(m, base, d0, d1, d2, b0, b1, swizzle);
+}
+
 template <int BN, int KC, int EPI, bool SWAP = false>
 static int launch_one(const ConvTcPlan& pl, cudaStream_t stream) {
   static bool attr_set = false;  // benign race: idempotent

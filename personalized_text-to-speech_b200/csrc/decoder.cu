@@ -30,6 +30,7 @@
 
 #include "../../include/vitsdec.h"
 #include "common.cuh"
+#include "conv_pair.h"
 #include "conv_tc.h"
 #include "pack.h"
 
@@ -46,7 +47,7 @@ constexpr float kPostSlope = 0.01f;  // F.leaky_relu default, models.py:285
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int ceildiv(int a, int b) { return -floordiv(-a, b); }
 
-enum LayerKind { kConv = 0, kConvT = 1, kPost = 2, kCond = 3, kMrf = 4 };
+enum LayerKind { kConv = 0, kConvT = 1, kPost = 2, kCond = 3, kMrf = 4, kPair = 5 };
 
 struct Layer {
   std::string name;
@@ -62,6 +63,8 @@ struct Layer {
   bool bias_dirty = false;       // combined bias = sum of member biases, rebuilt lazily
   int mrf_group = -1;            // real layers: id of the virtual layer they also feed, and their tap base in it
   int mrf_tap_base = 0;
+  int pair_group = -1;           // real layers: id of the fused-pair virtual layer (kPair) and their tap base in it
+  int pair_tap_base = 0;
 };
 
 static void conv_geom(Layer& l) {
@@ -111,6 +114,8 @@ struct Step {           // one launch of the conv primitive
   ConvEpilogue ep;
   int L;
   ConvTcPlan tc;
+  bool is_pair = false;     // fused ResBlock1 pair (conv_pair.cu): layer = the kPair virtual layer
+  PairPlan pair;
   bf16* dbg_dst = nullptr;  // debug_keep: copy ep.out here after the launch
   size_t dbg_bytes = 0;
 };
@@ -142,7 +147,8 @@ struct vitsdec_decoder {
   std::vector<int> stage_ch;
   int hop = 1;
   float* scale_scratch = nullptr;
-  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0;
+  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1;
+  std::map<std::pair<int, int>, int> l_pair;  // (resblock index, pair index) -> kPair virtual layer id
   int last_launches = 0;
   // profile=1: CUDA events around the convolution launches of every decode, accumulated on read
   cudaEvent_t ev_conv0 = nullptr, ev_conv1 = nullptr;
@@ -182,6 +188,10 @@ static int add_layer(vitsdec_decoder* d, const std::string& name, LayerKind kind
 }
 
 static int alloc_layer(Layer& l) {
+  if (l.kind == kPair) {
+    VD_CUDA(cudaMalloc(&l.w, (size_t)2 * l.k * l.c_out * l.c_in * sizeof(bf16)));
+    return 0;
+  }
   if (l.kind == kConv || l.kind == kConvT || l.kind == kMrf) {
     const size_t wn = (size_t)l.geom.ntaps * l.geom.n_total * l.geom.c_in;
     VD_CUDA(cudaMalloc(&l.w, wn * sizeof(bf16)));
@@ -315,6 +325,24 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
         const bool last = m == npairs - 1;
         const bf16* conv_in = cur;
         int lid;
+        auto pit = d->l_pair.find({i * nk + j, m});
+        if (!last && d->impl == 0 && d->fuse_pairs && pit != d->l_pair.end()) {
+          // whole pair in one launch: h stays in shared memory, the residual comes from the resident input tile
+          bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2;
+          Step s{};
+          s.layer = pit->second;
+          s.is_pair = true;
+          s.L = L;
+          s.xs[0] = cur;
+          s.ep = ep0(convs[2 * m]);
+          s.ep.out = dst;
+          const Layer& pv = d->layers[pit->second];
+          if (plan_conv_pair(&s.pair, B, L, pv.c_out, pv.k, pv.dil, cur, pv.w, d->num_sms)) return 1;
+          s.tc.p.g.B = B;
+          pl.steps.push_back(s);
+          cur = dst;
+          continue;
+        }
         if (d->hp.resblock == 1) {
           ConvEpilogue e1 = ep0(convs[2 * m]);
           e1.out = last ? Hj : T1;
@@ -372,6 +400,8 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
 
 static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
   Layer& ly = d->layers[s.layer];
+  if (s.is_pair)
+    return launch_conv_pair(s.pair, d->layers[ly.members[0]].bias, d->layers[ly.members[1]].bias, kSlope, s.ep.out, st);
   if (d->impl == 0) return launch_conv_tc(s.tc, s.ep, st);
   return launch_conv_simt(s.tc.p.g, s.ep, s.xs, ly.w, st);
 }
@@ -480,6 +510,32 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
       d->l_mrf.push_back(vid);
     }
   }
+  // Fused pairs: every non-final (c1, c2) pair of a ResBlock1 whose two weight sets, activation stages and the
+  // intermediate tile fit in shared memory (C <= 64) runs as one launch (conv_pair.cu).
+  if (hp->resblock == 1) {
+    for (size_t rb = 0; rb < d->l_rb.size(); ++rb) {
+      const std::vector<int> convs = d->l_rb[rb];
+      const int npairs = (int)convs.size() / 2;
+      for (int m = 0; m + 1 < npairs; ++m) {
+        const Layer c1 = d->layers[convs[2 * m]];
+        if (!pair_supported(c1.c_out, c1.k, c1.dil)) continue;
+        Layer v;
+        v.name = "pair." + c1.name;
+        v.kind = kPair;
+        v.c_in = v.c_out = c1.c_out;
+        v.k = c1.k;
+        v.dil = c1.dil;
+        v.members = {convs[2 * m], convs[2 * m + 1]};
+        const int vid = (int)d->layers.size();
+        d->layers[convs[2 * m]].pair_group = vid;
+        d->layers[convs[2 * m]].pair_tap_base = 0;
+        d->layers[convs[2 * m + 1]].pair_group = vid;
+        d->layers[convs[2 * m + 1]].pair_tap_base = c1.k;
+        d->layers.push_back(v);
+        d->l_pair[{(int)rb, m}] = vid;
+      }
+    }
+  }
   for (Layer& l : d->layers)
     if (alloc_layer(l)) return 1;
   VD_CUDA(cudaMalloc(&d->scale_scratch, 4096 * sizeof(float)));
@@ -529,6 +585,12 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
         return 1;
       v.bias_dirty = true;
     }
+    if (l.pair_group >= 0) {
+      Layer& v = d->layers[l.pair_group];
+      if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.pair_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
+                           st))
+        return 1;
+    }
   } else if (l.kind == kConvT) {
     VD_CHECK(l.c_in <= 4096, "too many channels");
     if (launch_wn_scale(w, wg, d->scale_scratch, l.c_in, l.c_out * l.k, st)) return 1;  // dim 0 of [C_in,C_out,k]
@@ -568,7 +630,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     std::lock_guard<std::mutex> lock(d->mu);
     for (size_t i = d->num_real_layers; i < d->layers.size(); ++i) {
       Layer& v = d->layers[i];
-      if (!v.bias_dirty) continue;
+      if (v.kind != kMrf || !v.bias_dirty) continue;
       const float* bs[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
       for (size_t j = 0; j < v.members.size(); ++j) bs[j] = d->layers[v.members[j]].bias;
       if (launch_sum_bias(bs[0], bs[1], bs[2], bs[3], v.bias, v.c_out, st)) return 1;
@@ -580,7 +642,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, d->desc_mode * 2 + d->debug_keep, ws};
+    const PlanKey key{B, T, d->impl, d->desc_mode * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -677,6 +739,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   if (!strcmp(key, "impl")) { VD_CHECK(value == 0 || value == 1, "impl: 0 (tcgen05) or 1 (simt)"); d->impl = value; }
   else if (!strcmp(key, "desc_mode")) d->desc_mode = value;
   else if (!strcmp(key, "debug_keep")) d->debug_keep = value ? 1 : 0;
+  else if (!strcmp(key, "fuse_pairs")) d->fuse_pairs = value ? 1 : 0;
   else if (!strcmp(key, "profile")) {
     d->profile = value ? 1 : 0;
     d->prof_conv_ms = 0.0;
@@ -707,6 +770,7 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   if (!strcmp(key, "impl")) *value = d->impl;
   else if (!strcmp(key, "desc_mode")) *value = d->desc_mode;
   else if (!strcmp(key, "debug_keep")) *value = d->debug_keep;
+  else if (!strcmp(key, "fuse_pairs")) *value = d->fuse_pairs;
   else if (!strcmp(key, "hop")) *value = d->hop;
   else if (!strcmp(key, "num_sms")) *value = d->num_sms;
   else { set_error(std::string("unknown option ") + key); return 1; }
@@ -805,6 +869,39 @@ int vitsdec_op_conv1d(int device, const void* x, const float* w, const float* bi
   conv_geom(l);
   return op_conv_common(device, l, x, w, bias, res, res_gain, out_slope, y, B, L, impl, desc_mode,
                         static_cast<cudaStream_t>(stream));
+}
+
+int vitsdec_op_resblock_pair(int device, const void* x, const float* w1, const float* b1, const float* w2,
+                             const float* b2, void* y, int B, int L, int channels, int k, int dilation, float slope,
+                             void* stream) {
+  VD_CHECK(x && w1 && w2 && y, "vitsdec_op_resblock_pair: null argument");
+  VD_CHECK(pair_supported(channels, k, dilation), "vitsdec_op_resblock_pair: shape not supported by the fused kernel");
+  DeviceGuard guard(device);
+  VD_CHECK(guard.ok, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  VD_CUDA(cudaGetDeviceProperties(&prop, device));
+  VD_CHECK(prop.major == 10, "vitsdec needs an sm_100 (B200) device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bf16* w = nullptr;
+  float *scale = nullptr, *bias = nullptr;
+  const size_t per = (size_t)k * channels * channels;
+  VD_CUDA(cudaMalloc(&w, 2 * per * sizeof(bf16)));
+  VD_CUDA(cudaMalloc(&scale, 4096 * sizeof(float)));
+  VD_CUDA(cudaMalloc(&bias, 2 * channels * sizeof(float)));
+  int rc = launch_wn_scale(w1, nullptr, scale, channels, channels * k, st) ||
+           launch_pack_conv(w1, scale, w, channels, channels, k, st) ||
+           launch_pack_conv(w2, scale, w + per, channels, channels, k, st) ||
+           launch_replicate_bias(b1, bias, channels, 1, st) || launch_replicate_bias(b2, bias + channels, channels, 1, st);
+  if (!rc) {
+    PairPlan pl{};
+    rc = plan_conv_pair(&pl, B, L, channels, k, dilation, static_cast<const bf16*>(x), w, prop.multiProcessorCount);
+    pl.p.trace = g_trace_buffer;
+    rc = rc || launch_conv_pair(pl, bias, bias + channels, slope, static_cast<bf16*>(y), st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(w); cudaFree(scale); cudaFree(bias);
+  if (!rc && se != cudaSuccess) { set_error(std::string("op_resblock_pair: ") + cudaGetErrorString(se)); rc = 1; }
+  return rc;
 }
 
 int vitsdec_op_conv_transpose1d(int device, const void* x, const float* w, const float* bias, float out_slope, void* y,

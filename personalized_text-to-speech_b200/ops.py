@@ -40,3 +40,17 @@ def conv_transpose1d_cl(x, w, bias=None, stride=2, out_slope=1.0, impl=0):
                                                         float(out_slope), _ptr(y), B, L, c_in, c_out, k, int(stride),
                                                         int(impl), st), "vitsdec_op_conv_transpose1d")
     return y
+
+
+def resblock_pair_cl(x, w1, b1, w2, b2, dilation=1, slope=0.1):
+    """Fused ResBlock1 iteration.  x: bf16 [B, L, C] a-form; w1, w2: fp32 [C, C, k]; -> bf16 [B, L, C] a-form."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
+    B, L, C = x.shape
+    k = w1.shape[2]
+    y = torch.empty_like(x)
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    ts = [t.float().contiguous() for t in (w1, b1, w2, b2)]
+    _capi.check(_capi.lib().vitsdec_op_resblock_pair(x.device.index or 0, _ptr(x), _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]),
+                                                     _ptr(ts[3]), _ptr(y), B, L, C, k, int(dilation), float(slope), st),
+                "vitsdec_op_resblock_pair")
+    return y

@@ -179,3 +179,19 @@ def test_sharded_single_rank_is_identity():
     g = torch.randn(3, hp.gin_channels, 1, device=DEV)
     with torch.no_grad():
         assert torch.equal(vitsdec.decode_sharded(G, z, g), G(z, g))
+
+
+def test_fused_pairs_equal_unfused_schedule():
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 40)
+    B, T = 2, 150
+    z = torch.randn(B, hp.initial_channel, T, device=DEV)
+    g = torch.randn(B, hp.gin_channels, 1, device=DEV)
+    with torch.no_grad():
+        a = G(z, g)
+        n_fused = G.last_launch_count()
+        G.set_option("fuse_pairs", 0)
+        b = G(z, g)
+        n_plain = G.last_launch_count()
+    assert n_fused < n_plain
+    assert torch.equal(a, b)

@@ -124,3 +124,36 @@ def test_channels_as_m_and_time_as_m_forms_agree_bitwise():
         c = ops.conv1d_cl(x, w, b, dilation=d, res=res, out_slope=0.1, impl=0, desc_mode=8)
         assert torch.equal(a, c)
         assert rel_err(a, ref_conv(x, w, b, d, res, 10.0, 0.1)) < REL_TOL
+
+
+def ref_pair(x, w1, b1, w2, b2, d, slope=0.1):
+    """One ResBlock1 iteration (modules.py:211-221) on the a-form input, h rounded to bf16 like the kernel stores it."""
+    k = w1.shape[2]
+    a = x.float().transpose(1, 2)
+    h = F.conv1d(a, w1.bfloat16().float(), b1, dilation=d, padding=(k - 1) // 2 * d)
+    h = torch.where(h >= 0, h, h * slope).bfloat16().float()
+    y = F.conv1d(h, w2.bfloat16().float(), b2, padding=(k - 1) // 2)
+    y = y + torch.where(a >= 0, a, a / slope)
+    return torch.where(y >= 0, y, y * slope).transpose(1, 2)
+
+
+@pytest.mark.parametrize("case", [(1, 300, 32, 3, 1), (2, 1000, 32, 7, 3), (3, 777, 32, 11, 5), (2, 250, 32, 11, 5),
+                                  (1, 5, 32, 7, 1), (1, 246, 32, 11, 1), (1, 247, 32, 11, 3), (2, 3000, 64, 3, 3),
+                                  (1, 254, 64, 3, 1), (1, 9000, 32, 3, 5)],
+                         ids=lambda c: "B%d_L%d_C%d_k%d_d%d" % c)
+def test_fused_resblock_pair_matches_torch_and_unfused(case):
+    B, L, C, k, d = case
+    torch.manual_seed(L + k)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, L, C, device=dev).bfloat16()
+    w1 = torch.randn(C, C, k, device=dev) / (C * k) ** 0.5
+    w2 = torch.randn(C, C, k, device=dev) / (C * k) ** 0.5
+    b1 = torch.randn(C, device=dev) * 0.1
+    b2 = torch.randn(C, device=dev) * 0.1
+    y = ops.resblock_pair_cl(x, w1, b1, w2, b2, dilation=d, slope=0.1)
+    torch.cuda.synchronize()
+    assert rel_err(y, ref_pair(x, w1, b1, w2, b2, d)) < REL_TOL
+    # identical arithmetic to the two single-conv launches (same bf16 h, same accumulation order)
+    h = ops.conv1d_cl(x, w1, b1, dilation=d, out_slope=0.1)
+    y2 = ops.conv1d_cl(h, w2, b2, dilation=1, res=x, res_gain=10.0, out_slope=0.1)
+    assert torch.equal(y, y2)
