@@ -33,15 +33,16 @@ __device__ __forceinline__ uint32_t swz_row(int row) {  // chunk XOR term of the
   return ROWB == 128 ? (row & 7) : ((row >> 1) & 3);
 }
 
-template <int CH, int KC>
+template <int CH, int KC, int NACC>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ PairParams p) {
   constexpr int ROWB = KC * 2;
   constexpr int B_STAGE = CH * ROWB;      // one tap's weights [CH][KC]
-  constexpr int ACC_COLS = 2 * CH;        // two 128-row accumulators per conv
+  constexpr int ACC_COLS = NACC * CH;     // NACC 128-row accumulators per conv (2, or 1 when smem is tight)
   constexpr int TMEM_COLS = 4 * ACC_COLS; // acc1[2] + acc2[2]
-  constexpr int CHUNKS = CH / 16, NITEMS = 2 * CHUNKS, NW = kPairEpiWarps / 4;
+  constexpr int CHUNKS = CH / 16, NITEMS = NACC * CHUNKS, NW = kPairEpiWarps / 4;
+  constexpr int HROWS = NACC == 2 ? kPairHRows : 144;
   static_assert(KC == CH, "pair kernel: one K chunk per tap");
   static_assert(TMEM_COLS <= 512 && NITEMS >= NW, "pair kernel: C must be 32 or 64");
 
@@ -51,7 +52,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smemA = smem;
   uint8_t* smemW = smemA + NA * p.a_stage_bytes;
   uint8_t* smemH = smemW + 2 * p.k * B_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemH + kPairHRows * ROWB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemH + HROWS * ROWB);
   uint64_t* a_full = bars;                 // [kPairMaxNA]
   uint64_t* a_empty = a_full + kPairMaxNA; // [kPairMaxNA]  1 (c1 retired) + 16 (epilogue warps read the residual)
   uint64_t* acc1_full = a_empty + kPairMaxNA;
@@ -134,7 +135,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t at = a_lo + ((uint32_t)(tap * p.dil * ROWB) >> 4);
         const uint32_t wt = w_lo0 + tap * (B_STAGE >> 4);
 #pragma unroll
-        for (int acc = 0; acc < 2; ++acc)
+        for (int acc = 0; acc < NACC; ++acc)
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk)
             umma_f16_lohi(d_base + acc * CH, at + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
@@ -155,7 +156,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t ht = h_lo0 + ((uint32_t)(tap * ROWB) >> 4);
         const uint32_t wt = w_lo0 + (p.k + tap) * (B_STAGE >> 4);
 #pragma unroll
-        for (int acc = 0; acc < 2; ++acc)
+        for (int acc = 0; acc < NACC; ++acc)
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk)
             umma_f16_lohi(d_base + acc * CH, ht + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
@@ -317,26 +318,36 @@ int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, u
 
 static constexpr int kPairSmemBudget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 1024 /*bias*/ - 16384 /*scratch*/;
 
-bool pair_supported(int channels, int k, int dil) {
-  if (channels != 32 && channels != 64) return false;
-  if (k % 2 == 0 || k > 15) return false;
+// rows of h per tile: 256 when three activation stages + both weight sets + h fit, else 128, else 0 (unsupported)
+static int pair_tile_rows(int channels, int k, int dil) {
+  if (channels != 32 && channels != 64) return 0;
+  if (k % 2 == 0 || k > 15) return 0;
   const int rowb = channels * 2;
-  const int nboxes = (256 + (k - 1) * dil + 63) / 64;
-  const int a_stage = nboxes * 64 * rowb;
-  const int need = 3 * a_stage + 2 * k * channels * rowb + kPairHRows * rowb;
-  return need <= kPairSmemBudget && 256 - (k - 1) >= 128;
+  for (int rows : {256, 128}) {
+    const int nboxes = (rows + (k - 1) * dil + 63) / 64;
+    const int a_stage = nboxes * 64 * rowb;
+    const int hrows = rows == 256 ? kPairHRows : 144;
+    const int need = 3 * a_stage + 2 * k * channels * rowb + hrows * rowb;
+    if (rows == 128 && channels != 64) continue;  // the 128-row form needs >= 4 epilogue items per tile
+    if (need <= kPairSmemBudget) return rows;
+  }
+  return 0;
 }
+
+bool pair_supported(int channels, int k, int dil) { return pair_tile_rows(channels, k, dil) != 0; }
 
 int plan_conv_pair(PairPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
                    const __nv_bfloat16* w_pair, int num_sms) {
   VD_CHECK(pair_supported(channels, k, dil), "conv_pair: unsupported shape");
   PairParams& p = pl->p;
   p.B = B; p.L = L; p.k = k; p.dil = dil; p.hk = (k - 1) / 2;
-  p.bmo = 256 - (k - 1);
+  const int rows = pair_tile_rows(channels, k, dil);
+  pl->nacc = rows / 128;
+  p.bmo = rows - (k - 1);
   const int rowb = channels * 2;
-  p.nboxes = (256 + (k - 1) * dil + 63) / 64;
+  p.nboxes = (rows + (k - 1) * dil + 63) / 64;
   p.a_stage_bytes = p.nboxes * 64 * rowb;
-  const int fixed = 2 * k * channels * rowb + kPairHRows * rowb;
+  const int fixed = 2 * k * channels * rowb + (rows == 256 ? kPairHRows : 144) * rowb;
   p.na_stages = std::min(kPairMaxNA, (kPairSmemBudget - fixed) / p.a_stage_bytes);
   p.m_tiles = (L + p.bmo - 1) / p.bmo;
   p.total_tiles = B * p.m_tiles;
@@ -350,14 +361,15 @@ int plan_conv_pair(PairPlan* pl, int B, int L, int channels, int k, int dil, con
   return 0;
 }
 
-template <int CH>
+template <int CH, int NACC>
 static int launch_pair_inst(const PairPlan& pl, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CUDA(cudaFuncSetAttribute(conv_pair_kernel<CH, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VD_CUDA(cudaFuncSetAttribute(conv_pair_kernel<CH, CH, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
     attr_set = true;
   }
-  conv_pair_kernel<CH, CH><<<pl.grid, kPairThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
+  conv_pair_kernel<CH, CH, NACC><<<pl.grid, kPairThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -369,8 +381,9 @@ int launch_conv_pair(PairPlan& pl, const float* bias1, const float* bias2, float
   pl.p.slope = slope;
   pl.p.res_gain = 1.f / slope;
   pl.p.out = out;
-  if (pl.channels == 32) return launch_pair_inst<32>(pl, stream);
-  if (pl.channels == 64) return launch_pair_inst<64>(pl, stream);
+  if (pl.channels == 32 && pl.nacc == 2) return launch_pair_inst<32, 2>(pl, stream);
+  if (pl.channels == 64 && pl.nacc == 2) return launch_pair_inst<64, 2>(pl, stream);
+  if (pl.channels == 64 && pl.nacc == 1) return launch_pair_inst<64, 1>(pl, stream);
   set_error("conv_pair: no kernel instance");
   return 1;
 }

@@ -28,6 +28,7 @@ struct PairPlan {
   CUtensorMap tmA, tmW;
   PairParams p;
   int channels;
+  int nacc;         // 128-row accumulators per conv per tile (2, or 1 when shared memory is tight)
   int grid;
   size_t smem;
 };

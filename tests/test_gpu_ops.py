@@ -139,7 +139,7 @@ def ref_pair(x, w1, b1, w2, b2, d, slope=0.1):
 
 @pytest.mark.parametrize("case", [(1, 300, 32, 3, 1), (2, 1000, 32, 7, 3), (3, 777, 32, 11, 5), (2, 250, 32, 11, 5),
                                   (1, 5, 32, 7, 1), (1, 246, 32, 11, 1), (1, 247, 32, 11, 3), (2, 3000, 64, 3, 3),
-                                  (1, 254, 64, 3, 1), (1, 9000, 32, 3, 5)],
+                                  (1, 254, 64, 3, 1), (1, 9000, 32, 3, 5), (2, 2000, 64, 7, 5), (1, 122, 64, 7, 1), (1, 123, 64, 7, 3)],
                          ids=lambda c: "B%d_L%d_C%d_k%d_d%d" % c)
 def test_fused_resblock_pair_matches_torch_and_unfused(case):
     B, L, C, k, d = case
