@@ -27,6 +27,18 @@ FLOP_PER_UTT = 262144            # cond(g)
 CONV_POST_FLOP_PER_FRAME = 2 * 57344  # conv_post runs on CUDA cores, not in the tcgen05 kernel
 
 
+def load_traffic(launches_per_step):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the tcgen05 conv launches of one 16 x 10 s step,
+    from the committed ncu pass (profiles/r01_launches_final.csv -> profiles/r01_traffic.json), per launch."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if d.get("conv_launches_per_step") != launches_per_step:
+        return None  # the schedule changed since the capture: do not quote a stale number
+    return d["conv_dram_bytes_per_step"] / launches_per_step
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -245,6 +257,7 @@ def main():
     conv_flops_step = B * (frames * (FLOP_PER_FRAME - CONV_POST_FLOP_PER_FRAME))  # per rank, tcgen05 kernel only
     conv_ms_step = conv_ms / args.steps
     achieved = conv_flops_step / (conv_ms_step / 1e3) / 1e12
+    launches_conv = conv_launches // max(1, args.steps)
     line = {
         "metric": "decoded audio-sec/sec, VITS Generator", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -254,11 +267,16 @@ def main():
                 "h2d_bytes_per_step": int(z_host.numel() * 4 + g_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)"
-                     % (conv_launches // max(1, args.steps)),
+        "roofline": {"bound": "tensor",
+                     "kernel": "conv_tc_kernel + conv_pair_kernel (tcgen05 implicit-GEMM convs: %d launches/step, "
+                               ">98%% of step time; figures are per launch, averaged over them)" % launches_conv,
                      "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                      "frac_of_sustained": achieved / sustained, "peak_source": peak_src + ", bf16 dense burst",
-                     "conv_ms_per_step": conv_ms_step, "traffic": None},
+                     "flop_per_launch": conv_flops_step / max(1, launches_conv),
+                     "ms_per_launch": conv_ms_step / max(1, launches_conv),
+                     "conv_ms_per_step": conv_ms_step,
+                     "traffic": load_traffic(launches_conv) if (B, frames) == (16, 862) else None,
+                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"},
         "clocks": clocks,
     }
     if gather_ms is not None:

@@ -1,0 +1,56 @@
+"""Per-launch table of one decode step from an ncu CSV with gpu__time_duration / dram bytes / tensor-pipe metrics.
+Writes the text summary committed under profiles/ and (optionally) the per-step traffic JSON bench.py reads."""
+import csv
+import json
+import sys
+
+
+def load(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    by = {}
+    order = []
+    for r in csv.DictReader(lines):
+        k = r["ID"]
+        if k not in by:
+            by[k] = {"name": r["Kernel Name"].split("(")[0].replace("void ", "")}
+            order.append(k)
+        try:
+            v = float(r["Metric Value"].replace(",", ""))
+        except ValueError:
+            v = float("nan")
+        u = r["Metric Unit"]
+        m = r["Metric Name"]
+        if m == "gpu__time_duration.sum":
+            v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+        elif m.startswith("dram__bytes"):
+            v = v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1, "Gbyte": 1e3}[u]
+        by[k][m] = v
+    return [by[k] for k in order]
+
+
+def main(path, out_json=None):
+    rows = load(path)
+    start = next(i for i, r in enumerate(rows) if "pack_z" in r["name"])
+    nxt = next((i for i, r in enumerate(rows) if "pack_z" in r["name"] and i > start), len(rows))
+    step = rows[start:nxt]
+    T = "gpu__time_duration.sum"
+    tot = sum(r[T] for r in step)
+    print("# one decode step (16 x 10 s): %d launches, %.1f us summed device time (ncu, cold-cache, serialised)" % (len(step), tot))
+    print("# idx kernel                                   us    share   dram_rd_MB dram_wr_MB  tensor_pipe_%")
+    conv = {"us": 0.0, "rd": 0.0, "wr": 0.0, "n": 0}
+    for i, r in enumerate(step):
+        rd, wr = r.get("dram__bytes_read.sum", 0), r.get("dram__bytes_write.sum", 0)
+        tp = r.get("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", float("nan"))
+        print("%3d %-38s %8.1f %6.2f%% %10.1f %10.1f %10.1f" % (i, r["name"][:38], r[T], 100 * r[T] / tot, rd, wr, tp))
+        if "conv_tc" in r["name"] or "conv_pair" in r["name"]:
+            conv["us"] += r[T]; conv["rd"] += rd; conv["wr"] += wr; conv["n"] += 1
+    print("# tcgen05 conv kernels: %d launches, %.1f us (%.1f%% of the step), DRAM read %.0f MB + write %.0f MB per step"
+          % (conv["n"], conv["us"], 100 * conv["us"] / tot, conv["rd"], conv["wr"]))
+    if out_json:
+        json.dump({"conv_launches_per_step": conv["n"], "conv_dram_bytes_per_step": (conv["rd"] + conv["wr"]) * 1e6,
+                   "conv_share_of_step": conv["us"] / tot, "source": path.split("/")[-1],
+                   "workload": "16 x 10 s decode"}, open(out_json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
