@@ -655,8 +655,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   }
   // Wide layers whose weights do not stay resident run channels-as-M (128 channels x 256 time rows): at N=128 the
   // time-as-M form is bound by shared-memory operand bandwidth, at N=256 by L2 weight streaming.
-  const bool want_swap = allow_swap && kc == 64 && g.n_total % 128 == 0 &&
-                         (size_t)g.ntaps * g.c_in * 128 * 2 > 110 * 1024 && !force_no_swap;
+  const bool want_swap = allow_swap && kc == 64 && g.n_total % 128 == 0 && !force_no_swap;
   if (want_swap) bn = 128;
   pl->swap = want_swap;
   const int nacc = bn >= 256 ? 1 : 2;

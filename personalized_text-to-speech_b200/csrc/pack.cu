@@ -106,20 +106,25 @@ __global__ void cond_kernel(const float* __restrict__ wc, const float* __restric
   if (lane == 0) cb[(long)b * c_out + warp] = s + bc[warp];
 }
 
-// out[b][t] = tanh( sum_j sum_c w[c][j] * x[b][t + j - 3][c] ), x already leaky-relu'ed (models.py:285-287)
-constexpr int kPostT = 256;
-__global__ void __launch_bounds__(kPostT) conv_post_kernel(const __nv_bfloat16* __restrict__ x,
-                                                           const float* __restrict__ w, float* __restrict__ out,
-                                                           int L, int C) {
+// out[b][t] = tanh( sum_j sum_c w[c][j] * x[b][t + j - 3][c] ), x already leaky-relu'ed (models.py:285-287).
+// M = 1 output channel: CUDA cores.  A block stages 512 + 6 rows in shared memory; each thread produces 4 outputs
+// 128 rows apart so that (a) every weight vector read from shared memory is used 4 times (the first version issued
+// one broadcast LDS per MAC and was LSU-bound at 168 us) and (b) a warp's row reads stay bank-conflict free.
+constexpr int kPostThreads = 128;
+template <int kPostPer>
+__global__ void __launch_bounds__(kPostThreads) conv_post_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                const float* __restrict__ w, float* __restrict__ out,
+                                                                int L, int C) {
+  constexpr int kPostTile = kPostThreads * kPostPer;
   extern __shared__ uint8_t sm[];
   float* ws = reinterpret_cast<float*>(sm);                                  // [7][C]
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(sm + 7 * C * 4);     // [kPostT + 6][C + 8] (padded rows)
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(sm + 7 * C * 4);     // [kPostTile + 6][C + 8] (padded rows)
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kPostT;
+  const int t0 = blockIdx.x * kPostTile;
   const int pitch = C + 8;
-  for (int i = threadIdx.x; i < 7 * C; i += kPostT) ws[i] = w[(i % C) * 7 + i / C];  // conv_post.weight [1][C][7]
+  for (int i = threadIdx.x; i < 7 * C; i += kPostThreads) ws[i] = w[(i % C) * 7 + i / C];  // conv_post.weight [1][C][7]
   const int vec_per_row = C / 8;
-  for (int i = threadIdx.x; i < (kPostT + 6) * vec_per_row; i += kPostT) {
+  for (int i = threadIdx.x; i < (kPostTile + 6) * vec_per_row; i += kPostThreads) {
     const int r = i / vec_per_row, v = i % vec_per_row;
     const int t = t0 + r - 3;
     uint4 val = make_uint4(0, 0, 0, 0);
@@ -127,24 +132,31 @@ __global__ void __launch_bounds__(kPostT) conv_post_kernel(const __nv_bfloat16* 
     *reinterpret_cast<uint4*>(xs + r * pitch + v * 8) = val;
   }
   __syncthreads();
-  const int t = t0 + threadIdx.x;
-  if (t >= L) return;
-  float acc = 0.f;
-  for (int j = 0; j < 7; ++j) {
-    const __nv_bfloat16* xr = xs + (threadIdx.x + j) * pitch;
-    const float* wr = ws + j * C;
-    for (int c = 0; c < C; c += 8) {
-      const uint4 xv = *reinterpret_cast<const uint4*>(xr + c);
-      const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+  float acc[kPostPer];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(x2[e]);
-        acc = fmaf(f.x, wr[c + 2 * e], acc);
-        acc = fmaf(f.y, wr[c + 2 * e + 1], acc);
+  for (int o = 0; o < kPostPer; ++o) acc[o] = 0.f;
+  for (int j = 0; j < 7; ++j) {
+    for (int c = 0; c < C; c += 8) {
+      const float4 w0 = *reinterpret_cast<const float4*>(ws + j * C + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(ws + j * C + c + 4);
+#pragma unroll
+      for (int o = 0; o < kPostPer; ++o) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + (threadIdx.x + o * kPostThreads + j) * pitch + c);
+        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+        const float2 f0 = __bfloat1622float2(x2[0]), f1 = __bfloat1622float2(x2[1]);
+        const float2 f2 = __bfloat1622float2(x2[2]), f3 = __bfloat1622float2(x2[3]);
+        float a = acc[o];
+        a = fmaf(f0.x, w0.x, a); a = fmaf(f0.y, w0.y, a); a = fmaf(f1.x, w0.z, a); a = fmaf(f1.y, w0.w, a);
+        a = fmaf(f2.x, w1.x, a); a = fmaf(f2.y, w1.y, a); a = fmaf(f3.x, w1.z, a); a = fmaf(f3.y, w1.w, a);
+        acc[o] = a;
       }
     }
   }
-  out[(long)b * L + t] = tanhf(acc);
+#pragma unroll
+  for (int o = 0; o < kPostPer; ++o) {
+    const int t = t0 + threadIdx.x + o * kPostThreads;
+    if (t < L) out[(long)b * L + t] = tanhf(acc[o]);
+  }
 }
 
 // a-form bf16 [B][L][C] -> residual-stream fp32 NCL [B][C][L]
@@ -208,10 +220,15 @@ int launch_cond(const float* wc, const float* bc, const float* g, float* cb, int
 }
 int launch_conv_post(const __nv_bfloat16* x, const float* w, float* out, int B, int L, int C, cudaStream_t st) {
   VD_CHECK(C % 8 == 0, "conv_post: channels must be a multiple of 8");
-  const size_t smem = 7 * C * 4 + (size_t)(kPostT + 6) * (C + 8) * 2;
-  VD_CHECK(smem <= 48 * 1024, "conv_post: too many channels");
-  dim3 grid((L + kPostT - 1) / kPostT, B);
-  conv_post_kernel<<<grid, kPostT, smem, st>>>(x, w, out, L, C);
+  auto smem_for = [&](int per) { return 7 * C * 4 + (size_t)(kPostThreads * per + 6) * (C + 8) * 2; };
+  if (smem_for(4) <= 48 * 1024) {
+    dim3 grid((L + kPostThreads * 4 - 1) / (kPostThreads * 4), B);
+    conv_post_kernel<4><<<grid, kPostThreads, smem_for(4), st>>>(x, w, out, L, C);
+  } else {
+    VD_CHECK(smem_for(1) <= 48 * 1024, "conv_post: too many channels");
+    dim3 grid((L + kPostThreads - 1) / kPostThreads, B);
+    conv_post_kernel<1><<<grid, kPostThreads, smem_for(1), st>>>(x, w, out, L, C);
+  }
   VD_CUDA(cudaGetLastError());
   return 0;
 }
