@@ -121,6 +121,14 @@ struct Step {           // one launch of the conv primitive
 };
 
 struct Plan {
+  ~Plan() {
+    for (cudaGraphExec_t e : graph_exec)
+      if (e) cudaGraphExecDestroy(e);
+  }
+  // CUDA graph of the conv steps (they only touch plan-owned workspace pointers, so one capture serves every call
+  // with this plan); index 0: no speaker conditioning, 1: conv_pre adds the per-utterance cond bias
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  bool graph_failed = false;
   std::vector<Step> steps;
   bf16* a0;          // packed latent
   float* cb;         // cond bias [B][C]
@@ -147,7 +155,8 @@ struct vitsdec_decoder {
   std::vector<int> stage_ch;
   int hop = 1;
   float* scale_scratch = nullptr;
-  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1;
+  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1;
+  cudaStream_t cstream = nullptr;  // capture-only stream (the caller's may be the legacy default stream)
   std::map<std::pair<int, int>, int> l_pair;  // (resblock index, pair index) -> kPair virtual layer id
   int last_launches = 0;
   // profile=1: CUDA events around the convolution launches of every decode, accumulated on read
@@ -553,6 +562,9 @@ void vitsdec_destroy(vitsdec_decoder* d) {
   cudaFree(d->scale_scratch);
   if (d->hbuf) cudaFree(d->hbuf);
   if (d->hstream) cudaStreamDestroy(d->hstream);
+  d->plans.clear();
+  d->last_plan.reset();
+  if (d->cstream) cudaStreamDestroy(d->cstream);
   if (d->ev_conv0) cudaEventDestroy(d->ev_conv0);
   if (d->ev_conv1) cudaEventDestroy(d->ev_conv1);
   delete d;
@@ -681,13 +693,43 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     }
     VD_CUDA(cudaEventRecord(d->ev_conv0, st));
   }
-  for (size_t i = 0; i < plan->steps.size(); ++i) {
-    Step s = plan->steps[i];  // copy: per-call epilogue fields, re-entrant across threads
-    if (i == 0) s.ep.bias_b = g ? plan->cb : nullptr;
-    if (run_conv(d, s, st)) return 1;
-    ++launches;
-    if (s.dbg_dst) VD_CUDA(cudaMemcpyAsync(s.dbg_dst, s.ep.out, s.dbg_bytes, cudaMemcpyDeviceToDevice, st));
+  auto enqueue_steps = [&](cudaStream_t qs) -> int {
+    for (size_t i = 0; i < plan->steps.size(); ++i) {
+      Step s = plan->steps[i];  // copy: per-call epilogue fields, re-entrant across threads
+      if (i == 0) s.ep.bias_b = g ? plan->cb : nullptr;
+      if (run_conv(d, s, qs)) return 1;
+      if (s.dbg_dst) VD_CUDA(cudaMemcpyAsync(s.dbg_dst, s.ep.out, s.dbg_bytes, cudaMemcpyDeviceToDevice, qs));
+    }
+    return 0;
+  };
+  bool launched = false;
+  if (d->use_graph && !d->debug_keep && !plan->graph_failed) {
+    // one graph launch instead of ~60 kernel launches: what makes a 2 s / batch-1 decode launch-bound otherwise
+    std::lock_guard<std::mutex> lock(d->mu);
+    cudaGraphExec_t& exec = plan->graph_exec[g ? 1 : 0];
+    if (!exec) {
+      if (!d->cstream) VD_CUDA(cudaStreamCreateWithFlags(&d->cstream, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      bool ok = cudaStreamBeginCapture(d->cstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        const int rc = enqueue_steps(d->cstream);
+        ok = cudaStreamEndCapture(d->cstream, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+      }
+      if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok) {
+        cudaGetLastError();
+        exec = nullptr;
+        plan->graph_failed = true;  // fall back to plain launches for this plan
+      }
+    }
+    if (exec) {
+      VD_CUDA(cudaGraphLaunch(exec, st));
+      launched = true;
+    }
   }
+  if (!launched && enqueue_steps(st)) return 1;
+  launches += (int)plan->steps.size();
   if (d->profile) {
     VD_CUDA(cudaEventRecord(d->ev_conv1, st));
     d->ev_pending = true;
@@ -740,6 +782,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "desc_mode")) d->desc_mode = value;
   else if (!strcmp(key, "debug_keep")) d->debug_keep = value ? 1 : 0;
   else if (!strcmp(key, "fuse_pairs")) d->fuse_pairs = value ? 1 : 0;
+  else if (!strcmp(key, "graph")) d->use_graph = value ? 1 : 0;
   else if (!strcmp(key, "profile")) {
     d->profile = value ? 1 : 0;
     d->prof_conv_ms = 0.0;
@@ -771,6 +814,7 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   else if (!strcmp(key, "desc_mode")) *value = d->desc_mode;
   else if (!strcmp(key, "debug_keep")) *value = d->debug_keep;
   else if (!strcmp(key, "fuse_pairs")) *value = d->fuse_pairs;
+  else if (!strcmp(key, "graph")) *value = d->use_graph;
   else if (!strcmp(key, "hop")) *value = d->hop;
   else if (!strcmp(key, "num_sms")) *value = d->num_sms;
   else { set_error(std::string("unknown option ") + key); return 1; }
