@@ -96,7 +96,8 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
 /* Options: "impl" = 0 tcgen05 tensor-core kernels (default), 1 CUDA-core cross-check kernels (tests only);
  *          "desc_mode" = debug knob of the UMMA descriptor (0 is the correct setting);
  *          "debug_keep" = 1 keep named intermediates for vitsdec_debug_read; "profile" = 1 see below;
- *          "fuse_pairs" = 0 run every ResBlock conv as its own launch (default 1: fused pairs where they fit). */
+ *          "fuse_pairs" = 0 run every ResBlock conv as its own launch (default 1: fused pairs where they fit);
+ *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph). */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
 
