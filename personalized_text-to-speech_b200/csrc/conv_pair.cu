@@ -21,6 +21,10 @@
 
 namespace vd {
 
+#ifndef VITSDEC_TRACE
+#define VITSDEC_TRACE 0
+#endif
+constexpr bool kPairTrace = VITSDEC_TRACE != 0;
 constexpr int kPairEpiWarps = 16;
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
 constexpr int kPairMaxNA = 4;
@@ -41,7 +45,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int B_STAGE = CH * ROWB;      // one tap's weights [CH][KC]
   constexpr int ACC_COLS = NACC * CH;     // NACC 128-row accumulators per conv (2, or 1 when smem is tight)
   constexpr int TMEM_COLS = 4 * ACC_COLS; // acc1[2] + acc2[2]
-  constexpr int CHUNKS = CH / 16, NITEMS = NACC * CHUNKS, NW = kPairEpiWarps / 4;
+  constexpr int CHUNKS = CH / 16, NITEMS = NACC * CHUNKS, NW = kPairEpiWarps / 8;  // warps per quadrant per group
   constexpr int HROWS = NACC == 2 ? kPairHRows : 144;
   static_assert(KC == CH, "pair kernel: one K chunk per tap");
   static_assert(TMEM_COLS <= 512 && NITEMS >= NW, "pair kernel: C must be 32 or 64");
@@ -52,16 +56,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smemA = smem;
   uint8_t* smemW = smemA + NA * p.a_stage_bytes;
   uint8_t* smemH = smemW + 2 * p.k * B_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemH + HROWS * ROWB);
+  const int NH = p.nh;                     // 1 or 2 buffers for the intermediate h
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemH + NH * HROWS * ROWB);
   uint64_t* a_full = bars;                 // [kPairMaxNA]
   uint64_t* a_empty = a_full + kPairMaxNA; // [kPairMaxNA]  1 (c1 retired) + 16 (epilogue warps read the residual)
   uint64_t* acc1_full = a_empty + kPairMaxNA;
   uint64_t* acc1_empty = acc1_full + 2;
   uint64_t* acc2_full = acc1_empty + 2;
   uint64_t* acc2_empty = acc2_full + 2;
-  uint64_t* h_full = acc2_empty + 2;
-  uint64_t* h_empty = h_full + 1;
-  uint64_t* w_full = h_empty + 1;
+  uint64_t* h_full = acc2_empty + 2;      // [2]
+  uint64_t* h_empty = h_full + 2;         // [2]
+  uint64_t* w_full = h_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   float* sbias = reinterpret_cast<float*>(bars + 32);                 // 256 B of barriers, then 2*CH floats
   uint8_t* scratch_base = reinterpret_cast<uint8_t*>(sbias) + 1024;   // 16 warps x 1 KB
@@ -72,13 +77,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
-    for (int i = 0; i < kPairMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kPairEpiWarps); }
+    // epilogue warps work in two groups of 8: group 0 turns c1's accumulator into h, group 1 finishes c2's
+    for (int i = 0; i < kPairMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kPairEpiWarps / 2); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kPairEpiWarps);
-      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kPairEpiWarps);
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kPairEpiWarps / 2);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kPairEpiWarps / 2);
+      mbar_init(&h_full[i], kPairEpiWarps / 2);
+      mbar_init(&h_empty[i], 1);
     }
-    mbar_init(h_full, kPairEpiWarps);
-    mbar_init(h_empty, 1);
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -129,6 +135,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&acc1_empty[as], ((i >> 1) & 1) ^ 1);
       mbar_wait(&a_full[sa], (i / NA) & 1);
       tc_fence_after();
+      const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
+      if (tr) p.trace[i * 12 + 0] = clock64();
       const uint32_t d_base = tmem_base + as * ACC_COLS;
       const uint32_t a_lo = a_lo0 + sa * a_stage16;
       for (int tap = 0; tap < p.k; ++tap) {
@@ -145,15 +153,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit(&acc1_full[as]);
         umma_commit(&a_empty[sa]);
       }
+      if (tr) p.trace[i * 12 + 1] = clock64();
     };
     auto c2 = [&](int i) {
-      const uint32_t as = i & 1;
-      mbar_wait(h_full, i & 1);
+      const uint32_t as = i & 1, hb = i % NH;
+      mbar_wait(&h_full[hb], (i / NH) & 1);
       mbar_wait(&acc2_empty[as], ((i >> 1) & 1) ^ 1);
       tc_fence_after();
+      const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
+      if (tr) p.trace[i * 12 + 2] = clock64();
       const uint32_t d_base = tmem_base + 2 * ACC_COLS + as * ACC_COLS;
       for (int tap = 0; tap < p.k; ++tap) {
-        const uint32_t ht = h_lo0 + ((uint32_t)(tap * ROWB) >> 4);
+        const uint32_t ht = h_lo0 + ((uint32_t)(hb * HROWS * ROWB + tap * ROWB) >> 4);
         const uint32_t wt = w_lo0 + (p.k + tap) * (B_STAGE >> 4);
 #pragma unroll
         for (int acc = 0; acc < NACC; ++acc)
@@ -164,8 +175,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (leader) {
         umma_commit(&acc2_full[as]);
-        umma_commit(h_empty);
+        umma_commit(&h_empty[hb]);
       }
+      if (tr) p.trace[i * 12 + 3] = clock64();
     };
     if (my_tiles > 0) c1(0);
     for (int i = 0; i < my_tiles; ++i) {
@@ -176,7 +188,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ------------------------------------------------------------ epilogue warps
     const int q = warp & 3;
-    const int hsel = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 3;          // 0: epi1 (h producer), 1: epi2 (output)
+    const int hsel = ((warp - 2) & 7) >> 2;   // which of the group's two warps on this TMEM lane quadrant
     uint8_t* scratch = scratch_base + (warp - 2) * 1024;
     const int L = p.L, C = CH;
     const float slope = p.slope, res_gain = p.res_gain;
@@ -188,9 +201,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t b, mt;
       p.div_m.divmod(tile, b, mt);
       const int t0 = mt * p.bmo;
-      const uint32_t as = i & 1;
+      const uint32_t as = i & 1, hb = i % NH;
+      uint8_t* const hbuf = smemH + hb * HROWS * ROWB;
       mbar_wait(&acc1_full[as], (i >> 1) & 1);
       tc_fence_after();
+      const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 256;
+      if (tr) p.trace[i * 12 + 4] = clock64();
       bool h_free = false;
       for (int it = hsel; it < NITEMS; it += NW) {
         const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 16;
@@ -219,22 +235,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             o2[e] = __floats2bfloat162_rn(v0, v1);
           }
         }
-        if (!h_free) {  // c2 of the previous tile must have finished reading h before it is overwritten
-          mbar_wait(h_empty, (i & 1) ^ 1);
+        if (!h_free) {  // the c2 that last read this h buffer must have retired before it is overwritten
+          mbar_wait(&h_empty[hb], ((i / NH) & 1) ^ 1);
           h_free = true;
         }
         const uint32_t sw = swz_row<ROWB>(r);
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2)
-          *reinterpret_cast<uint4*>(smemH + r * ROWB + ((((c0 >> 3) + h2) ^ sw) << 4)) = o[h2];
+          *reinterpret_cast<uint4*>(hbuf + r * ROWB + ((((c0 >> 3) + h2) ^ sw) << 4)) = o[h2];
       }
       fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(h_full);
+        mbar_arrive(&h_full[hb]);
         mbar_arrive(&acc1_empty[as]);
       }
+      if (tr) p.trace[i * 12 + 5] = clock64();
     };
 
     // y = lrelu(c2 + b2 + x), x recovered from the resident activation tile; coalesced channels-last store
@@ -247,6 +264,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint8_t* atile = smemA + sa * p.a_stage_bytes;
       mbar_wait(&acc2_full[as], (i >> 1) & 1);
       tc_fence_after();
+      const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 256;
+      if (tr) p.trace[i * 12 + 6] = clock64();
       for (int it = hsel; it < NITEMS; it += NW) {
         const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 16;
         const int i0 = acc * 128 + q * 32;            // first output row of this warp's 32
@@ -295,12 +314,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_arrive(&acc2_empty[as]);
         mbar_arrive(&a_empty[sa]);
       }
+      if (tr) p.trace[i * 12 + 7] = clock64();
     };
 
-    if (my_tiles > 0) epi1(0);
-    for (int i = 0; i < my_tiles; ++i) {
-      if (i + 1 < my_tiles) epi1(i + 1);
-      epi2(i);
+    if (grp == 0) {
+      for (int i = 0; i < my_tiles; ++i) epi1(i);
+    } else {
+      for (int i = 0; i < my_tiles; ++i) epi2(i);
     }
   }
 
@@ -327,7 +347,7 @@ static int pair_tile_rows(int channels, int k, int dil) {
     const int nboxes = (rows + (k - 1) * dil + 63) / 64;
     const int a_stage = nboxes * 64 * rowb;
     const int hrows = rows == 256 ? kPairHRows : 144;
-    const int need = 3 * a_stage + 2 * k * channels * rowb + hrows * rowb;
+    const int need = 3 * a_stage + 2 * k * channels * rowb + hrows * rowb;  // one h buffer is the minimum
     if (rows == 128 && channels != 64) continue;  // the 128-row form needs >= 4 epilogue items per tile
     if (need <= kPairSmemBudget) return rows;
   }
@@ -347,7 +367,13 @@ int plan_conv_pair(PairPlan* pl, int B, int L, int channels, int k, int dil, con
   const int rowb = channels * 2;
   p.nboxes = (rows + (k - 1) * dil + 63) / 64;
   p.a_stage_bytes = p.nboxes * 64 * rowb;
-  const int fixed = 2 * k * channels * rowb + (rows == 256 ? kPairHRows : 144) * rowb;
+  const int hbytes = (rows == 256 ? kPairHRows : 144) * rowb;
+  int fixed = 2 * k * channels * rowb + hbytes;
+  p.nh = 1;
+  if (fixed + hbytes + 3 * p.a_stage_bytes <= kPairSmemBudget) {  // double-buffer h when there is room
+    p.nh = 2;
+    fixed += hbytes;
+  }
   p.na_stages = std::min(kPairMaxNA, (kPairSmemBudget - fixed) / p.a_stage_bytes);
   p.m_tiles = (L + p.bmo - 1) / p.bmo;
   p.total_tiles = B * p.m_tiles;

@@ -15,6 +15,7 @@ struct PairParams {
   int nboxes;            // 64-row TMA boxes per activation stage (256 + (k-1)*dil rows)
   int a_stage_bytes;
   int na_stages;
+  int nh;                // buffers for the intermediate h (2 when shared memory allows)
   int m_tiles, total_tiles;
   FastDiv div_m;
   const float* bias1;
