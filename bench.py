@@ -181,6 +181,9 @@ def main():
             if name.endswith("weight_g"):
                 p.mul_(torch.empty_like(p).uniform_(0.5, 1.5))
     G = G.to(dev).eval()
+    for kv in filter(None, os.environ.get("VITSDEC_OPTS", "").split(",")):  # experiment knob, e.g. "fold=0,fuse_pairs=0"
+        k, v = kv.split("=")
+        G.set_option(k, int(v))
     G.assume_frozen = True
     rs = np.random.RandomState(1 + rank)
     z_host = torch.from_numpy(rs.standard_normal((B, cargs[0], frames)).astype(np.float32)).pin_memory()

@@ -23,6 +23,9 @@ struct ConvGeom {
   int tap_off[kMaxTaps];  // input-row offset of each tap
   int tap_nlo[kMaxTaps];  // tap contributes only to columns [nlo, nhi) (polyphase zero blocks)
   int tap_nhi[kMaxTaps];
+  // bit kc set: K-chunk kc of the tap (64 channels, or 32 when c_in is not a multiple of 64) holds non-zero weights.
+  // All ones for ordinary layers; time-folded layers (decoder.cu fold_geom) have structurally zero chunks.
+  uint32_t tap_kmask[kMaxTaps];
   // Segments: taps [seg_tap_end[s-1], seg_tap_end[s]) read input tensor s.  One segment for an ordinary conv; the
   // last convs of the MRF branches (models.py:279-284) run as ONE launch with one segment per branch, so the branch
   // sum is formed in the accumulator instead of in HBM.

@@ -322,10 +322,13 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       uint32_t ita = 0, itb = 0;
       if (p.stationary) {
         // all taps x K-chunks of this layer's weights stay resident: one bulk load per CTA, no per-tap handshake
-        mbar_expect_tx(w_full, p.g.ntaps * nkc * B_STAGE);
+        int nchunks = 0;
+        for (int tap = 0; tap < p.g.ntaps; ++tap) nchunks += __popc(p.g.tap_kmask[tap] & ((1u << nkc) - 1u));
+        mbar_expect_tx(w_full, nchunks * B_STAGE);
         for (int tap = 0; tap < p.g.ntaps; ++tap)
           for (int kc = 0; kc < nkc; ++kc)
-            tma_load_3d(&tmW, w_full, smemB + (tap * nkc + kc) * B_STAGE, kc * KC, 0, tap);
+            if ((p.g.tap_kmask[tap] >> kc) & 1u)
+              tma_load_3d(&tmW, w_full, smemB + (tap * nkc + kc) * B_STAGE, kc * KC, 0, tap);
       }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         uint32_t mb, nt, bq, mt;
@@ -357,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
             ++ita;
             if (p.stationary) continue;
             for (int tap = tap0; tap < tap1; ++tap) {
-              if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0) continue;
+              if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0 || !((p.g.tap_kmask[tap] >> kc) & 1u)) continue;
               const uint32_t sb = itb % NB, pb = (itb / NB) & 1;
               mbar_wait(&b_empty[sb], pb ^ 1);
               mbar_expect_tx(&b_full[sb], B_STAGE);
@@ -409,7 +412,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         if (tr && sg == 0 && kc == 0) p.trace[itt * 12 + 2] = clock64();
         const uint32_t a_lo_stage = a_lo0 + sa * a_stage16;
         for (int tap = tap0; tap < tap1; ++tap) {
-          if (!((tapmask >> tap) & 1u)) continue;
+          if (!((tapmask >> tap) & 1u) || !((p.g.tap_kmask[tap] >> kc) & 1u)) continue;
           uint32_t sb = 0;
           uint32_t b_lo;
           if (p.stationary) {
@@ -649,6 +652,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   VD_CHECK(g.nseg >= 1 && g.nseg <= kMaxSeg && g.seg_tap_end[g.nseg - 1] == g.ntaps, "conv_tc: bad segment table");
   VD_CHECK(g.n_total <= 2048, "conv_tc: at most 2048 output columns per row");
   const int kc = (g.c_in % 64 == 0) ? 64 : 32;
+  VD_CHECK(g.c_in / kc <= 31, "conv_tc: too many K-chunks per tap");
   int bn = 32;
   for (int c : {256, 128, 64}) {
     if (g.n_total % c == 0) { bn = c; break; }

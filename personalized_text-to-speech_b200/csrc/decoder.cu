@@ -65,6 +65,12 @@ struct Layer {
   int mrf_tap_base = 0;
   int pair_group = -1;           // real layers: id of the fused-pair virtual layer (kPair) and their tap base in it
   int pair_tap_base = 0;
+  // time-folded form (fold_geom): r time samples per row, r*C virtual channels; 0 = layer has no folded form
+  int fold_r = 0;
+  ConvGeom fgeom{};
+  bf16* wfold = nullptr;         // [folded taps][r*C][r*C]
+  float* bias_fold = nullptr;    // [r*C]
+  int mrf_ftap_base = 0;         // real layers: first folded tap inside the virtual MRF layer's folded weights
 };
 
 static void conv_geom(Layer& l) {
@@ -76,7 +82,52 @@ static void conv_geom(Layer& l) {
     g.tap_off[j] = (j - (l.k - 1) / 2) * l.dil;  // get_padding(k, d) = d(k-1)/2, commons.py:14-15
     g.tap_nlo[j] = 0;
     g.tap_nhi[j] = l.c_out;
+    g.tap_kmask[j] = ~0u;
   }
+  g.nseg = 1;
+  g.seg_tap_end[0] = g.ntaps;
+}
+
+// Time folding (narrow layers).  A C-channel tensor [B][L][C] is bit-for-bit a (r*C)-channel tensor [B][L/r][r*C]:
+// row n of the folded view holds time samples r*n .. r*n+r-1.  A k-tap dilation-1 convolution over time is then a
+// convolution over folded rows with block-Toeplitz weights
+//     W'[s][phi*C + co][psi*C + ci] = W[j][co][ci],   j - (k-1)/2 = r*s + psi - phi   (zero when no such tap exists)
+// which turns the N = 32/64 tensor-core tiles of stages 2-3 (bound by shared-memory operand reads: 4 KB of activations
+// per 16/32-cycle MMA) into 128-channel channels-as-M tiles (N = 256 time rows per instruction) at the price of
+// (k + r - 1)/k more MACs.  K-chunks of a folded tap that are structurally zero are skipped (tap_kmask).
+static int fold_factor(const Layer& l) {
+  if (l.kind != kConv || l.dil != 1 || l.c_in != l.c_out) return 0;
+  if (l.c_in == 32) return 4;
+  if (l.c_in == 64) return 2;
+  return 0;
+}
+
+// folded taps of one k-tap conv appended to g (tap table only); returns the number of folded taps
+static int fold_taps(int c, int k, int r, ConvGeom& g, int tap_base) {
+  const int hk = (k - 1) / 2;
+  const int s_min = floordiv(-hk, r), s_max = floordiv(r - 1 + hk, r);
+  const int kc = 64, per = kc / c;  // folded K-chunk = `per` consecutive time phases
+  for (int s = s_min; s <= s_max; ++s) {
+    const int i = tap_base + (s - s_min);
+    g.tap_off[i] = s;
+    g.tap_nlo[i] = 0;
+    g.tap_nhi[i] = r * c;
+    uint32_t mask = 0;
+    for (int psi = 0; psi < r; ++psi)
+      for (int phi = 0; phi < r; ++phi)
+        if (std::abs(r * s + psi - phi) <= hk) mask |= 1u << (psi / per);
+    g.tap_kmask[i] = mask;
+  }
+  return s_max - s_min + 1;
+}
+
+static void fold_geom(Layer& l) {
+  l.fold_r = fold_factor(l);
+  if (!l.fold_r) return;
+  ConvGeom& g = l.fgeom;
+  g = ConvGeom{};
+  g.c_in = g.n_total = l.fold_r * l.c_in;
+  g.ntaps = fold_taps(l.c_in, l.k, l.fold_r, g, 0);
   g.nseg = 1;
   g.seg_tap_end[0] = g.ntaps;
 }
@@ -95,6 +146,7 @@ static void convT_geom(Layer& l) {
     const int rlo = std::max(0, s * off - p), rhi = std::min(s, s * off - p + k);
     g.tap_nlo[i] = rlo * l.c_out;
     g.tap_nhi[i] = rhi * l.c_out;
+    g.tap_kmask[i] = ~0u;
   }
   g.nseg = 1;
   g.seg_tap_end[0] = g.ntaps;
@@ -155,7 +207,7 @@ struct vitsdec_decoder {
   std::vector<int> stage_ch;
   int hop = 1;
   float* scale_scratch = nullptr;
-  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1;
+  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1;
   cudaStream_t cstream = nullptr;  // capture-only stream (the caller's may be the legacy default stream)
   std::map<std::pair<int, int>, int> l_pair;  // (resblock index, pair index) -> kPair virtual layer id
   int last_launches = 0;
@@ -189,7 +241,7 @@ static int add_layer(vitsdec_decoder* d, const std::string& name, LayerKind kind
                      int stride) {
   Layer l;
   l.name = name; l.kind = kind; l.c_in = c_in; l.c_out = c_out; l.k = k; l.dil = dil; l.stride = stride;
-  if (kind == kConv) conv_geom(l);
+  if (kind == kConv) { conv_geom(l); fold_geom(l); }
   if (kind == kConvT) convT_geom(l);
   d->layers.push_back(l);
   d->by_name[name] = (int)d->layers.size() - 1;
@@ -206,6 +258,12 @@ static int alloc_layer(Layer& l) {
     VD_CUDA(cudaMalloc(&l.w, wn * sizeof(bf16)));
     VD_CUDA(cudaMalloc(&l.bias, (size_t)l.geom.n_total * sizeof(float)));
     VD_CUDA(cudaMemset(l.bias, 0, (size_t)l.geom.n_total * sizeof(float)));
+    if (l.fold_r) {
+      const size_t fn = (size_t)l.fgeom.ntaps * l.fgeom.n_total * l.fgeom.c_in;
+      VD_CUDA(cudaMalloc(&l.wfold, fn * sizeof(bf16)));
+      VD_CUDA(cudaMalloc(&l.bias_fold, (size_t)l.fgeom.n_total * sizeof(float)));
+      VD_CUDA(cudaMemset(l.bias_fold, 0, (size_t)l.fgeom.n_total * sizeof(float)));
+    }
   } else {
     VD_CUDA(cudaMalloc(&l.wf32, (size_t)l.c_out * l.c_in * l.k * sizeof(float)));
     if (l.kind == kCond) VD_CUDA(cudaMalloc(&l.bias, (size_t)l.c_out * sizeof(float)));
@@ -272,10 +330,18 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     Layer& ly = d->layers[layer];
     ConvGeom g = ly.geom;
     g.B = B; g.L = L;
+    const bf16* wts = ly.w;
+    if (d->impl == 0 && d->fold && ly.fold_r && L % ly.fold_r == 0 && ep.mrf == nullptr && ep.bias_b == nullptr) {
+      // time-folded launch: same bytes viewed as [B][L/r][r*C] (see fold_geom)
+      g = ly.fgeom;
+      g.B = B; g.L = L / ly.fold_r;
+      wts = ly.wfold;
+      s.ep.bias = ly.bias_fold;
+    }
     for (int i = 0; i < g.nseg; ++i) s.xs[i] = xs[i];
     s.tc.p.g = g;
     if (d->impl == 0) {
-      if (plan_conv_tc(&s.tc, g, s.xs, ly.w, d->num_sms, d->desc_mode, ep.mrf == nullptr)) return 1;
+      if (plan_conv_tc(&s.tc, g, s.xs, wts, d->num_sms, d->desc_mode, ep.mrf == nullptr)) return 1;
       if (bind_residual_tc(s.tc, ep)) return 1;
     }
     pl.steps.push_back(s);
@@ -511,9 +577,32 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
           g.tap_off[g.ntaps] = m.geom.tap_off[t];
           g.tap_nlo[g.ntaps] = 0;
           g.tap_nhi[g.ntaps] = v.c_out;
+          g.tap_kmask[g.ntaps] = ~0u;
         }
         g.seg_tap_end[j] = g.ntaps;
         v.members.push_back(lid);
+      }
+      {  // folded form of the same launch, when every member folds (they share C, dilation 1)
+        int r = fold_factor(d->layers[v.members[0]]);
+        int nft = 0;
+        for (int lid : v.members) {
+          const Layer& m = d->layers[lid];
+          if (fold_factor(m) != r) r = 0;
+          if (r) nft += floordiv(r - 1 + (m.k - 1) / 2, r) - floordiv(-((m.k - 1) / 2), r) + 1;
+        }
+        if (r && nft <= kMaxTaps) {
+          v.fold_r = r;
+          ConvGeom& fg = v.fgeom;
+          fg = ConvGeom{};
+          fg.c_in = fg.n_total = r * v.c_in;
+          fg.nseg = hp->num_kernels;
+          for (int j = 0; j < hp->num_kernels; ++j) {
+            Layer& m = d->layers[v.members[j]];
+            m.mrf_ftap_base = fg.ntaps;
+            fg.ntaps += fold_taps(m.c_in, m.k, r, fg, fg.ntaps);
+            fg.seg_tap_end[j] = fg.ntaps;
+          }
+        }
       }
       d->layers.push_back(v);
       d->l_mrf.push_back(vid);
@@ -557,7 +646,7 @@ void vitsdec_destroy(vitsdec_decoder* d) {
   DeviceGuard guard(d->device);
   cudaDeviceSynchronize();
   for (Layer& l : d->layers) {
-    cudaFree(l.w); cudaFree(l.bias); cudaFree(l.wf32);
+    cudaFree(l.w); cudaFree(l.bias); cudaFree(l.wf32); cudaFree(l.wfold); cudaFree(l.bias_fold);
   }
   cudaFree(d->scale_scratch);
   if (d->hbuf) cudaFree(d->hbuf);
@@ -590,10 +679,19 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
     if (launch_wn_scale(w, wg, d->scale_scratch, l.c_out, l.c_in * l.k, st)) return 1;
     if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st)) return 1;
     if (launch_replicate_bias(bias, l.bias, l.c_out, 1, st)) return 1;
+    if (l.fold_r) {
+      if (launch_pack_conv_fold(w, d->scale_scratch, l.wfold, l.c_in, l.k, l.fold_r, st)) return 1;
+      if (launch_replicate_bias(bias, l.bias_fold, l.c_out, l.fold_r, st)) return 1;
+    }
     if (l.mrf_group >= 0) {
       Layer& v = d->layers[l.mrf_group];
       if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.mrf_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
                            st))
+        return 1;
+      if (v.fold_r &&
+          launch_pack_conv_fold(w, d->scale_scratch,
+                                v.wfold + (size_t)l.mrf_ftap_base * v.fgeom.n_total * v.fgeom.c_in, l.c_in, l.k,
+                                v.fold_r, st))
         return 1;
       v.bias_dirty = true;
     }
@@ -646,6 +744,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
       const float* bs[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
       for (size_t j = 0; j < v.members.size(); ++j) bs[j] = d->layers[v.members[j]].bias;
       if (launch_sum_bias(bs[0], bs[1], bs[2], bs[3], v.bias, v.c_out, st)) return 1;
+      if (v.fold_r && launch_replicate_bias(v.bias, v.bias_fold, v.c_out, v.fold_r, st)) return 1;
       v.bias_dirty = false;
     }
   }
@@ -654,7 +753,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, d->desc_mode * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
+    const PlanKey key{B, T, d->impl, d->desc_mode * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -783,6 +882,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "debug_keep")) d->debug_keep = value ? 1 : 0;
   else if (!strcmp(key, "fuse_pairs")) d->fuse_pairs = value ? 1 : 0;
   else if (!strcmp(key, "graph")) d->use_graph = value ? 1 : 0;
+  else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "profile")) {
     d->profile = value ? 1 : 0;
     d->prof_conv_ms = 0.0;
@@ -815,6 +915,7 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   else if (!strcmp(key, "debug_keep")) *value = d->debug_keep;
   else if (!strcmp(key, "fuse_pairs")) *value = d->fuse_pairs;
   else if (!strcmp(key, "graph")) *value = d->use_graph;
+  else if (!strcmp(key, "fold")) *value = d->fold;
   else if (!strcmp(key, "hop")) *value = d->hop;
   else if (!strcmp(key, "num_sms")) *value = d->num_sms;
   else { set_error(std::string("unknown option ") + key); return 1; }
@@ -856,6 +957,11 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
   cudaDeviceProp prop;
   VD_CUDA(cudaGetDeviceProperties(&prop, device));
   VD_CHECK(prop.major == 10, "vitsdec needs an sm_100 (B200) device");
+  const bool fold = (desc_mode & 16) != 0;  // test knob: run the time-folded form of a narrow dilation-1 layer
+  if (fold) {
+    fold_geom(l);
+    VD_CHECK(impl == 0 && l.fold_r && L % l.fold_r == 0, "op_conv: layer has no time-folded form");
+  }
   if (alloc_layer(l)) return 1;
   float* scale = nullptr;
   VD_CUDA(cudaMalloc(&scale, 4096 * sizeof(float)));
@@ -864,6 +970,9 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
     rc = launch_wn_scale(w, nullptr, scale, l.c_out, l.c_in * l.k, st) ||
          launch_pack_conv(w, scale, l.w, l.c_out, l.c_in, l.k, st) ||
          launch_replicate_bias(bias, l.bias, l.c_out, 1, st);
+    if (!rc && fold)
+      rc = launch_pack_conv_fold(w, scale, l.wfold, l.c_in, l.k, l.fold_r, st) ||
+           launch_replicate_bias(bias, l.bias_fold, l.c_out, l.fold_r, st);
   } else {
     rc = launch_wn_scale(w, nullptr, scale, l.c_in, l.c_out * l.k, st) ||
          launch_pack_convT(w, scale, l.w, l.c_in, l.c_out, l.k, l.stride, (l.k - l.stride) / 2, l.geom.ntaps,
@@ -871,10 +980,10 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
          launch_replicate_bias(bias, l.bias, l.c_out, l.stride, st);
   }
   if (!rc) {
-    ConvGeom g = l.geom;
-    g.B = B; g.L = L;
+    ConvGeom g = fold ? l.fgeom : l.geom;
+    g.B = B; g.L = fold ? L / l.fold_r : L;
     ConvEpilogue e{};
-    e.bias = l.bias;
+    e.bias = fold ? l.bias_fold : l.bias;
     e.res[0] = static_cast<const bf16*>(res);
     e.nres = res ? 1 : 0;
     e.res_gain = res_gain;
@@ -884,7 +993,7 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
     if (impl == 0) {
       ConvTcPlan pl{};
       const bf16* xs[kMaxSeg] = {static_cast<const bf16*>(x), nullptr, nullptr, nullptr};
-      rc = plan_conv_tc(&pl, g, xs, l.w, prop.multiProcessorCount, desc_mode);
+      rc = plan_conv_tc(&pl, g, xs, fold ? l.wfold : l.w, prop.multiProcessorCount, desc_mode);
       pl.p.trace = g_trace_buffer;
       rc = rc || launch_conv_tc(pl, e, st);
     } else {
@@ -893,7 +1002,7 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
     }
   }
   cudaError_t se = cudaStreamSynchronize(st);
-  cudaFree(scale); cudaFree(l.w); cudaFree(l.bias);
+  cudaFree(scale); cudaFree(l.w); cudaFree(l.bias); cudaFree(l.wfold); cudaFree(l.bias_fold);
   if (!rc && se != cudaSuccess) { set_error(std::string("op_conv: ") + cudaGetErrorString(se)); rc = 1; }
   return rc;
 }

@@ -39,6 +39,26 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
   }
 }
 
+// Conv1d weight [co][ci][k] (C x C, dilation 1) -> time-folded block-Toeplitz operand [s][phi*C+co][psi*C+ci]
+// (decoder.cu fold_geom): folded row n holds time samples r*n..r*n+r-1; tap j contributes where
+// j - (k-1)/2 = r*(s_min+s) + psi - phi.
+__global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                      __nv_bfloat16* __restrict__ wp, int C, int k, int r, int s_min, int ntaps) {
+  const int rc = r * C;
+  const long total = (long)ntaps * rc * rc;
+  const int hk = (k - 1) / 2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cc = i % rc;
+    const int nn = (i / rc) % rc;
+    const int s = s_min + (int)(i / ((long)rc * rc));
+    const int psi = cc / C, ci = cc % C, phi = nn / C, co = nn % C;
+    const int j = r * s + psi - phi + hk;
+    float val = 0.f;
+    if (j >= 0 && j < k) val = w[((long)co * C + ci) * k + j] * scale[co];
+    wp[i] = __float2bfloat16_rn(val);
+  }
+}
+
 // ConvTranspose1d weight [ci][co][k] (stride s, padding p) -> polyphase packed [tap][r*c_out+co][ci]:
 // output sample s*i + r takes input rows i + off; the contributing kernel index is j = r + p - s*off.
 __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __restrict__ scale,
@@ -183,6 +203,17 @@ int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int 
                      cudaStream_t st) {
   const long total = (long)k * c_out * c_in;
   pack_conv_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_out, c_in, k);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp, int C, int k, int r,
+                          cudaStream_t st) {
+  const int hk = (k - 1) / 2;
+  const int s_min = -((hk + r - 1) / r), s_max = (r - 1 + hk) / r;  // floor(-hk/r), floor((r-1+hk)/r)
+  const int ntaps = s_max - s_min + 1;
+  const long total = (long)ntaps * r * C * r * C;
+  pack_conv_fold_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, C, k, r, s_min,
+                                                                                        ntaps);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -126,6 +126,27 @@ def test_channels_as_m_and_time_as_m_forms_agree_bitwise():
         assert rel_err(a, ref_conv(x, w, b, d, res, 10.0, 0.1)) < REL_TOL
 
 
+@pytest.mark.parametrize("case", [(2, 1024, 32, 3, True), (3, 1500, 32, 7, False), (2, 3108, 32, 11, True),
+                                  (2, 1000, 64, 3, True), (1, 518, 64, 7, False), (2, 2222, 64, 11, True),
+                                  (1, 4, 32, 11, True), (1, 2, 64, 3, False), (16, 260, 32, 7, True)],
+                         ids=lambda c: "B%d_L%d_C%d_k%d_r%d" % c)
+def test_time_folded_conv_matches_torch_and_unfolded(case):
+    """desc_mode bit 4: the same dilation-1 conv run on the folded view [B][L/r][r*C] with block-Toeplitz weights."""
+    B, L, C, k, use_res = case
+    torch.manual_seed(L * 7 + k)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, L, C, device=dev).bfloat16()
+    w = torch.randn(C, C, k, device=dev) / (C * k) ** 0.5
+    b = torch.randn(C, device=dev) * 0.1
+    res = torch.randn(B, L, C, device=dev).bfloat16() if use_res else None
+    y = ops.conv1d_cl(x, w, b, dilation=1, res=res, res_gain=10.0, out_slope=0.1, impl=0, desc_mode=16)
+    y0 = ops.conv1d_cl(x, w, b, dilation=1, res=res, res_gain=10.0, out_slope=0.1, impl=0, desc_mode=0)
+    torch.cuda.synchronize()
+    assert rel_err(y, ref_conv(x, w, b, 1, res, 10.0, 0.1)) < REL_TOL
+    # same bf16 operands, fp32 accumulation in a different order: at most one bf16 ulp apart
+    assert float(((y.float() - y0.float()).abs() / (y0.float().abs() + 1e-3)).max()) < 2 ** -7
+
+
 def ref_pair(x, w1, b1, w2, b2, d, slope=0.1):
     """One ResBlock1 iteration (modules.py:211-221) on the a-form input, h rounded to bf16 like the kernel stores it."""
     k = w1.shape[2]
