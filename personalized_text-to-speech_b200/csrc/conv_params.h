@@ -31,6 +31,13 @@ struct ConvGeom {
   // sum is formed in the accumulator instead of in HBM.
   int nseg;
   int seg_tap_end[kMaxSeg];
+  // Dilated time-folded view (decoder.cu fold_geom, rho > 1): the tensor is C = c_real channels x L_real samples and
+  // row n of sub-sequence rho holds samples t = rho_d*(r*n + phi) + rho, phi = 0..r-1 (r = c_in / c_real), so that a
+  // dilation-rho_d convolution is a dilation-1 convolution on each sub-sequence.  L is then rows per sub-sequence,
+  // ceil(L_real / (rho_d*r)).  0/1 = ordinary contiguous view.
+  int rho_d;
+  int c_real;
+  int L_real;
 };
 
 // Epilogue:  v = acc + bias[n] (+ bias_b[b][n]) (+ sum_i unlrelu(res[i][b,t,n]))
@@ -39,6 +46,8 @@ struct ConvGeom {
 //   mrf_mode 2: mrf += v                       (middle MRF branches)       no bf16 output
 //   mrf_mode 3: out = lrelu((mrf + v) * mrf_scale, out_slope)  (last branch; mrf may be null -- it is when the
 //               branches were accumulated in TMEM by a multi-segment launch)
+//   mrf_mode 4: conv_post on the time-folded view (channels-as-M tiles only): out_f32[b][r*n + phi] = tanh(acc) for
+//               the folded output column phi*post_c + 0; no bias, no bf16 output            models.py:286-287
 // Activations are stored post-leaky-relu ("a-form"): the next conv's tensor-core operand.  The
 // residual stream x is recovered exactly (up to the bf16 rounding of a) as x = a >= 0 ? a : a * res_gain
 // with res_gain = 1/slope, which is what lets one bf16 tensor serve as both operand and residual.
@@ -53,6 +62,8 @@ struct ConvEpilogue {
   float mrf_scale;
   float out_slope;             // 1.0f = identity
   __nv_bfloat16* out;          // [B][L][n_total]
+  float* out_f32;              // mrf_mode 4: waveform [B][L * n_total / post_c]
+  int post_c;                  // mrf_mode 4: real channels per time sample (n_total = r * post_c)
 };
 
 }  // namespace vd

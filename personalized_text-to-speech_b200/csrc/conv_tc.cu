@@ -70,6 +70,7 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 struct EpiItem {
   int b, n, rows_valid;
   long row0;       // b*L + t of lane 0's row
+  long base;       // channels-as-M: element offset of (first row of the item, this warp's first channel)
   uint32_t tcol;   // TMEM column of the item inside its accumulator buffer
 };
 
@@ -77,10 +78,11 @@ struct EpiItem {
 // launch constants per item, and a lone warp pays ~20-30 cycles per resolved branch):
 //   0 generic (runtime flags: per-utterance bias, any residual count, fp32 MRF fallback)
 //   1 plain (bias + leaky-relu)      2 one residual      3 three residuals + 1/nk scale (fused MRF)
+//   4 conv_post on the folded view (tanh, fp32 waveform; channels-as-M only)
 template <int EPI>
 __device__ __forceinline__ bool epi_has_res(const ConvEpilogue& ep, int i) {
   if constexpr (EPI == 0) return i < ep.nres;
-  if constexpr (EPI == 1) return false;
+  if constexpr (EPI == 1 || EPI == 4) return false;
   if constexpr (EPI == 2) return i < 1;
   return i < 3;
 }
@@ -201,7 +203,7 @@ __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scrat
 __device__ __forceinline__ uint32_t scrT_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
 template <int EPI>
-__device__ __forceinline__ void epiT_issue_loads(const ConvEpilogue& ep, const EpiItem& it, int n_total, int lane,
+__device__ __forceinline__ void epiT_issue_loads(const ConvEpilogue& ep, const EpiItem& it, int rowstride, int lane,
                                                  EpiLoads& ld) {
 #pragma unroll
   for (int i = 0; i < kMaxRes; ++i) {
@@ -210,7 +212,7 @@ __device__ __forceinline__ void epiT_issue_loads(const ConvEpilogue& ep, const E
       for (int j = 0; j < 2; ++j) {
         const int row = 8 * j + (lane >> 2);
         if (row < it.rows_valid)
-          ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + (it.row0 + row) * n_total + it.n) +
+          ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + it.base + (long)row * rowstride) +
                                       (lane & 3));
       }
     }
@@ -244,7 +246,7 @@ __device__ __forceinline__ void epiT_accumulate(const ConvEpilogue& ep, float bi
 }
 
 template <int EPI>
-__device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int n_total,
+__device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int rowstride,
                                            int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
   if (EPI == 3 || (EPI == 0 && ep.mrf_mode == 3)) {
 #pragma unroll
@@ -262,7 +264,7 @@ __device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scra
     const int row = 8 * j + (lane >> 2);
     const uint4 ov = *reinterpret_cast<const uint4*>(scratch + scrT_off(row, lane & 3));
     if (row < it.rows_valid)
-      *(reinterpret_cast<uint4*>(ep.out + (it.row0 + row) * n_total + it.n) + (lane & 3)) = ov;
+      *(reinterpret_cast<uint4*>(ep.out + it.base + (long)row * rowstride) + (lane & 3)) = ov;
   }
   __syncwarp();
 }
@@ -322,19 +324,22 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       uint32_t ita = 0, itb = 0;
       if (p.stationary) {
         // all taps x K-chunks of this layer's weights stay resident: one bulk load per CTA, no per-tap handshake
+        // non-zero K-chunks only, packed in (tap, chunk) order: slot = w_slot[tap] + rank of the chunk in the mask
         int nchunks = 0;
         for (int tap = 0; tap < p.g.ntaps; ++tap) nchunks += __popc(p.g.tap_kmask[tap] & ((1u << nkc) - 1u));
         mbar_expect_tx(w_full, nchunks * B_STAGE);
+        int slot = 0;
         for (int tap = 0; tap < p.g.ntaps; ++tap)
           for (int kc = 0; kc < nkc; ++kc)
             if ((p.g.tap_kmask[tap] >> kc) & 1u)
-              tma_load_3d(&tmW, w_full, smemB + (tap * nkc + kc) * B_STAGE, kc * KC, 0, tap);
+              tma_load_3d(&tmW, w_full, smemB + (slot++) * B_STAGE, kc * KC, 0, tap);
       }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        uint32_t mb, nt, bq, mt;
+        uint32_t mb, nt, bq, mt, bu, rho;
         p.div_n.divmod(tile, mb, nt);
         p.div_m.divmod(mb, bq, mt);
-        const int b = bq;
+        p.div_rho.divmod(bq, bu, rho);
+        const int b = bu;
         const int t0 = mt * BM;
         const int n0 = nt * BN;
         if (p.res_prefetch) {
@@ -354,8 +359,11 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
             if (kTrace && p.trace && blockIdx.x == 0 && sg == 0 && kc == 0 && tile / gridDim.x < 256)
               p.trace[(tile / gridDim.x) * 12 + 0] = clock64();
             mbar_expect_tx(&a_full[sa], nbx * 64 * ROWB);
+            // activation map dims: [KC][K-chunk][1][row][utterance], or for a dilated folded view
+            // [C][sub-sequence rho][phase = K-chunk][row][utterance] (conv_params.h)
+            const int c1 = p.rho_d > 1 ? (int)rho : kc, c2 = p.rho_d > 1 ? kc : 0;
             for (int bx = 0; bx < nbx; ++bx)
-              tma_load_3d(&tm.a[sg], &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, kc * KC,
+              tma_load_5d(&tm.a[sg], &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, 0, c1, c2,
                           t0 + p.seg_halo_lo[sg] + bx * 64, b);
             ++ita;
             if (p.stationary) continue;
@@ -391,7 +399,11 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       tc_fence_after();
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
-      const int n0 = (tile - p.div_n.quot(tile) * p.n_tiles) * BN;
+      const uint32_t mb_ = p.div_n.quot(tile);
+      const int n0 = (tile - mb_ * p.n_tiles) * BN;
+      uint32_t bq_, mt_, bu_, rho_;
+      p.div_m.divmod(mb_, bq_, mt_);
+      p.div_rho.divmod(bq_, bu_, rho_);
       uint32_t tapmask = 0;
       for (int tap = 0; tap < p.g.ntaps; ++tap)
         if (p.g.tap_nlo[tap] < n0 + BN && p.g.tap_nhi[tap] > n0) tapmask |= 1u << tap;
@@ -410,13 +422,28 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
         if (tr && sg == 0 && kc == 0) p.trace[itt * 12 + 2] = clock64();
+        if (p.rho_d > 1) {
+          // Dilated folded view: the last row of a sub-sequence may hold samples t >= L_real, whose addresses alias the
+          // next utterance (the tensor map bounds rows, not samples).  The convolution needs zeros there: overwrite
+          // that one row of the staged tile before the MMAs read it.
+          const int rem = p.L_real - (int)rho_ - p.rho_d * kc;  // K-chunk == phase of the row's samples
+          const int nlim = rem > 0 ? (int)p.div_dr.quot(rem + p.rho_d * p.r_fold - 1) : 0;
+          const int idx = p.g.L - 1 - ((int)mt_ * BM + p.seg_halo_lo[sg]);
+          if (nlim < p.g.L && idx >= 0 && idx < p.seg_nboxes[sg] * 64) {
+            if (lane < ROWB / 16)
+              *reinterpret_cast<uint4*>(smemA + sa * p.a_stage_bytes + idx * ROWB + lane * 16) = make_uint4(0, 0, 0, 0);
+            fence_proxy_async();
+            __syncwarp();
+          }
+        }
         const uint32_t a_lo_stage = a_lo0 + sa * a_stage16;
         for (int tap = tap0; tap < tap1; ++tap) {
           if (!((tapmask >> tap) & 1u) || !((p.g.tap_kmask[tap] >> kc) & 1u)) continue;
           uint32_t sb = 0;
           uint32_t b_lo;
           if (p.stationary) {
-            b_lo = b_lo0 + (uint32_t)(tap * nkc + kc) * (B_STAGE >> 4);
+            const uint32_t slot = p.w_slot[tap] + __popc(p.g.tap_kmask[tap] & ((1u << kc) - 1u));
+            b_lo = b_lo0 + slot * (B_STAGE >> 4);
           } else {
             sb = itb % NB;
             mbar_wait(&b_full[sb], (itb / NB) & 1);
@@ -458,6 +485,9 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     // ------------------------------------------------------------ epilogue warps
     // TMEM lane quadrant = warp % 4 (hardware rule); the four warps of a quadrant take a tile's items round-robin.
     static_assert(!SWAP || (BN == 128 && NACC == 2), "SWAP tiles are 128 channels x 256 time rows");
+    const FastDiv div_rho = p.div_rho, div_dr = p.div_dr;
+    const int rho_d = p.rho_d, c_shift = p.c_shift, r_fold = p.r_fold, L_real = p.L_real, rowstride = p.rowstride;
+    const long bstride = p.bstride;
     constexpr int CHUNKS = BN / kIW, NITEMS = SWAP ? 256 / kIW : NACC * CHUNKS, NW = kEpiWarps / 4;
     static_assert(NITEMS >= NW, "every epilogue warp needs at least one item per tile");
     const int q = warp & 3;
@@ -476,8 +506,19 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       if constexpr (SWAP) {
         const int t = mt * BM + it * kIW;       // item = 16 time rows (TMEM columns) x this warp's 32 channels
         e.n = nt * BN + q * 32;
-        e.rows_valid = min(kIW, max(0, L - t));
+        // utterance x sub-sequence -> (utterance, rho); the warp's 32 columns are channels [c, c+32) of phase phi
+        uint32_t bu, rho;
+        div_rho.divmod(bq, bu, rho);
+        e.b = bu;
+        const int phi = e.n >> c_shift, c = e.n & ((1 << c_shift) - 1);
+        int nlim = L;
+        if (rho_d > 1) {
+          const int rem = L_real - (int)rho - rho_d * phi;
+          nlim = rem > 0 ? (int)div_dr.quot(rem + rho_d * r_fold - 1) : 0;
+        }
+        e.rows_valid = min(kIW, max(0, nlim - t));
         e.row0 = (long)e.b * L + t;
+        e.base = (long)e.b * bstride + (((int)rho + rho_d * phi) << c_shift) + c + (long)t * rowstride;
         e.tcol = it * kIW;
       } else {
         const int acc = it / CHUNKS, c0 = (it % CHUNKS) * kIW;
@@ -489,7 +530,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       }
     };
     auto issue = [&](const EpiItem& e, EpiLoads& l) {
-      if constexpr (SWAP) epiT_issue_loads<EPI>(ep, e, n_total, lane, l);
+      if constexpr (SWAP) epiT_issue_loads<EPI>(ep, e, rowstride, lane, l);
       else epi_issue_loads<EPI>(ep, e, n_total, lane, l);
     };
     int tile = blockIdx.x, it = hsel;
@@ -523,7 +564,22 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       }
       tmem_ld_wait();
       if (tr) p.trace[itt * 12 + 5] = clock64();
-      if constexpr (SWAP) epiT_accumulate<EPI>(ep, bias_lane, scratch, cur, n_total, lane, res_gain, acc, ld, v);
+      if constexpr (EPI == 4) {
+        // conv_post: this lane's folded column is (phase, channel) = ((32q + lane) / C, (32q + lane) % C); only
+        // channel 0 is a real output.  Columns of the item are consecutive folded rows: samples r apart.
+        const int pc = ep.post_c;
+        if ((q * 32) % pc == 0) {  // warp-uniform: lane 0 of this warp holds channel 0 of phase 32q / C
+          // spread lane 0's 16 columns over lanes 0..15: one tanh and one store per lane instead of 16 in one lane
+          float x = 0.f;
+#pragma unroll
+          for (int j = 0; j < kIW; ++j) {
+            const float t = __shfl_sync(0xffffffffu, __uint_as_float(acc[j]), 0);
+            if (lane == j) x = t;
+          }
+          const int r = n_total / pc;
+          if (lane < cur.rows_valid) ep.out_f32[(cur.row0 + lane) * r + (q * 32) / pc] = tanhf(x);
+        }
+      } else if constexpr (SWAP) epiT_accumulate<EPI>(ep, bias_lane, scratch, cur, n_total, lane, res_gain, acc, ld, v);
       else epi_accumulate<EPI>(ep, bv, scratch, cur, n_total, lane, res_gain, acc, ld, v);
       if (tr) p.trace[itt * 12 + 6] = clock64();
       if (last) {  // accumulator fully read: hand the TMEM buffer back before the stores
@@ -542,7 +598,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         issue(cur, ld);
       }
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 9] = clock64();
-      if constexpr (SWAP) epiT_store<EPI>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
+      if constexpr (EPI == 4) { (void)done; }
+      else if constexpr (SWAP) epiT_store<EPI>(ep, scratch, done, rowstride, lane, out_slope, mrf_scale, v);
       else epi_store<EPI>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 7] = clock64();
       tile = ntile; it = nit;
@@ -599,6 +656,33 @@ static int encode_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1,
   return 0;
 }
 
+// Activation tensor as the kernel's 5-d view (bf16): dims {kc, d1, d2, rows, B} with element strides
+// {1, s1, s2, srow, sb}; box {kc, 1, 1, 64, 1}, swizzle span = kc*2 bytes.
+static int encode_act(CUtensorMap* m, const void* base, uint32_t kc, uint64_t d1, uint64_t s1, uint64_t d2, uint64_t s2,
+                      uint64_t rows, uint64_t srow, uint64_t B, uint64_t sb) {
+  EncodeTiledFn fn = get_encode_fn();
+  VD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[5] = {kc, d1, d2, rows, B};
+  cuuint64_t strides[4] = {s1 * 2, s2 * 2, srow * 2, sb * 2};
+  cuuint32_t box[5] = {kc, 1, 1, 64, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = kc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                        : (kc * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[320];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled(5d) failed (%d) dims=(%u,%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu,%llu)", (int)r,
+             kc, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)rows, (unsigned long long)B,
+             (unsigned long long)s1, (unsigned long long)s2, (unsigned long long)srow, (unsigned long long)sb);
+    set_error(buf);
+    return 1;
+  }
+  return 0;
+}
+
 int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
                    bool swizzle) {
   return encode_3d(m, base, d0, d1, d2, b0, b1, swizzle);
@@ -621,6 +705,13 @@ static int launch_one(const ConvTcPlan& pl, cudaStream_t stream) {
 static int launch_swapped(const ConvTcPlan& pl, cudaStream_t stream) {
   const ConvEpilogue& e = pl.p.ep;
   const bool simple = e.bias_b == nullptr;
+  if (pl.kc == 32) {  // dilated folded view of a 32-channel tensor: K-chunk = one time phase
+    if (simple && e.mrf_mode == 0 && e.nres == 0) return launch_one<128, 32, 1, true>(pl, stream);
+    if (simple && e.mrf_mode == 0 && e.nres == 1) return launch_one<128, 32, 2, true>(pl, stream);
+    VD_CHECK(e.mrf_mode == 0 || e.mrf_mode == 3, "conv_tc: epilogue not available for 32-channel K-chunks");
+    return launch_one<128, 32, 0, true>(pl, stream);
+  }
+  if (e.mrf_mode == 4) return launch_one<128, 64, 4, true>(pl, stream);
   if (simple && e.mrf_mode == 0 && e.nres == 0) return launch_one<128, 64, 1, true>(pl, stream);
   if (simple && e.mrf_mode == 0 && e.nres == 1) return launch_one<128, 64, 2, true>(pl, stream);
   if (simple && e.mrf_mode == 3 && e.nres == 3) return launch_one<128, 64, 3, true>(pl, stream);
@@ -651,7 +742,13 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   VD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, "conv_tc: 1..32 taps supported");
   VD_CHECK(g.nseg >= 1 && g.nseg <= kMaxSeg && g.seg_tap_end[g.nseg - 1] == g.ntaps, "conv_tc: bad segment table");
   VD_CHECK(g.n_total <= 2048, "conv_tc: at most 2048 output columns per row");
-  const int kc = (g.c_in % 64 == 0) ? 64 : 32;
+  const int rho_d = std::max(1, g.rho_d);
+  int kc = (g.c_in % 64 == 0) ? 64 : 32;
+  if (rho_d > 1) {
+    VD_CHECK((g.c_real == 32 || g.c_real == 64) && g.c_in % g.c_real == 0 && g.n_total == 128 && allow_swap,
+             "conv_tc: a dilated folded view needs 32 or 64 real channels and 128 folded columns");
+    kc = g.c_real;  // one time phase per K-chunk: phases of a dilated view are not contiguous in memory
+  }
   VD_CHECK(g.c_in / kc <= 31, "conv_tc: too many K-chunks per tap");
   int bn = 32;
   for (int c : {256, 128, 64}) {
@@ -659,9 +756,10 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   }
   // Wide layers whose weights do not stay resident run channels-as-M (128 channels x 256 time rows): at N=128 the
   // time-as-M form is bound by shared-memory operand bandwidth, at N=256 by L2 weight streaming.
-  const bool want_swap = allow_swap && kc == 64 && g.n_total % 128 == 0 && !force_no_swap;
+  const bool want_swap = allow_swap && (kc == 64 || rho_d > 1) && g.n_total % 128 == 0 && !force_no_swap;
   if (want_swap) bn = 128;
   pl->swap = want_swap;
+  VD_CHECK(rho_d == 1 || want_swap, "conv_tc: a dilated folded view runs channels-as-M only");
   const int nacc = bn >= 256 ? 1 : 2;
   const int bm = 128 * nacc;
   ConvTcParams& p = pl->p;
@@ -681,9 +779,26 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   }
   p.m_tiles = (g.L + bm - 1) / bm;
   p.n_tiles = g.n_total / bn;
-  p.total_tiles = g.B * p.m_tiles * p.n_tiles;
+  p.total_tiles = g.B * rho_d * p.m_tiles * p.n_tiles;
   p.div_n.init(p.n_tiles);
   p.div_m.init(p.m_tiles);
+  p.div_rho.init(rho_d);
+  p.rho_d = rho_d;
+  if (rho_d > 1) {
+    p.r_fold = g.c_in / g.c_real;
+    p.c_shift = g.c_real == 32 ? 5 : 6;
+    p.L_real = g.L_real;
+    p.bstride = (long)g.L_real * g.c_real;
+    p.rowstride = rho_d * p.r_fold * g.c_real;
+    VD_CHECK(g.L == (g.L_real + rho_d * p.r_fold - 1) / (rho_d * p.r_fold), "conv_tc: folded row count mismatch");
+  } else {
+    p.r_fold = 1;
+    p.c_shift = 5;
+    p.L_real = g.L;
+    p.bstride = (long)g.L * g.n_total;
+    p.rowstride = g.n_total;
+  }
+  p.div_dr.init(rho_d * p.r_fold);
   p.desc_mode = desc_mode;
   p.res_prefetch = 0;
   p.trace = nullptr;
@@ -691,7 +806,12 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   pl->kc = kc;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const int b_stage = bn * kc * 2;
-  const int w_all = g.ntaps * (g.c_in / kc) * b_stage;
+  int w_chunks = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    p.w_slot[t] = (uint16_t)w_chunks;
+    w_chunks += __builtin_popcount(g.tap_kmask[t] & ((1u << (g.c_in / kc)) - 1u));
+  }
+  const int w_all = w_chunks * b_stage;  // non-zero K-chunks only
   // weights stay resident in shared memory when the whole layer fits next to >= 2 activation stages
   p.stationary = (p.n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= kSmemBudget) ? 1 : 0;
   if (force_streaming) p.stationary = 0;
@@ -708,8 +828,18 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   }
   pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + 8192 + 16384;
   for (int sg = 0; sg < kMaxSeg; ++sg) {
-    if (encode_3d(&pl->tm.a[sg], xs[sg < g.nseg ? sg : 0], g.c_in, g.L, g.B, kc, 64)) return 1;
-    pl->tm.r[sg] = pl->tm.a[sg];  // placeholder until a residual is bound
+    const void* x = xs[sg < g.nseg ? sg : 0];
+    if (rho_d > 1) {
+      // [C][rho][phase][row][utterance]: sample t = rho_d*(r*row + phase) + rho
+      if (encode_act(&pl->tm.a[sg], x, kc, rho_d, g.c_real, p.r_fold, (uint64_t)rho_d * g.c_real, g.L,
+                     (uint64_t)p.rowstride, g.B, (uint64_t)p.bstride))
+        return 1;
+    } else {
+      if (encode_act(&pl->tm.a[sg], x, kc, g.c_in / kc, kc, 1, g.c_in, g.L, g.c_in, g.B, (uint64_t)g.L * g.c_in))
+        return 1;
+    }
+    if (sg == 0 && encode_3d(&pl->tm.r[0], x, g.c_in, g.L, g.B, kc, 64)) return 1;
+    pl->tm.r[sg] = pl->tm.r[0];  // placeholder until a residual is bound
     pl->res_bound[sg] = nullptr;
   }
   if (encode_3d(&pl->tmW, w, g.c_in, g.n_total, g.ntaps, kc, bn)) return 1;
@@ -718,6 +848,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
 
 int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep) {
   VD_CHECK(ep.nres >= 0 && ep.nres <= kMaxSeg - 1, "conv_tc: at most 3 residual tensors");
+  if (pl.p.rho_d > 1) return 0;  // dilated folded view: residual rows are strided, no L2 prefetch maps
   for (int i = 0; i < ep.nres; ++i) {
     if (pl.res_bound[i] != ep.res[i]) {
       if (encode_3d(&pl.tm.r[i], ep.res[i], pl.p.g.n_total, pl.p.g.L, pl.p.g.B, pl.bn < 64 ? pl.bn : 64, 64, false))
@@ -731,11 +862,12 @@ int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep) {
 int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) {
   pl.p.ep = ep;
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
-  pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch) ? 1 : 0;
+  pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch && pl.p.rho_d == 1) ? 1 : 0;
   if (pl.swap) {
     VD_CHECK(ep.mrf == nullptr, "conv_tc: the channels-as-M variant has no fp32 MRF accumulator path");
     return launch_swapped(pl, stream);
   }
+  VD_CHECK(ep.mrf_mode != 4, "conv_tc: the conv_post epilogue needs a channels-as-M (folded) launch");
   switch (pl.bn * 100 + pl.kc) {
     case 25664: return launch_inst<256, 64, true>(pl, stream);
     case 12864: return launch_inst<128, 64, true>(pl, stream);

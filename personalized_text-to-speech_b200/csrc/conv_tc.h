@@ -39,7 +39,16 @@ struct ConvTcParams {
   int m_tiles;                // per utterance
   int n_tiles;
   int total_tiles;
-  FastDiv div_n, div_m;       // tile -> (n-tile, m-block) -> (utterance, m-tile)
+  FastDiv div_n, div_m;       // tile -> (n-tile, m-block) -> (utterance x sub-sequence, m-tile)
+  FastDiv div_rho;            // (utterance x sub-sequence) -> (utterance, rho)
+  FastDiv div_dr;             // division by rho_d * r (rows of a dilated folded view)
+  int rho_d;                  // sub-sequences per utterance (1 = ordinary view), see ConvGeom
+  int c_shift;                // log2(channels per time sample) of a dilated folded view (5 otherwise)
+  int r_fold;                 // time samples per folded row
+  int L_real;                 // time samples per utterance
+  long bstride;               // elements between utterances in the output / residual tensors
+  int rowstride;              // elements between consecutive rows of one lane group (channels-as-M epilogue)
+  uint16_t w_slot[kMaxTaps];  // resident weights: shared-memory slot of the tap's first non-zero K-chunk
   uint32_t tap_delta16[kMaxTaps];  // (tap_off - seg_halo_lo) * row_bytes >> 4: descriptor start-address delta per tap
   int res_prefetch;           // 1: the producer prefetches the residual tiles (tmR) into L2
   unsigned long long* trace;  // debug: per-tile clock64 stamps of CTA 0 ([tile][8]) or null

@@ -92,21 +92,21 @@ static void conv_geom(Layer& l) {
 // row n of the folded view holds time samples r*n .. r*n+r-1.  A k-tap dilation-1 convolution over time is then a
 // convolution over folded rows with block-Toeplitz weights
 //     W'[s][phi*C + co][psi*C + ci] = W[j][co][ci],   j - (k-1)/2 = r*s + psi - phi   (zero when no such tap exists)
-// which turns the N = 32/64 tensor-core tiles of stages 2-3 (bound by shared-memory operand reads: 4 KB of activations
+// (dilated convs: see fold_geom) which turns the N = 32/64 tensor-core tiles of stages 2-3 (bound by shared-memory operand reads: 4 KB of activations
 // per 16/32-cycle MMA) into 128-channel channels-as-M tiles (N = 256 time rows per instruction) at the price of
 // (k + r - 1)/k more MACs.  K-chunks of a folded tap that are structurally zero are skipped (tap_kmask).
 static int fold_factor(const Layer& l) {
-  if (l.kind != kConv || l.dil != 1 || l.c_in != l.c_out) return 0;
+  if (l.kind != kConv || l.c_in != l.c_out) return 0;
   if (l.c_in == 32) return 4;
   if (l.c_in == 64) return 2;
   return 0;
 }
 
 // folded taps of one k-tap conv appended to g (tap table only); returns the number of folded taps
-static int fold_taps(int c, int k, int r, ConvGeom& g, int tap_base) {
+static int fold_taps(int c, int k, int r, ConvGeom& g, int tap_base, int kc = 64) {
   const int hk = (k - 1) / 2;
   const int s_min = floordiv(-hk, r), s_max = floordiv(r - 1 + hk, r);
-  const int kc = 64, per = kc / c;  // folded K-chunk = `per` consecutive time phases
+  const int per = kc / c;  // folded K-chunk = `per` consecutive time phases
   for (int s = s_min; s <= s_max; ++s) {
     const int i = tap_base + (s - s_min);
     g.tap_off[i] = s;
@@ -127,9 +127,15 @@ static void fold_geom(Layer& l) {
   ConvGeom& g = l.fgeom;
   g = ConvGeom{};
   g.c_in = g.n_total = l.fold_r * l.c_in;
-  g.ntaps = fold_taps(l.c_in, l.k, l.fold_r, g, 0);
+  // A dilation-d conv is a dilation-1 conv on each of the d sub-sequences t = d*q + rho: same Toeplitz weights, the
+  // folded rows are taken from one sub-sequence (ConvGeom::rho_d; K-chunk = one time phase, phases are d*C apart).
+  g.ntaps = fold_taps(l.c_in, l.k, l.fold_r, g, 0, l.dil > 1 ? l.c_in : 64);
   g.nseg = 1;
   g.seg_tap_end[0] = g.ntaps;
+  if (l.dil > 1) {
+    g.rho_d = l.dil;
+    g.c_real = l.c_in;
+  }
 }
 
 // ConvTranspose1d(k, s, p=(k-s)/2): output sample s*i + r reads input rows i + off, kernel index j = r + p - s*off
@@ -186,6 +192,8 @@ struct Plan {
   float* cb;         // cond bias [B][C]
   bf16* x_final;     // input of conv_post
   int L_final, C_final;
+  bool post_tc = false;  // conv_post runs as a time-folded tensor-core launch (its output pointer is per call, so it
+  Step post;             // stays outside the graph)
   std::vector<std::pair<std::string, std::tuple<const bf16*, int, int, float>>> debug;  // name -> (ptr, C, L, gain)
 };
 
@@ -258,15 +266,15 @@ static int alloc_layer(Layer& l) {
     VD_CUDA(cudaMalloc(&l.w, wn * sizeof(bf16)));
     VD_CUDA(cudaMalloc(&l.bias, (size_t)l.geom.n_total * sizeof(float)));
     VD_CUDA(cudaMemset(l.bias, 0, (size_t)l.geom.n_total * sizeof(float)));
-    if (l.fold_r) {
-      const size_t fn = (size_t)l.fgeom.ntaps * l.fgeom.n_total * l.fgeom.c_in;
-      VD_CUDA(cudaMalloc(&l.wfold, fn * sizeof(bf16)));
-      VD_CUDA(cudaMalloc(&l.bias_fold, (size_t)l.fgeom.n_total * sizeof(float)));
-      VD_CUDA(cudaMemset(l.bias_fold, 0, (size_t)l.fgeom.n_total * sizeof(float)));
-    }
   } else {
     VD_CUDA(cudaMalloc(&l.wf32, (size_t)l.c_out * l.c_in * l.k * sizeof(float)));
     if (l.kind == kCond) VD_CUDA(cudaMalloc(&l.bias, (size_t)l.c_out * sizeof(float)));
+  }
+  if (l.fold_r) {
+    const size_t fn = (size_t)l.fgeom.ntaps * l.fgeom.n_total * l.fgeom.c_in;
+    VD_CUDA(cudaMalloc(&l.wfold, fn * sizeof(bf16)));
+    VD_CUDA(cudaMalloc(&l.bias_fold, (size_t)l.fgeom.n_total * sizeof(float)));
+    VD_CUDA(cudaMemset(l.bias_fold, 0, (size_t)l.fgeom.n_total * sizeof(float)));
   }
   return 0;
 }
@@ -308,6 +316,7 @@ static WsLayout ws_layout(const vitsdec_decoder* d, int B, int T) {
   w.off_slots = o; o += (size_t)w.nslots * slot;
   w.off_dbg = o;
   if (d->debug_keep) o += align_up(dbg, 1024);
+  o += 4096;  // dilated folded views read (and mask) up to rho_d*r rows past the last utterance of a slot
   w.total = o;
   return w;
 }
@@ -331,10 +340,17 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     ConvGeom g = ly.geom;
     g.B = B; g.L = L;
     const bf16* wts = ly.w;
-    if (d->impl == 0 && d->fold && ly.fold_r && L % ly.fold_r == 0 && ep.mrf == nullptr && ep.bias_b == nullptr) {
+    if (d->impl == 0 && d->fold && ly.fold_r && (L % ly.fold_r == 0 || ly.fgeom.rho_d > 1) && ep.mrf == nullptr &&
+        ep.bias_b == nullptr) {
       // time-folded launch: same bytes viewed as [B][L/r][r*C] (see fold_geom)
       g = ly.fgeom;
-      g.B = B; g.L = L / ly.fold_r;
+      g.B = B;
+      if (g.rho_d > 1) {
+        g.L_real = L;
+        g.L = ceildiv(L, g.rho_d * ly.fold_r);
+      } else {
+        g.L = L / ly.fold_r;
+      }
       wts = ly.wfold;
       s.ep.bias = ly.bias_fold;
     }
@@ -470,6 +486,25 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   pl.x_final = X;
   pl.L_final = L;
   pl.C_final = d->stage_ch.back();
+  pl.post_tc = false;
+  Layer& lp = d->layers[d->l_post];
+  if (d->impl == 0 && d->fold && lp.fold_r && L % lp.fold_r == 0) {
+    Step s{};
+    s.layer = d->l_post;
+    s.L = L;
+    s.xs[0] = X;
+    ConvGeom g = lp.fgeom;
+    g.B = B; g.L = L / lp.fold_r;
+    s.ep.bias = lp.bias_fold;  // zeros: conv_post has no bias (models.py:264)
+    s.ep.mrf_mode = 4;
+    s.ep.post_c = lp.c_in;
+    s.ep.res_gain = s.ep.out_slope = s.ep.mrf_scale = 1.f;
+    s.tc.p.g = g;
+    if (plan_conv_tc(&s.tc, g, s.xs, lp.wfold, d->num_sms, d->desc_mode, true)) return 1;
+    VD_CHECK(s.tc.swap, "conv_post: folded launch must be channels-as-M");
+    pl.post = s;
+    pl.post_tc = true;
+  }
   return 0;
 }
 
@@ -549,6 +584,21 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
     }
   }
   d->l_post = add_layer(d.get(), "conv_post", kPost, d->stage_ch.back(), 1, 7, 1, 1);
+  {
+    // conv_post on the tensor cores: time-folded like the narrow ResBlock convs, the single output channel padded to C
+    // (zero weight rows), tanh + fp32 store in the epilogue (conv_tc.cu EPI 4)
+    Layer& lp = d->layers[d->l_post];
+    const int r = lp.c_in == 32 ? 4 : (lp.c_in == 64 ? 2 : 0);
+    if (r) {
+      lp.fold_r = r;
+      ConvGeom& fg = lp.fgeom;
+      fg = ConvGeom{};
+      fg.c_in = fg.n_total = r * lp.c_in;
+      fg.ntaps = fold_taps(lp.c_in, lp.k, r, fg, 0);
+      fg.nseg = 1;
+      fg.seg_tap_end[0] = fg.ntaps;
+    }
+  }
   if (hp->gin_channels > 0) d->l_cond = add_layer(d.get(), "cond", kCond, hp->gin_channels, c0, 1, 1, 1);
   d->num_real_layers = (int)d->layers.size();
   // Fused MRF: one virtual layer per stage whose segments are the LAST conv of every branch (weights concatenated
@@ -587,7 +637,7 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
         int nft = 0;
         for (int lid : v.members) {
           const Layer& m = d->layers[lid];
-          if (fold_factor(m) != r) r = 0;
+          if (fold_factor(m) != r || m.dil != 1) r = 0;  // one launch = one view: dilation-1 members only
           if (r) nft += floordiv(r - 1 + (m.k - 1) / 2, r) - floordiv(-((m.k - 1) / 2), r) + 1;
         }
         if (r && nft <= kMaxTaps) {
@@ -680,7 +730,7 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
     if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st)) return 1;
     if (launch_replicate_bias(bias, l.bias, l.c_out, 1, st)) return 1;
     if (l.fold_r) {
-      if (launch_pack_conv_fold(w, d->scale_scratch, l.wfold, l.c_in, l.k, l.fold_r, st)) return 1;
+      if (launch_pack_conv_fold(w, d->scale_scratch, l.wfold, l.c_in, l.c_out, l.k, l.fold_r, st)) return 1;
       if (launch_replicate_bias(bias, l.bias_fold, l.c_out, l.fold_r, st)) return 1;
     }
     if (l.mrf_group >= 0) {
@@ -690,8 +740,8 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
         return 1;
       if (v.fold_r &&
           launch_pack_conv_fold(w, d->scale_scratch,
-                                v.wfold + (size_t)l.mrf_ftap_base * v.fgeom.n_total * v.fgeom.c_in, l.c_in, l.k,
-                                v.fold_r, st))
+                                v.wfold + (size_t)l.mrf_ftap_base * v.fgeom.n_total * v.fgeom.c_in, l.c_in, l.c_out,
+                                l.k, v.fold_r, st))
         return 1;
       v.bias_dirty = true;
     }
@@ -711,6 +761,7 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
   } else {
     VD_CHECK(wg == nullptr, "conv_post / cond are not weight-normed in the reference (models.py:264,268)");
     VD_CUDA(cudaMemcpyAsync(l.wf32, w, (size_t)l.c_out * l.c_in * l.k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (l.kind == kPost && l.fold_r && launch_pack_conv_fold(w, nullptr, l.wfold, l.c_in, 1, l.k, l.fold_r, st)) return 1;
     if (l.kind == kCond) {
       VD_CHECK(bias != nullptr, "cond needs a bias");
       VD_CUDA(cudaMemcpyAsync(l.bias, bias, (size_t)l.c_out * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -834,7 +885,13 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     d->ev_pending = true;
     d->prof_conv_launches += (long)plan->steps.size();
   }
-  if (launch_conv_post(plan->x_final, d->layers[d->l_post].wf32, out, B, plan->L_final, plan->C_final, st)) return 1;
+  if (plan->post_tc) {
+    Step s = plan->post;
+    s.ep.out_f32 = out;
+    if (launch_conv_tc(s.tc, s.ep, st)) return 1;
+  } else if (launch_conv_post(plan->x_final, d->layers[d->l_post].wf32, out, B, plan->L_final, plan->C_final, st)) {
+    return 1;
+  }
   ++launches;
   d->last_launches = launches;
   return 0;
@@ -960,7 +1017,7 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
   const bool fold = (desc_mode & 16) != 0;  // test knob: run the time-folded form of a narrow dilation-1 layer
   if (fold) {
     fold_geom(l);
-    VD_CHECK(impl == 0 && l.fold_r && L % l.fold_r == 0, "op_conv: layer has no time-folded form");
+    VD_CHECK(impl == 0 && l.fold_r && (L % l.fold_r == 0 || l.dil > 1), "op_conv: layer has no time-folded form");
   }
   if (alloc_layer(l)) return 1;
   float* scale = nullptr;
@@ -971,7 +1028,7 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
          launch_pack_conv(w, scale, l.w, l.c_out, l.c_in, l.k, st) ||
          launch_replicate_bias(bias, l.bias, l.c_out, 1, st);
     if (!rc && fold)
-      rc = launch_pack_conv_fold(w, scale, l.wfold, l.c_in, l.k, l.fold_r, st) ||
+      rc = launch_pack_conv_fold(w, scale, l.wfold, l.c_in, l.c_out, l.k, l.fold_r, st) ||
            launch_replicate_bias(bias, l.bias_fold, l.c_out, l.fold_r, st);
   } else {
     rc = launch_wn_scale(w, nullptr, scale, l.c_in, l.c_out * l.k, st) ||
@@ -982,6 +1039,10 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
   if (!rc) {
     ConvGeom g = fold ? l.fgeom : l.geom;
     g.B = B; g.L = fold ? L / l.fold_r : L;
+    if (fold && g.rho_d > 1) {  // NB reads up to rho_d*r rows past the end of x (masked to zero in the kernel)
+      g.L_real = L;
+      g.L = ceildiv(L, g.rho_d * l.fold_r);
+    }
     ConvEpilogue e{};
     e.bias = fold ? l.bias_fold : l.bias;
     e.res[0] = static_cast<const bf16*>(res);

@@ -40,10 +40,11 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
 }
 
 // Conv1d weight [co][ci][k] (C x C, dilation 1) -> time-folded block-Toeplitz operand [s][phi*C+co][psi*C+ci]
-// (decoder.cu fold_geom): folded row n holds time samples r*n..r*n+r-1; tap j contributes where
+// (decoder.cu fold_geom; output channels c_out..C-1 are zero padding): folded row n holds time samples r*n..r*n+r-1; tap j contributes where
 // j - (k-1)/2 = r*(s_min+s) + psi - phi.
 __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                      __nv_bfloat16* __restrict__ wp, int C, int k, int r, int s_min, int ntaps) {
+                                      __nv_bfloat16* __restrict__ wp, int C, int c_out, int k, int r, int s_min,
+                                      int ntaps) {
   const int rc = r * C;
   const long total = (long)ntaps * rc * rc;
   const int hk = (k - 1) / 2;
@@ -54,7 +55,7 @@ __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* 
     const int psi = cc / C, ci = cc % C, phi = nn / C, co = nn % C;
     const int j = r * s + psi - phi + hk;
     float val = 0.f;
-    if (j >= 0 && j < k) val = w[((long)co * C + ci) * k + j] * scale[co];
+    if (j >= 0 && j < k && co < c_out) val = w[((long)co * C + ci) * k + j] * (scale ? scale[co] : 1.f);
     wp[i] = __float2bfloat16_rn(val);
   }
 }
@@ -206,14 +207,14 @@ int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int 
   VD_CUDA(cudaGetLastError());
   return 0;
 }
-int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp, int C, int k, int r,
+int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp, int C, int c_out, int k, int r,
                           cudaStream_t st) {
   const int hk = (k - 1) / 2;
   const int s_min = -((hk + r - 1) / r), s_max = (r - 1 + hk) / r;  // floor(-hk/r), floor((r-1+hk)/r)
   const int ntaps = s_max - s_min + 1;
   const long total = (long)ntaps * r * C * r * C;
-  pack_conv_fold_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, C, k, r, s_min,
-                                                                                        ntaps);
+  pack_conv_fold_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, C, c_out, k, r,
+                                                                                        s_min, ntaps);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

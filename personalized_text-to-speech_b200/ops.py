@@ -18,6 +18,12 @@ def conv1d_cl(x, w, bias=None, dilation=1, res=None, res_gain=10.0, out_slope=1.
     w = w.float().contiguous()
     bias = None if bias is None else bias.float().contiguous()
     y = torch.empty((B, L, c_out), dtype=torch.bfloat16, device=x.device)
+    if (desc_mode & 16) and dilation > 1:
+        # the dilated folded view reads (and masks) up to dilation*r rows past the end of x: give it NaN slack, like
+        # the decoder's workspace does with its tail bytes
+        buf = torch.full((x.numel() + 4096,), float("nan"), dtype=torch.bfloat16, device=x.device)
+        buf[:x.numel()].copy_(x.reshape(-1))
+        x = buf[:x.numel()].view(B, L, c_in)
     st = torch.cuda.current_stream(x.device).cuda_stream
     _capi.check(_capi.lib().vitsdec_op_conv1d(x.device.index or 0, _ptr(x), _ptr(w), _ptr(bias), _ptr(res),
                                               float(res_gain), float(out_slope), _ptr(y), B, L, c_in, c_out, k,

@@ -153,8 +153,17 @@ def test_chunked_long_form_matches_unchunked():
         full = G(z, g)
         chunked = vitsdec.decode_chunked(G, z, g, chunk_frames=256, halo=12, hop=hp.hop)
     assert chunked.shape == full.shape
-    # the receptive field is covered by the halo; what is left is bf16 re-rounding of identical values
-    assert snr_db(full.cpu(), chunked.cpu()) > 60.0
+    # The receptive field is covered by the halo.  What is left is bf16 re-rounding: a chunk starts at another phase of
+    # the time-folded tiles, so its fp32 sums are formed in another order than the unchunked decode's.
+    assert snr_db(full.cpu(), chunked.cpu()) > 42.0
+    ref = generator_forward_torch(hp, to_torch_state_dict(sd), z.cpu(), g.cpu())
+    check(ref, chunked.cpu())
+    check(ref, full.cpu())
+    G.set_option("fold", 0)   # plain tiles sum in a position-independent order: chunks reproduce the full decode
+    with torch.no_grad():
+        full0 = G(z, g)
+        chunked0 = vitsdec.decode_chunked(G, z, g, chunk_frames=256, halo=12, hop=hp.hop)
+    assert snr_db(full0.cpu(), chunked0.cpu()) > 60.0
 
 
 def test_decode_host_entry_matches_device_entry():

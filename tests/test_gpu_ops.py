@@ -147,6 +147,28 @@ def test_time_folded_conv_matches_torch_and_unfolded(case):
     assert float(((y.float() - y0.float()).abs() / (y0.float().abs() + 1e-3)).max()) < 2 ** -7
 
 
+@pytest.mark.parametrize("case", [(2, 1000, 32, 3, 3, False), (3, 777, 32, 11, 5, True), (2, 3111, 32, 7, 3, False),
+                                  (2, 517, 64, 7, 3, True), (1, 4000, 64, 11, 5, False), (1, 1, 32, 11, 5, False),
+                                  (1, 7, 64, 3, 5, True), (16, 260, 32, 7, 5, False), (2, 2049, 64, 3, 3, False),
+                                  (3, 3072, 32, 11, 3, True), (2, 2560, 64, 11, 5, True)],
+                         ids=lambda c: "B%d_L%d_C%d_k%d_d%d_r%d" % c)
+def test_dilated_time_folded_conv_matches_torch_and_unfolded(case):
+    """Dilated convs fold per sub-sequence t = d*q + rho (5-d TMA view); ragged ends are masked in shared memory."""
+    B, L, C, k, d, use_res = case
+    torch.manual_seed(L * 7 + k + d)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, L, C, device=dev).bfloat16()
+    w = torch.randn(C, C, k, device=dev) / (C * k) ** 0.5
+    b = torch.randn(C, device=dev) * 0.1
+    res = torch.randn(B, L, C, device=dev).bfloat16() if use_res else None
+    y = ops.conv1d_cl(x, w, b, dilation=d, res=res, res_gain=10.0, out_slope=0.1, impl=0, desc_mode=16)
+    y0 = ops.conv1d_cl(x, w, b, dilation=d, res=res, res_gain=10.0, out_slope=0.1, impl=0, desc_mode=0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all()
+    assert rel_err(y, ref_conv(x, w, b, d, res, 10.0, 0.1)) < REL_TOL
+    assert float(((y.float() - y0.float()).abs() / (y0.float().abs() + 1e-3)).max()) < 2 ** -7
+
+
 def ref_pair(x, w1, b1, w2, b2, d, slope=0.1):
     """One ResBlock1 iteration (modules.py:211-221) on the a-form input, h rounded to bf16 like the kernel stores it."""
     k = w1.shape[2]
