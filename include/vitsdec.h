@@ -97,7 +97,9 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
  *          "desc_mode" = debug knob of the UMMA descriptor (0 is the correct setting);
  *          "debug_keep" = 1 keep named intermediates for vitsdec_debug_read; "profile" = 1 see below;
  *          "fuse_pairs" = 0 run every ResBlock conv as its own launch (default 1: fused pairs where they fit);
- *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph). */
+ *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph);
+ *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
+ *          "pairf" = 0 keeps fused pairs on conv_pair.cu (default 1: time-folded conv_pairf.cu). */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
 
@@ -133,6 +135,13 @@ VITSDEC_API int vitsdec_op_conv1d(int device, const void* x_dev, const float* w_
 VITSDEC_API int vitsdec_op_resblock_pair(int device, const void* x_dev, const float* w1_dev, const float* b1_dev,
                                          const float* w2_dev, const float* b2_dev, void* y_dev, int batch, int length,
                                          int channels, int k, int dilation, float slope, void* stream);
+
+/* The same ResBlock1 iteration through the time-folded fused kernel (conv_pairf.cu: both convs as 128-virtual-channel
+ * channels-as-M tiles, weights streamed).  length must be a multiple of 128 / channels. */
+VITSDEC_API int vitsdec_op_resblock_pair_folded(int device, const void* x_dev, const float* w1_dev, const float* b1_dev,
+                                                const float* w2_dev, const float* b2_dev, void* y_dev, int batch,
+                                                int length, int channels, int k, int dilation, float slope,
+                                                void* stream);
 
 /* Same for ConvTranspose1d(c_in, c_out, k, stride, padding=(k-stride)/2) in polyphase form:
  *   w_dev fp32 [c_in, c_out, k]; y_dev bf16 [batch, length*stride, c_out]. */

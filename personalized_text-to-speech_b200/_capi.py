@@ -62,6 +62,7 @@ SIGNATURES = {
     "vitsdec_debug_set_trace": (_i, [_vp]),
     "vitsdec_op_conv1d": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vitsdec_op_resblock_pair": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "vitsdec_op_resblock_pair_folded": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "vitsdec_op_conv_transpose1d": (_i, [_i, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

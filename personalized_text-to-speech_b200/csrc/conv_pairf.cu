@@ -1,0 +1,511 @@
+// Time-folded fused ResBlock1 pair on the sm_100a tensor cores (narrow stages, C = 32 / 64):
+//     y = lrelu( c2( lrelu( c1(a) + b1 ) ) + b2 + x(a) )          (modules.py:211-221, one loop iteration)
+// Same fusion as conv_pair.cu (h never leaves the SM), but both convs run on the folded view of decoder.cu
+// fold_geom: r = 128/C time samples per row, 128 virtual channels, block-Toeplitz weights, channels-as-M tiles
+// (M = 128 virtual output channels, N = up to 256 folded rows per instruction).  The N = 32/64 time-as-M tiles of
+// conv_pair.cu read 4 KB of activations from shared memory per 16/32-cycle MMA and run at 25-45 % of the tensor
+// rate; here one MMA reads 4 KB of weights + 8 KB of activations per 128 cycles.
+//
+// Per CTA tile: WO folded output rows (c2's N), HR = WO + nt - 1 rows of h (c2's halo).
+//   c1 (dilation d): for each sub-sequence rho of its dilated view, D1[:, rho*N1 ..] = sum_taps W1' . X(rho, phase)
+//        X sub-tiles arrive by TMA (one per (rho, phase), 5-d view), weights stream through a ring
+//   h  : TMEM -> registers (+b1, leaky-relu, zero outside the utterance) -> shared memory in the NATURAL folded
+//        layout (row = sample / r, K-chunk = sample % r), i.e. c2's swizzled K-major B operand; a dilated c1
+//        produces samples d*(r*n+phi)+rho, so this store is where the sub-sequences are interleaved back
+//   c2 (dilation 1): D2 = sum_taps W2' . H
+//   out: D2 + b2 + x (residual re-read from global memory: the tile was loaded a moment ago, L2-hot) -> lrelu -> bf16
+// TMEM: D1 = columns [0, d*N1), D2 = columns [256, 256+WO).  MMA order c1(0) c2(0) c1(1) c2(1) ...: the output
+// epilogue of tile i overlaps c1(i+1); only the h epilogue is exposed.
+#include <algorithm>
+
+#include "common.cuh"
+#include "conv_pairf.h"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace vd {
+
+#ifndef VITSDEC_TRACE
+#define VITSDEC_TRACE 0
+#endif
+constexpr bool kPfTrace = VITSDEC_TRACE != 0;
+constexpr int kPfEpiWarps = 16;
+constexpr int kPfThreads = 96 + 32 * kPfEpiWarps;  // warp 0: weight producer, 1: MMA issuer, 2: x producer, 3..18: epilogue
+
+// K-chunks are always 64 virtual channels = 128-byte rows (SWIZZLE_128B): with 64-byte rows (one 32-channel phase
+// per chunk) the 32-byte K=16 slices of 8 consecutive rows fall on the same banks twice and every MMA ran at half
+// rate (320 vs 160 cycles at N=256, profiles/r01_trace_pairf.txt).  For C = 32 a chunk is two time phases.
+template <int CH>
+__global__ void __launch_bounds__(kPfThreads, 1)
+conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ PairFParams p) {
+  constexpr int KC = 64, ROWB = 128;
+  constexpr int R = 128 / CH;              // time samples (phases) per folded row
+  constexpr int RSH = CH == 32 ? 2 : 1;    // log2(R)
+  constexpr int PPC = KC / CH;             // phases per K-chunk
+  constexpr int NCH = 2;                   // K-chunks per folded row
+  constexpr int B_STAGE = 128 * ROWB;      // one K-chunk of one folded tap: [128 virtual out channels][64]
+  constexpr int HS_SUB = 256 * ROWB;       // one K-chunk of the h tile
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int xs_sub = p.XR * ROWB;
+  uint8_t* XS = smem;                               // [d][NCH] sub-tiles of XR rows
+  uint8_t* HS = XS + p.d * NCH * xs_sub;            // [NCH] chunks of 256 rows
+  uint8_t* WS = HS + NCH * HS_SUB;                  // weight ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(WS + p.nw * B_STAGE);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = bars + 1;
+  uint64_t* d1_full = bars + 2;
+  uint64_t* h_ready = bars + 3;
+  uint64_t* d2_full = bars + 4;
+  uint64_t* d2_empty = bars + 5;
+  uint64_t* w_full = bars + 8;
+  uint64_t* w_empty = w_full + kPfMaxW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + kPfMaxW);
+  float* sbias = reinterpret_cast<float*>(bars + 32);                 // 256 B of barriers, then 2 x 128 floats
+  uint8_t* scratch_base = reinterpret_cast<uint8_t*>(sbias) + 1024;   // 16 warps x 1 KB
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NW = p.nw;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    mbar_init(d1_full, 1);
+    mbar_init(h_ready, kPfEpiWarps);
+    mbar_init(d2_full, 1);
+    mbar_init(d2_empty, kPfEpiWarps);
+    for (int i = 0; i < kPfMaxW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 256; i += kPfThreads) sbias[i] = i < 128 ? p.bias1[i % CH] : p.bias2[i % CH];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int my_tiles =
+      p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int dR = p.d * R;
+  // first row of sub-sequence rho that holds a sample >= R*hbase:  floor((R*hbase - rho) / (d*R))
+  auto nlo_of = [&](int hbase, int rho) -> int {
+    return (int)p.div_dr.quot((uint32_t)(R * hbase - rho + 1024 * dR)) - 1024;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight producer: c1's chunks, then c2's, per tile
+    if (lane == 0) {
+      uint32_t itw = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        for (int conv = 0; conv < 2; ++conv) {
+          for (int ch = 0; ch < NCH; ++ch) {
+            for (int tap = 0; tap < p.nt; ++tap) {
+              if (!((p.kmask[tap] >> ch) & 1u)) continue;
+              const uint32_t sb = itw % NW;
+              mbar_wait(&w_empty[sb], ((itw / NW) & 1) ^ 1);
+              mbar_expect_tx(&w_full[sb], B_STAGE);
+              tma_load_3d(&tmW, &w_full[sb], WS + sb * B_STAGE, ch * KC, 0, conv * p.nt + tap);
+              ++itw;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ x producer: d*R sub-tiles per tile
+    if (lane == 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const uint32_t tile = blockIdx.x + i * gridDim.x;
+        uint32_t b, mt;
+        p.div_m.divmod(tile, b, mt);
+        const int hbase = (int)mt * p.WO + p.smin;
+        mbar_wait(x_empty, (i & 1) ^ 1);
+        mbar_expect_tx(x_full, p.d * NCH * xs_sub);
+        for (int rho = 0; rho < p.d; ++rho) {
+          const int row0 = nlo_of(hbase, rho) + p.smin;
+          for (int ch = 0; ch < NCH; ++ch) {
+            uint8_t* dst = XS + (rho * NCH + ch) * xs_sub;
+            // dilated view [C][rho][phase][row][b]: a chunk is PPC phases (box {C, 1, PPC, XR, 1} -> 128-byte rows)
+            if (p.d > 1) tma_load_5d(&tmX, x_full, dst, 0, rho, ch * PPC, row0, (int)b);
+            else tma_load_5d(&tmX, x_full, dst, 0, ch, 0, row0, (int)b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform; elected lane issues)
+    const uint32_t idesc1 = umma_idesc_f16(p.N1, false), idesc2 = umma_idesc_f16(p.WO, false);
+    constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
+    const uint32_t leader = elect_one();
+    const uint32_t x_lo0 = umma_desc_lo(smem_u32(XS)), h_lo0 = umma_desc_lo(smem_u32(HS));
+    const uint32_t w_lo0 = umma_desc_lo(smem_u32(WS));
+    uint32_t itw = 0;
+    auto c1 = [&](int i) {
+      const bool tr = kPfTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
+      if (tr) p.trace[i * 12 + 8] = clock64();
+      mbar_wait(x_full, i & 1);
+      tc_fence_after();
+      if (tr) p.trace[i * 12 + 0] = clock64();
+      if (p.d > 1) {
+        // rows of the dilated view past the utterance end alias the next utterance: zero them (see conv_tc.cu)
+        const uint32_t tile = blockIdx.x + i * gridDim.x;
+        uint32_t b, mt;
+        p.div_m.divmod(tile, b, mt);
+        const int hbase = (int)mt * p.WO + p.smin;
+        bool wrote = false;
+        for (int rho = 0; rho < p.d; ++rho) {
+          const int idx = p.rows_rho - 1 - (nlo_of(hbase, rho) + p.smin);
+          if (idx < 0 || idx >= p.XR) continue;
+          for (int psi = 0; psi < R; ++psi) {
+            const int rem = p.L - rho - p.d * psi;
+            const int nlim = rem > 0 ? (int)p.div_dr.quot(rem + dR - 1) : 0;
+            if (nlim < p.rows_rho) {
+              // phase psi = CH channels of the row: 16-byte chunks (psi % PPC) * CH/8 + lane, 128B-swizzled
+              if (lane < CH / 8) {
+                const uint32_t c16 = (uint32_t)((psi % PPC) * (CH / 8) + lane);
+                *reinterpret_cast<uint4*>(XS + (rho * NCH + psi / PPC) * xs_sub + idx * ROWB + ((c16 ^ (idx & 7)) << 4)) =
+                    make_uint4(0, 0, 0, 0);
+              }
+              wrote = true;
+            }
+          }
+        }
+        if (wrote) {
+          fence_proxy_async();
+          __syncwarp();
+        }
+      }
+      uint32_t started = 0;
+      for (int ch = 0; ch < NCH; ++ch) {
+        for (int tap = 0; tap < p.nt; ++tap) {
+          if (!((p.kmask[tap] >> ch) & 1u)) continue;
+          const uint32_t sb = itw % NW;
+          mbar_wait(&w_full[sb], (itw / NW) & 1);
+          tc_fence_after();
+          const uint32_t w_lo = w_lo0 + sb * (B_STAGE >> 4);
+          for (int rho = 0; rho < p.d; ++rho) {
+            const uint32_t x_lo = x_lo0 + ((uint32_t)((rho * NCH + ch) * xs_sub + tap * ROWB) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < KC / 16; ++kk)
+              umma_f16_lohi(tmem_base + rho * p.N1, w_lo + kk * 2, desc_hi, x_lo + kk * 2, desc_hi, idesc1,
+                            kk == 0 ? started : 1u, leader);
+          }
+          started = 1;
+          if (leader) umma_commit(&w_empty[sb]);
+          ++itw;
+        }
+      }
+      if (leader) {
+        umma_commit(d1_full);
+        umma_commit(x_empty);
+      }
+      if (tr) p.trace[i * 12 + 1] = clock64();
+    };
+    auto c2 = [&](int i) {
+      const bool tr = kPfTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
+      if (tr) p.trace[i * 12 + 9] = clock64();
+      mbar_wait(h_ready, i & 1);
+      mbar_wait(d2_empty, (i & 1) ^ 1);
+      tc_fence_after();
+      if (tr) p.trace[i * 12 + 2] = clock64();
+      uint32_t started = 0;
+      for (int ch = 0; ch < NCH; ++ch) {
+        for (int tap = 0; tap < p.nt; ++tap) {
+          if (!((p.kmask[tap] >> ch) & 1u)) continue;
+          const uint32_t sb = itw % NW;
+          mbar_wait(&w_full[sb], (itw / NW) & 1);
+          tc_fence_after();
+          const uint32_t w_lo = w_lo0 + sb * (B_STAGE >> 4);
+          const uint32_t h_lo = h_lo0 + ((uint32_t)(ch * HS_SUB + tap * ROWB) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk)
+            umma_f16_lohi(tmem_base + 256, w_lo + kk * 2, desc_hi, h_lo + kk * 2, desc_hi, idesc2,
+                          kk == 0 ? started : 1u, leader);
+          started = 1;
+          if (leader) umma_commit(&w_empty[sb]);
+          ++itw;
+        }
+      }
+      if (leader) umma_commit(d2_full);
+      if (tr) p.trace[i * 12 + 3] = clock64();
+    };
+    if (my_tiles > 0) c1(0);
+    for (int i = 0; i < my_tiles; ++i) {
+      c2(i);
+      if (i + 1 < my_tiles) c1(i + 1);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue warps: h of tile i, then its output
+    const int q = warp & 3;                 // TMEM lane quadrant (hardware rule: warp % 4)
+    const int sub = (warp - 3) >> 2;        // which of the quadrant's four warps
+    uint8_t* scratch = scratch_base + (warp - 3) * 1024;
+    const int phi = (q * 32) / CH;          // time phase of this warp's virtual channels (phase * C + channel)
+    // fragment layout (tmem_ld_frag): this thread's channels are q*32 + 8m + lane/4, m = 0..3
+    float b1f[4], b2f[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      b1f[m] = sbias[q * 32 + 8 * m + (lane >> 2)];
+      b2f[m] = sbias[128 + q * 32 + 8 * m + (lane >> 2)];
+    }
+    const int co0 = (q * 32) % CH;          // first real channel of this warp's 32 virtual channels
+    uint8_t* const dummy = scratch + lane * 16;  // stmatrix target for rows that fall outside the h tile
+    const float slope = p.slope, res_gain = p.res_gain;
+    const int d = p.d, N1 = p.N1, HR = p.HR, Lf = p.Lf, WO = p.WO;
+    const int ipr = N1 / 16;                // h items per sub-sequence
+    const int n_hitems = d * ipr, n_oitems = WO / 16;
+    ConvEpilogue ep{};
+    ep.res[0] = p.x;
+    ep.out = p.out;
+
+    for (int i = 0; i < my_tiles; ++i) {
+      const uint32_t tile = blockIdx.x + i * gridDim.x;
+      uint32_t b, mt;
+      p.div_m.divmod(tile, b, mt);
+      const int n0 = (int)mt * WO;
+      const int hbase = n0 + p.smin;
+
+      // ---- output items of this warp: residual loads of the first one go out before anything is waited for
+      auto ocoords = [&](int it, EpiItem& e) {
+        const int t = n0 + it * 16;
+        e.b = (int)b;
+        e.n = q * 32;
+        e.rows_valid = min(16, max(0, Lf - t));
+        e.row0 = (long)b * Lf + t;
+        e.base = e.row0 * 128 + q * 32;
+        e.tcol = 256 + it * 16;
+      };
+      EpiLoads ld;
+      EpiItem cur{};
+      if (sub < n_oitems) {
+        ocoords(sub, cur);
+        epiT_issue_loads<2>(ep, cur, 128, lane, ld);
+      }
+
+      // ---- h = lrelu(c1 + b1), zero outside the utterance, stored as c2's B operand in the natural folded layout
+      mbar_wait(d1_full, i & 1);
+      tc_fence_after();
+      const bool tr = kPfTrace && p.trace && blockIdx.x == 0 && warp == 3 && lane == 0 && i < 256;
+      if (tr) p.trace[i * 12 + 4] = clock64();
+      for (int it = sub; it < n_hitems; it += 4) {
+        int rho = 0, jn = it;
+        while (jn >= ipr) { jn -= ipr; ++rho; }
+        const int u = d * phi + rho;                       // sample offset inside a row of the dilated view
+        const int phase = u & (R - 1), rowoff = u >> RSH;  // its place in the natural view
+        const int rel0 = d * (nlo_of(hbase, rho) + jn * 16) + rowoff - hbase;  // h-tile row of column 0; +d per column
+        uint32_t a[16];
+        __syncwarp();
+        tmem_ld_frag(tmem_base + ((uint32_t)(q * 32) << 16) + it * 16, a);
+        // stmatrix row addresses: lane i stores row (i & 7) of the 8-channel chunk (i >> 3), for columns cg*8 + (i & 7)
+        uint32_t haddr[2];
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          const int rel = rel0 + d * (cg * 8 + (lane & 7));
+          const int vcol0 = phase * CH + co0;   // first virtual channel of this warp's 32 in the natural folded row
+          const uint32_t c16 = (uint32_t)((vcol0 & (KC - 1)) >> 3) + (lane >> 3);
+          haddr[cg] = (rel >= 0 && rel < HR)
+                          ? smem_u32(HS + (vcol0 >> 6) * HS_SUB + rel * ROWB + ((c16 ^ (rel & 7)) << 4))
+                          : smem_u32(dummy);
+        }
+        // zero outside the utterance (c2's zero padding): per column held by this thread
+        bool inside[2][2];
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int arow = rel0 + d * (cg * 8 + 2 * (lane & 3) + e) + hbase;
+            inside[cg][e] = arow >= 0 && arow < Lf;
+          }
+        tmem_ld_wait();
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            float v0 = __uint_as_float(a[frag_idx(m, cg, 0)]) + b1f[m];
+            float v1 = __uint_as_float(a[frag_idx(m, cg, 1)]) + b1f[m];
+            v0 = inside[cg][0] ? fmaxf(v0, v0 * slope) : 0.f;
+            v1 = inside[cg][1] ? fmaxf(v1, v1 * slope) : 0.f;
+            const __nv_bfloat162 o = __floats2bfloat162_rn(v0, v1);
+            pk[m] = *reinterpret_cast<const uint32_t*>(&o);
+          }
+          stmatrix_x4_trans(haddr[cg], pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_ready);
+      if (tr) p.trace[i * 12 + 5] = clock64();
+
+      // ---- y = lrelu(c2 + b2 + x): same item pipeline as conv_tc.cu's channels-as-M epilogue
+      mbar_wait(d2_full, i & 1);
+      tc_fence_after();
+      if (tr) p.trace[i * 12 + 6] = clock64();
+      for (int it = sub; it < n_oitems; it += 4) {
+        uint32_t acc[kIW];
+        float v[kIW];
+        __syncwarp();
+        tmem_ld_frag(tmem_base + ((uint32_t)(q * 32) << 16) + cur.tcol, acc);
+        tmem_ld_wait();
+        epiT_accumulate<2>(ep, b2f, scratch, cur, 128, lane, res_gain, acc, ld, v);
+        const bool last = it + 4 >= n_oitems;
+        if (last) {  // accumulator fully read by this warp: hand D2 back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d2_empty);
+        }
+        const EpiItem done = cur;
+        if (!last) {
+          ocoords(it + 4, cur);
+          epiT_issue_loads<2>(ep, cur, 128, lane, ld);
+        }
+        epiT_store<2>(ep, scratch, done, 128, lane, slope, 1.f, v);
+      }
+      if (tr) p.trace[i * 12 + 7] = clock64();
+      if (sub >= n_oitems) {  // a warp without output items still owes its arrival
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                   bool swizzle);
+
+static constexpr int kPfSmemBudget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 1024 /*bias*/ - 16384 /*scratch*/;
+
+static int pf_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+struct PfGeom {
+  int r, nt, smin, WO, HR, N1, XR, nw;
+  bool ok;
+};
+
+static PfGeom pf_geom(int channels, int k, int dil) {
+  PfGeom g{};
+  g.ok = false;
+  if ((channels != 32 && channels != 64) || k % 2 == 0 || k > 15 || dil < 1 || dil > 8) return g;
+  // C = 32 with a dilated c1 would need two time phases side by side in one 128-byte shared-memory row (TMA box
+  // {32, 1, 2, rows}); that load did not produce the expected layout on hardware (tools/probes/tma_box_probe.cu) and the
+  // 64-byte-row alternative runs the MMAs at half rate, so those pairs stay on conv_pair.cu.
+  if (channels == 32 && dil > 1) return g;
+  const int r = 128 / channels, hk = (k - 1) / 2, rowb = 128;
+  g.r = r;
+  g.smin = pf_floordiv(-hk, r);
+  g.nt = pf_floordiv(r - 1 + hk, r) - g.smin + 1;
+  if (g.nt > kPfMaxTaps) return g;
+  for (int wo = 240; wo >= 64; wo -= 16) {
+    const int hr = wo + g.nt - 1;
+    if (hr > 256) continue;
+    // rows of one sub-sequence that hold a sample of the h tile (hr*r consecutive samples)
+    const int need = dil == 1 ? hr : (hr * r - 1) / (dil * r) + 2;
+    const int n1 = (need + 15) / 16 * 16;
+    if (dil * n1 > 256) continue;
+    const int xr = (n1 + g.nt - 1 + 7) / 8 * 8;
+    if (xr > 256) continue;
+    const int fixed = dil * 2 * xr * rowb + 2 * 256 * rowb;
+    const int nw = std::min(kPfMaxW, (kPfSmemBudget - fixed) / (128 * rowb));
+    if (nw < 3) continue;
+    g.WO = wo; g.HR = hr; g.N1 = n1; g.XR = xr; g.nw = nw;
+    g.ok = true;
+    return g;
+  }
+  return g;
+}
+
+int pairf_taps(int channels, int k) { return pf_geom(channels, k, 1).nt; }
+bool pairf_supported(int channels, int k, int dil) { return pf_geom(channels, k, dil).ok; }
+// Where the folded kernel beats conv_pair.cu inside the 16 x 10 s decode (ncu launch lists, profiles/): C=32 k=11 d=1
+// 271 vs 300 us.  Ties elsewhere (C=32 k=7: 229 vs 226; C=64 k=11 vs the two unfused folded convs: 358 vs 347), losses
+// for k=3: the exposed h epilogue and the output epilogue's shared-memory traffic (it slows the overlapping c1 MMAs
+// from 160 to 260 cycles) eat what the wider MMAs gain (profiles/r01_trace_pairf.txt).
+bool pairf_preferred(int channels, int k, int dil) {
+  return pairf_supported(channels, k, dil) && dil == 1 && channels == 32 && k >= 11;
+}
+
+int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
+                    const __nv_bfloat16* w_fold, int num_sms) {
+  const PfGeom g = pf_geom(channels, k, dil);
+  VD_CHECK(g.ok, "conv_pairf: unsupported shape");
+  VD_CHECK(L % g.r == 0, "conv_pairf: the utterance length must be a multiple of the fold factor");
+  PairFParams& p = pl->p;
+  p.B = B; p.L = L; p.Lf = L / g.r; p.d = dil;
+  p.WO = g.WO; p.HR = g.HR; p.N1 = g.N1; p.XR = g.XR; p.nt = g.nt; p.smin = g.smin; p.nw = g.nw;
+  const int hk = (k - 1) / 2;
+  for (int t = 0; t < g.nt; ++t) {
+    uint32_t mask = 0;
+    for (int psi = 0; psi < g.r; ++psi)
+      for (int phi = 0; phi < g.r; ++phi)
+        if (std::abs(g.r * (g.smin + t) + psi - phi) <= hk) mask |= 1u << (psi * channels / 64);  // 64-channel chunks
+    p.kmask[t] = mask;
+  }
+  p.rows_rho = (L + dil * g.r - 1) / (dil * g.r);
+  p.m_tiles = (p.Lf + p.WO - 1) / p.WO;
+  p.total_tiles = B * p.m_tiles;
+  p.div_m.init(p.m_tiles);
+  p.div_dr.init(dil * g.r);
+  p.x = x;
+  p.trace = nullptr;
+  pl->channels = channels;
+  pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  const int rowb = 128;
+  pl->smem = 1024 + (size_t)dil * 2 * g.XR * rowb + (size_t)2 * 256 * rowb + (size_t)g.nw * 128 * rowb + 256 + 1024 +
+             16384;
+  if (dil > 1) {
+    // [C][rho][phase][row][utterance]: sample t = dil*(r*row + phase) + rho
+    // a K-chunk = 64/C phases: box {C, 1, 64/C, XR, 1} lands as 128-byte rows [phase][channel]
+    if (encode_tmap_act(&pl->tmX, x, channels, dil, channels, g.r, (uint64_t)dil * channels, p.rows_rho,
+                        (uint64_t)dil * g.r * channels, B, (uint64_t)L * channels, g.XR, 64 / channels))
+      return 1;
+  } else {
+    if (encode_tmap_act(&pl->tmX, x, 64, 2, 64, 1, 128, p.Lf, 128, B, (uint64_t)L * channels, g.XR, 1)) return 1;
+  }
+  if (encode_tmap_3d(&pl->tmW, w_fold, 128, 128, 2 * g.nt, 64, 128, true)) return 1;
+  return 0;
+}
+
+template <int CH>
+static int launch_pairf_inst(const PairFPlan& pl, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VD_CUDA(cudaFuncSetAttribute(conv_pairf_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_pairf_kernel<CH><<<pl.grid, kPfThreads, pl.smem, stream>>>(pl.tmX, pl.tmW, pl.p);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv_pairf(PairFPlan& pl, const float* bias1, const float* bias2, float slope, __nv_bfloat16* out,
+                      cudaStream_t stream) {
+  pl.p.bias1 = bias1;
+  pl.p.bias2 = bias2;
+  pl.p.slope = slope;
+  pl.p.res_gain = 1.f / slope;
+  pl.p.out = out;
+  if (pl.channels == 32) return launch_pairf_inst<32>(pl, stream);
+  if (pl.channels == 64) return launch_pairf_inst<64>(pl, stream);
+  set_error("conv_pairf: no kernel instance");
+  return 1;
+}
+
+}  // namespace vd

@@ -15,7 +15,9 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "conv_pairf.h"
 #include "conv_tc.h"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace vd {
@@ -27,7 +29,6 @@ constexpr int kMaxNB = 8;      // weight-tile stages when weights are streamed
 #endif
 constexpr bool kTrace = VITSDEC_TRACE != 0;
 constexpr int kEpiWarps = 16;  // four warps per TMEM lane quadrant: the epilogue is instruction-latency bound, TLP hides it
-constexpr int kIW = 16;        // epilogue work item: 32 rows (TMEM lanes of one warp) x kIW output columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - 8192 /*bias*/ - 16384 /*scratch*/;
 
@@ -42,232 +43,6 @@ struct TcCfg {
   static constexpr int TMEM_COLS = NBUF * ACC_COLS;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
-
-// Epilogue work item = 32 rows x 16 output columns per warp (one row per thread).  Global reads (residuals) are
-// issued one item AHEAD of their use so their DRAM/L2 latency overlaps the TMEM load, the math and the stores of the
-// current item.  Sixteen epilogue warps (four per scheduler) because the per-item instruction stream is a long
-// dependent chain: with two warps per scheduler it ran at ~7 cycles/instruction and bounded every k=3 layer
-// (profiles/r01_trace_probe.txt).
-//
-// Per-warp 1 KB transpose scratch: a 32-row x 32-byte item, 16-byte chunks XOR-swizzled so that both access patterns
-// below are bank-conflict free.  Threads OWN rows for the math (TMEM lane == row), but global memory wants each warp
-// instruction to cover contiguous row segments (16 rows x 32 B per LDG/STG.128 instead of 32 rows x 16 B).
-__device__ __forceinline__ uint32_t scr_off(int row, int chunk) { return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4); }
-
-constexpr int kMaxRes = kMaxSeg - 1;
-struct EpiLoads {
-  uint4 res[kMaxRes][2];  // residual tensors, COALESCED mapping: element j = row 16*j + lane/2, chunk lane%2
-};
-
-__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-
-// One epilogue work item: rows [row0, row0+32) x columns [n, n+kIW) of utterance b; rows_valid of them exist.
-struct EpiItem {
-  int b, n, rows_valid;
-  long row0;       // b*L + t of lane 0's row
-  long base;       // channels-as-M: element offset of (first row of the item, this warp's first channel)
-  uint32_t tcol;   // TMEM column of the item inside its accumulator buffer
-};
-
-// EPI specialisation: straight-line epilogue code for the common cases (the generic path re-tests half a dozen
-// launch constants per item, and a lone warp pays ~20-30 cycles per resolved branch):
-//   0 generic (runtime flags: per-utterance bias, any residual count, fp32 MRF fallback)
-//   1 plain (bias + leaky-relu)      2 one residual      3 three residuals + 1/nk scale (fused MRF)
-//   4 conv_post on the folded view (tanh, fp32 waveform; channels-as-M only)
-template <int EPI>
-__device__ __forceinline__ bool epi_has_res(const ConvEpilogue& ep, int i) {
-  if constexpr (EPI == 0) return i < ep.nres;
-  if constexpr (EPI == 1 || EPI == 4) return false;
-  if constexpr (EPI == 2) return i < 1;
-  return i < 3;
-}
-
-template <int EPI>
-__device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, const EpiItem& it, int n_total, int lane,
-                                                EpiLoads& ld) {
-#pragma unroll
-  for (int i = 0; i < kMaxRes; ++i) {
-    if (epi_has_res<EPI>(ep, i)) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int row = 16 * j + (lane >> 1);
-        if (row < it.rows_valid)
-          ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + (it.row0 + row) * n_total + it.n) +
-                                      (lane & 1));
-      }
-    }
-  }
-}
-
-// v = acc + bias (+ per-utterance bias) (+ residuals) (+ MRF accumulator)
-template <int EPI>
-__device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const float4 (&bias)[4], uint8_t* scratch,
-                                               const EpiItem& it, int n_total, int lane, float res_gain,
-                                               const uint32_t (&acc)[kIW], const EpiLoads& ld, float (&v)[kIW]) {
-#pragma unroll
-  for (int j = 0; j < kIW; j += 4) {
-    const float4 bv = bias[j >> 2];
-    v[j + 0] = __uint_as_float(acc[j + 0]) + bv.x;
-    v[j + 1] = __uint_as_float(acc[j + 1]) + bv.y;
-    v[j + 2] = __uint_as_float(acc[j + 2]) + bv.z;
-    v[j + 3] = __uint_as_float(acc[j + 3]) + bv.w;
-  }
-  if (EPI == 0 && ep.bias_b) {
-    const float* bb = ep.bias_b + (long)it.b * n_total + it.n;
-#pragma unroll
-    for (int j = 0; j < kIW; j += 4) {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(bb + j));
-      v[j + 0] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kMaxRes; ++i) {
-    if (epi_has_res<EPI>(ep, i)) {
-      // coalesced registers -> scratch -> row-owner registers
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        *reinterpret_cast<uint4*>(scratch + scr_off(16 * j + (lane >> 1), lane & 1)) = ld.res[i][j];
-      __syncwarp();
-      uint4 mine[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) mine[c] = *reinterpret_cast<const uint4*>(scratch + scr_off(lane, c));
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&mine[q]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 a = __bfloat1622float2(r2[e]);
-          v[q * 8 + e * 2 + 0] += a.x >= 0.f ? a.x : a.x * res_gain;
-          v[q * 8 + e * 2 + 1] += a.y >= 0.f ? a.y : a.y * res_gain;
-        }
-      }
-    }
-  }
-  if (EPI == 0 && (ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) && lane < it.rows_valid) {  // fp32 fallback path
-    const float4* mp = reinterpret_cast<const float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
-#pragma unroll
-    for (int j = 0; j < kIW / 4; ++j) {
-      const float4 m = mp[j];
-      v[4 * j] += m.x; v[4 * j + 1] += m.y; v[4 * j + 2] += m.z; v[4 * j + 3] += m.w;
-    }
-  }
-}
-
-template <int EPI>
-__device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int n_total,
-                                          int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
-  if (EPI == 0 && (ep.mrf_mode == 1 || ep.mrf_mode == 2)) {
-    if (lane < it.rows_valid) {
-      float4* mp = reinterpret_cast<float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
-#pragma unroll
-      for (int j = 0; j < kIW / 4; ++j) mp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-    return;
-  }
-  if (EPI == 3 || (EPI == 0 && ep.mrf_mode == 3)) {
-#pragma unroll
-    for (int j = 0; j < kIW; ++j) v[j] *= mrf_scale;
-  }
-  // row-owner registers -> scratch -> coalesced 32-byte row segments
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint4 ov;
-    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      o2[e] = __floats2bfloat162_rn(fmaxf(v[q * 8 + e * 2], v[q * 8 + e * 2] * out_slope),
-                                    fmaxf(v[q * 8 + e * 2 + 1], v[q * 8 + e * 2 + 1] * out_slope));  // slope in (0,1]
-    *reinterpret_cast<uint4*>(scratch + scr_off(lane, q)) = ov;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int row = 16 * j + (lane >> 1);
-    const uint4 ov = *reinterpret_cast<const uint4*>(scratch + scr_off(row, lane & 1));
-    if (row < it.rows_valid)
-      *(reinterpret_cast<uint4*>(ep.out + (it.row0 + row) * n_total + it.n) + (lane & 1)) = ov;
-  }
-  __syncwarp();
-}
-
-// ---- SWAP epilogue (channels on TMEM lanes, time on TMEM columns) --------------------------------------------------
-// Item = 32 channels (one per thread) x 16 time rows.  Global memory is [time][channel]: the item is 16 rows of 64
-// bytes.  Scratch holds it row-major (64-byte rows, chunk-swizzled); the thread<->time transposition happens in the
-// 2-byte shared-memory accesses, global accesses stay 16 bytes per lane over 8 rows x 64 B per instruction.
-__device__ __forceinline__ uint32_t scrT_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
-
-template <int EPI>
-__device__ __forceinline__ void epiT_issue_loads(const ConvEpilogue& ep, const EpiItem& it, int rowstride, int lane,
-                                                 EpiLoads& ld) {
-#pragma unroll
-  for (int i = 0; i < kMaxRes; ++i) {
-    if (epi_has_res<EPI>(ep, i)) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int row = 8 * j + (lane >> 2);
-        if (row < it.rows_valid)
-          ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + it.base + (long)row * rowstride) +
-                                      (lane & 3));
-      }
-    }
-  }
-}
-
-template <int EPI>
-__device__ __forceinline__ void epiT_accumulate(const ConvEpilogue& ep, float bias, uint8_t* scratch, const EpiItem& it,
-                                                int n_total, int lane, float res_gain, const uint32_t (&acc)[kIW],
-                                                const EpiLoads& ld, float (&v)[kIW]) {
-  if (EPI == 0 && ep.bias_b) bias += __ldg(ep.bias_b + (long)it.b * n_total + it.n + lane);
-#pragma unroll
-  for (int j = 0; j < kIW; ++j) v[j] = __uint_as_float(acc[j]) + bias;
-  const uint32_t mine = ((lane >> 3) << 4), sub = (lane & 7) * 2;  // my channel inside a 64-byte row
-#pragma unroll
-  for (int i = 0; i < kMaxRes; ++i) {
-    if (epi_has_res<EPI>(ep, i)) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        *reinterpret_cast<uint4*>(scratch + scrT_off(8 * j + (lane >> 2), lane & 3)) = ld.res[i][j];
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < kIW; ++j) {
-        const uint16_t raw = *reinterpret_cast<const uint16_t*>(scratch + j * 64 + (mine ^ (((j >> 1) & 3) << 4)) + sub);
-        const float a = __uint_as_float((uint32_t)raw << 16);
-        v[j] += a >= 0.f ? a : a * res_gain;
-      }
-      __syncwarp();
-    }
-  }
-}
-
-template <int EPI>
-__device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int rowstride,
-                                           int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
-  if (EPI == 3 || (EPI == 0 && ep.mrf_mode == 3)) {
-#pragma unroll
-    for (int j = 0; j < kIW; ++j) v[j] *= mrf_scale;
-  }
-  const uint32_t mine = ((lane >> 3) << 4), sub = (lane & 7) * 2;
-#pragma unroll
-  for (int j = 0; j < kIW; ++j) {
-    const __nv_bfloat16 o = __float2bfloat16_rn(fmaxf(v[j], v[j] * out_slope));
-    *reinterpret_cast<__nv_bfloat16*>(scratch + j * 64 + (mine ^ (((j >> 1) & 3) << 4)) + sub) = o;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int row = 8 * j + (lane >> 2);
-    const uint4 ov = *reinterpret_cast<const uint4*>(scratch + scrT_off(row, lane & 3));
-    if (row < it.rows_valid)
-      *(reinterpret_cast<uint4*>(ep.out + it.base + (long)row * rowstride) + (lane & 3)) = ov;
-  }
-  __syncwarp();
-}
 
 template <int BN, int KC, int EPI, bool SWAP>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -553,11 +328,13 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       uint32_t acc[kIW];
       float v[kIW];
       __syncwarp();
-      tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + cur.tcol, acc);
+      if constexpr (SWAP) tmem_ld_frag(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + cur.tcol, acc);
+      else tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + cur.tcol, acc);
       float4 bv[kIW / 4];  // bias for this item's columns: read from smem while the TMEM load is in flight
-      float bias_lane = 0.f;
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f};  // channels-as-M: this thread's channels are 8m + lane/4 (fragment layout)
       if constexpr (SWAP) {
-        bias_lane = sbias[cur.n + lane];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) bias4[m] = sbias[cur.n + 8 * m + (lane >> 2)];
       } else {
 #pragma unroll
         for (int j = 0; j < kIW / 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + cur.n + 4 * j);
@@ -568,18 +345,18 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         // conv_post: this lane's folded column is (phase, channel) = ((32q + lane) / C, (32q + lane) % C); only
         // channel 0 is a real output.  Columns of the item are consecutive folded rows: samples r apart.
         const int pc = ep.post_c;
-        if ((q * 32) % pc == 0) {  // warp-uniform: lane 0 of this warp holds channel 0 of phase 32q / C
-          // spread lane 0's 16 columns over lanes 0..15: one tanh and one store per lane instead of 16 in one lane
-          float x = 0.f;
-#pragma unroll
-          for (int j = 0; j < kIW; ++j) {
-            const float t = __shfl_sync(0xffffffffu, __uint_as_float(acc[j]), 0);
-            if (lane == j) x = t;
-          }
+        if ((q * 32) % pc == 0 && lane < 4) {  // fragment layout: lanes 0..3 hold channel 32q, four columns each
           const int r = n_total / pc;
-          if (lane < cur.rows_valid) ep.out_f32[(cur.row0 + lane) * r + (q * 32) / pc] = tanhf(x);
+          float* o = ep.out_f32 + cur.row0 * r + (q * 32) / pc;
+#pragma unroll
+          for (int cg = 0; cg < 2; ++cg)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = cg * 8 + 2 * lane + e;
+              if (col < cur.rows_valid) o[(long)col * r] = tanhf(__uint_as_float(acc[frag_idx(0, cg, e)]));
+            }
         }
-      } else if constexpr (SWAP) epiT_accumulate<EPI>(ep, bias_lane, scratch, cur, n_total, lane, res_gain, acc, ld, v);
+      } else if constexpr (SWAP) epiT_accumulate<EPI>(ep, bias4, scratch, cur, n_total, lane, res_gain, acc, ld, v);
       else epi_accumulate<EPI>(ep, bv, scratch, cur, n_total, lane, res_gain, acc, ld, v);
       if (tr) p.trace[itt * 12 + 6] = clock64();
       if (last) {  // accumulator fully read: hand the TMEM buffer back before the stores
@@ -659,15 +436,17 @@ static int encode_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1,
 // Activation tensor as the kernel's 5-d view (bf16): dims {kc, d1, d2, rows, B} with element strides
 // {1, s1, s2, srow, sb}; box {kc, 1, 1, 64, 1}, swizzle span = kc*2 bytes.
 static int encode_act(CUtensorMap* m, const void* base, uint32_t kc, uint64_t d1, uint64_t s1, uint64_t d2, uint64_t s2,
-                      uint64_t rows, uint64_t srow, uint64_t B, uint64_t sb) {
+                      uint64_t rows, uint64_t srow, uint64_t B, uint64_t sb, uint32_t box_rows = 64,
+                      uint32_t box_d2 = 1) {
   EncodeTiledFn fn = get_encode_fn();
   VD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[5] = {kc, d1, d2, rows, B};
   cuuint64_t strides[4] = {s1 * 2, s2 * 2, srow * 2, sb * 2};
-  cuuint32_t box[5] = {kc, 1, 1, 64, 1};
+  cuuint32_t box[5] = {kc, 1, box_d2, box_rows, 1};  // box_d2 > 1: several phases side by side in one shared-memory row
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUtensorMapSwizzle sw = kc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                        : (kc * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const uint32_t row_bytes = kc * 2 * box_d2;
+  CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -681,6 +460,11 @@ static int encode_act(CUtensorMap* m, const void* base, uint32_t kc, uint64_t d1
     return 1;
   }
   return 0;
+}
+
+int encode_tmap_act(CUtensorMap* m, const void* base, uint32_t kc, uint64_t d1, uint64_t s1, uint64_t d2, uint64_t s2,
+                    uint64_t rows, uint64_t srow, uint64_t B, uint64_t sb, uint32_t box_rows, uint32_t box_d2) {
+  return encode_act(m, base, kc, d1, s1, d2, s2, rows, srow, B, sb, box_rows, box_d2);
 }
 
 int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,

@@ -31,6 +31,7 @@
 #include "../../include/vitsdec.h"
 #include "common.cuh"
 #include "conv_pair.h"
+#include "conv_pairf.h"
 #include "conv_tc.h"
 #include "pack.h"
 
@@ -71,6 +72,8 @@ struct Layer {
   bf16* wfold = nullptr;         // [folded taps][r*C][r*C]
   float* bias_fold = nullptr;    // [r*C]
   int mrf_ftap_base = 0;         // real layers: first folded tap inside the virtual MRF layer's folded weights
+  int pair_ftap_base = 0;        // real layers: first folded tap inside the pair layer's folded weights (0 or nt)
+  bool pair_plain = false;       // kPair: conv_pair.cu (resident unfolded weights) can run this pair
 };
 
 static void conv_geom(Layer& l) {
@@ -174,6 +177,8 @@ struct Step {           // one launch of the conv primitive
   ConvTcPlan tc;
   bool is_pair = false;     // fused ResBlock1 pair (conv_pair.cu): layer = the kPair virtual layer
   PairPlan pair;
+  bool is_pairf = false;    // time-folded fused pair (conv_pairf.cu)
+  PairFPlan pairf;
   bf16* dbg_dst = nullptr;  // debug_keep: copy ep.out here after the launch
   size_t dbg_bytes = 0;
 };
@@ -215,7 +220,7 @@ struct vitsdec_decoder {
   std::vector<int> stage_ch;
   int hop = 1;
   float* scale_scratch = nullptr;
-  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1;
+  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1;
   cudaStream_t cstream = nullptr;  // capture-only stream (the caller's may be the legacy default stream)
   std::map<std::pair<int, int>, int> l_pair;  // (resblock index, pair index) -> kPair virtual layer id
   int last_launches = 0;
@@ -259,6 +264,7 @@ static int add_layer(vitsdec_decoder* d, const std::string& name, LayerKind kind
 static int alloc_layer(Layer& l) {
   if (l.kind == kPair) {
     VD_CUDA(cudaMalloc(&l.w, (size_t)2 * l.k * l.c_out * l.c_in * sizeof(bf16)));
+    if (l.fold_r) VD_CUDA(cudaMalloc(&l.wfold, (size_t)l.fgeom.ntaps * 128 * 128 * sizeof(bf16)));
     return 0;
   }
   if (l.kind == kConv || l.kind == kConvT || l.kind == kMrf) {
@@ -417,18 +423,29 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
         const bf16* conv_in = cur;
         int lid;
         auto pit = d->l_pair.find({i * nk + j, m});
-        if (!last && d->impl == 0 && d->fuse_pairs && pit != d->l_pair.end()) {
-          // whole pair in one launch: h stays in shared memory, the residual comes from the resident input tile
+        // pairf: 1 = where it is the faster kernel (pairf_preferred), 2 = wherever it exists (tests)
+        const bool pair_f = pit != d->l_pair.end() && d->fold && d->pairf && d->layers[pit->second].fold_r &&
+                            L % d->layers[pit->second].fold_r == 0 &&
+                            (d->pairf == 2 || pairf_preferred(d->layers[pit->second].c_out, d->layers[pit->second].k,
+                                                              d->layers[pit->second].dil));
+        const bool pair_p = pit != d->l_pair.end() && d->layers[pit->second].pair_plain;
+        if (!last && d->impl == 0 && d->fuse_pairs && (pair_f || pair_p)) {
+          // whole pair in one launch: h stays in shared memory
           bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2;
           Step s{};
           s.layer = pit->second;
-          s.is_pair = true;
           s.L = L;
           s.xs[0] = cur;
           s.ep = ep0(convs[2 * m]);
           s.ep.out = dst;
           const Layer& pv = d->layers[pit->second];
-          if (plan_conv_pair(&s.pair, B, L, pv.c_out, pv.k, pv.dil, cur, pv.w, d->num_sms)) return 1;
+          if (pair_f) {
+            s.is_pairf = true;
+            if (plan_conv_pairf(&s.pairf, B, L, pv.c_out, pv.k, pv.dil, cur, pv.wfold, d->num_sms)) return 1;
+          } else {
+            s.is_pair = true;
+            if (plan_conv_pair(&s.pair, B, L, pv.c_out, pv.k, pv.dil, cur, pv.w, d->num_sms)) return 1;
+          }
           s.tc.p.g.B = B;
           pl.steps.push_back(s);
           cur = dst;
@@ -510,6 +527,9 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
 
 static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
   Layer& ly = d->layers[s.layer];
+  if (s.is_pairf)
+    return launch_conv_pairf(s.pairf, d->layers[ly.members[0]].bias, d->layers[ly.members[1]].bias, kSlope, s.ep.out,
+                             st);
   if (s.is_pair)
     return launch_conv_pair(s.pair, d->layers[ly.members[0]].bias, d->layers[ly.members[1]].bias, kSlope, s.ep.out, st);
   if (d->impl == 0) return launch_conv_tc(s.tc, s.ep, st);
@@ -666,14 +686,23 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
       const int npairs = (int)convs.size() / 2;
       for (int m = 0; m + 1 < npairs; ++m) {
         const Layer c1 = d->layers[convs[2 * m]];
-        if (!pair_supported(c1.c_out, c1.k, c1.dil)) continue;
+        const bool plain = pair_supported(c1.c_out, c1.k, c1.dil), folded = pairf_supported(c1.c_out, c1.k, c1.dil);
+        if (!plain && !folded) continue;
         Layer v;
         v.name = "pair." + c1.name;
         v.kind = kPair;
         v.c_in = v.c_out = c1.c_out;
         v.k = c1.k;
         v.dil = c1.dil;
+        v.pair_plain = plain;
         v.members = {convs[2 * m], convs[2 * m + 1]};
+        if (folded) {  // conv_pairf.cu: block-Toeplitz taps of c1, then of c2
+          v.fold_r = 128 / c1.c_out;
+          v.fgeom = ConvGeom{};
+          v.fgeom.c_in = v.fgeom.n_total = 128;
+          v.fgeom.ntaps = 2 * pairf_taps(c1.c_out, c1.k);
+          d->layers[convs[2 * m + 1]].pair_ftap_base = v.fgeom.ntaps / 2;
+        }
         const int vid = (int)d->layers.size();
         d->layers[convs[2 * m]].pair_group = vid;
         d->layers[convs[2 * m]].pair_tap_base = 0;
@@ -750,6 +779,9 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
       if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.pair_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
                            st))
         return 1;
+      if (v.fold_r && launch_pack_conv_fold(w, d->scale_scratch, v.wfold + (size_t)l.pair_ftap_base * 128 * 128, l.c_in,
+                                            l.c_out, l.k, v.fold_r, st))
+        return 1;
     }
   } else if (l.kind == kConvT) {
     VD_CHECK(l.c_in <= 4096, "too many channels");
@@ -804,7 +836,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, d->desc_mode * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
+    const PlanKey key{B, T, d->impl, d->desc_mode * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -940,6 +972,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "fuse_pairs")) d->fuse_pairs = value ? 1 : 0;
   else if (!strcmp(key, "graph")) d->use_graph = value ? 1 : 0;
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
+  else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "profile")) {
     d->profile = value ? 1 : 0;
     d->prof_conv_ms = 0.0;
@@ -973,6 +1006,7 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   else if (!strcmp(key, "fuse_pairs")) *value = d->fuse_pairs;
   else if (!strcmp(key, "graph")) *value = d->use_graph;
   else if (!strcmp(key, "fold")) *value = d->fold;
+  else if (!strcmp(key, "pairf")) *value = d->pairf;
   else if (!strcmp(key, "hop")) *value = d->hop;
   else if (!strcmp(key, "num_sms")) *value = d->num_sms;
   else { set_error(std::string("unknown option ") + key); return 1; }
@@ -1115,6 +1149,40 @@ int vitsdec_op_resblock_pair(int device, const void* x, const float* w1, const f
   cudaError_t se = cudaStreamSynchronize(st);
   cudaFree(w); cudaFree(scale); cudaFree(bias);
   if (!rc && se != cudaSuccess) { set_error(std::string("op_resblock_pair: ") + cudaGetErrorString(se)); rc = 1; }
+  return rc;
+}
+
+int vitsdec_op_resblock_pair_folded(int device, const void* x, const float* w1, const float* b1, const float* w2,
+                                    const float* b2, void* y, int B, int L, int channels, int k, int dilation,
+                                    float slope, void* stream) {
+  VD_CHECK(x && w1 && w2 && y, "vitsdec_op_resblock_pair_folded: null argument");
+  VD_CHECK(pairf_supported(channels, k, dilation) && L % (128 / channels) == 0,
+           "vitsdec_op_resblock_pair_folded: shape not supported by the folded fused kernel");
+  DeviceGuard guard(device);
+  VD_CHECK(guard.ok, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  VD_CUDA(cudaGetDeviceProperties(&prop, device));
+  VD_CHECK(prop.major == 10, "vitsdec needs an sm_100 (B200) device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nt = pairf_taps(channels, k), r = 128 / channels;
+  bf16* w = nullptr;
+  float *scale = nullptr, *bias = nullptr;
+  VD_CUDA(cudaMalloc(&w, (size_t)2 * nt * 128 * 128 * sizeof(bf16)));
+  VD_CUDA(cudaMalloc(&scale, 4096 * sizeof(float)));
+  VD_CUDA(cudaMalloc(&bias, 2 * channels * sizeof(float)));
+  int rc = launch_wn_scale(w1, nullptr, scale, channels, channels * k, st) ||
+           launch_pack_conv_fold(w1, scale, w, channels, channels, k, r, st) ||
+           launch_pack_conv_fold(w2, scale, w + (size_t)nt * 128 * 128, channels, channels, k, r, st) ||
+           launch_replicate_bias(b1, bias, channels, 1, st) || launch_replicate_bias(b2, bias + channels, channels, 1, st);
+  if (!rc) {
+    PairFPlan pl{};
+    rc = plan_conv_pairf(&pl, B, L, channels, k, dilation, static_cast<const bf16*>(x), w, prop.multiProcessorCount);
+    pl.p.trace = g_trace_buffer;
+    rc = rc || launch_conv_pairf(pl, bias, bias + channels, slope, static_cast<bf16*>(y), st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(w); cudaFree(scale); cudaFree(bias);
+  if (!rc && se != cudaSuccess) { set_error(std::string("op_resblock_pair_folded: ") + cudaGetErrorString(se)); rc = 1; }
   return rc;
 }
 

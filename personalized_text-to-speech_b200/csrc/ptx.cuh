@@ -170,6 +170,30 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "memory");
 }
 
+// 16 lanes x 16 consecutive fp32 columns in the mma-fragment layout (measured, tools/probes/frag_probe.cu): thread t
+// gets lane t/4 (r0,r1,r4,r5) and lane t/4+8 (r2,r3,r6,r7); columns 2(t%4), 2(t%4)+1 in r0..r3 and 8 + the same in
+// r4..r7.  The layout stmatrix/ldmatrix .trans speak, so a channels-as-M accumulator tile can be transposed to
+// channels-last rows with two instructions instead of sixteen 2-byte shared-memory accesses.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// Four 8x8 b16 matrices, transposed: register m of thread t holds M_m[t/4][2(t%4)], M_m[t/4][2(t%4)+1]; shared-memory
+// row r of matrix m (16 bytes at the address given by lane 8m + r) holds M_m[0..7][r].
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(r0), "r"(r1),
+               "r"(r2), "r"(r3)
+               : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr)
+               : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand, swizzled rows (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows)
 //   [46,48) version=1 | [49,52) base offset | [61,64) layout (2 = SW128, 4 = SW64, 6 = SW32)

@@ -48,12 +48,25 @@ def conv_transpose1d_cl(x, w, bias=None, stride=2, out_slope=1.0, impl=0):
     return y
 
 
-def resblock_pair_cl(x, w1, b1, w2, b2, dilation=1, slope=0.1):
-    """Fused ResBlock1 iteration.  x: bf16 [B, L, C] a-form; w1, w2: fp32 [C, C, k]; -> bf16 [B, L, C] a-form."""
+def resblock_pair_cl(x, w1, b1, w2, b2, dilation=1, slope=0.1, folded=False):
+    """Fused ResBlock1 iteration.  x: bf16 [B, L, C] a-form; w1, w2: fp32 [C, C, k]; -> bf16 [B, L, C] a-form.
+    folded=True runs the time-folded kernel (conv_pairf.cu)."""
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
     B, L, C = x.shape
     k = w1.shape[2]
     y = torch.empty_like(x)
+    if folded:
+        if dilation > 1:  # the dilated view reads (and masks) a few rows past the end of x: NaN slack, see conv1d_cl
+            buf = torch.full((x.numel() + 4096,), float("nan"), dtype=torch.bfloat16, device=x.device)
+            buf[:x.numel()].copy_(x.reshape(-1))
+            x = buf[:x.numel()].view(B, L, C)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        ts = [t.float().contiguous() for t in (w1, b1, w2, b2)]
+        _capi.check(_capi.lib().vitsdec_op_resblock_pair_folded(x.device.index or 0, _ptr(x), _ptr(ts[0]), _ptr(ts[1]),
+                                                                _ptr(ts[2]), _ptr(ts[3]), _ptr(y), B, L, C, k,
+                                                                int(dilation), float(slope), st),
+                    "vitsdec_op_resblock_pair_folded")
+        return y
     st = torch.cuda.current_stream(x.device).cuda_stream
     ts = [t.float().contiguous() for t in (w1, b1, w2, b2)]
     _capi.check(_capi.lib().vitsdec_op_resblock_pair(x.device.index or 0, _ptr(x), _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]),

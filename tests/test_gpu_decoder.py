@@ -221,7 +221,10 @@ def test_time_folded_schedule_tracks_the_unfolded_one():
         G.set_option("fuse_pairs", 0)
         G.set_option("fold", 1)
         c = G(z, g).clone()
+        G.set_option("fuse_pairs", 1)
+        G.set_option("pairf", 2)   # the folded fused-pair kernel wherever it exists, not only where it is faster
+        e = G(z, g).clone()
     ref = generator_forward_torch(hp, to_torch_state_dict(sd), z.cpu(), g.cpu())
-    for y in (a, b, c):
+    for y in (a, b, c, e):
         check(ref, y.cpu())
-    assert snr_db(b.cpu(), a.cpu()) > 45.0 and snr_db(b.cpu(), c.cpu()) > 45.0
+    assert snr_db(b.cpu(), a.cpu()) > 45.0 and snr_db(b.cpu(), c.cpu()) > 45.0 and snr_db(b.cpu(), e.cpu()) > 45.0
