@@ -24,7 +24,6 @@ sys.path.insert(0, ROOT)
 SR, HOP = 22050, 256
 FLOP_PER_FRAME = 614907904       # SURVEY.md section 8d / BASELINE.md section 3 (2 x 307 453 952 MAC)
 FLOP_PER_UTT = 262144            # cond(g)
-CONV_POST_FLOP_PER_FRAME = 2 * 57344  # conv_post runs on CUDA cores, not in the tcgen05 kernel
 
 
 def load_traffic(launches_per_step):
@@ -257,7 +256,7 @@ def main():
     value = audio_s / (ms_step / 1e3)
     e2e_val = audio_s / (ms_e2e / args.steps / 1e3)
     burst, sustained, peak_src = load_peaks()
-    conv_flops_step = B * (frames * (FLOP_PER_FRAME - CONV_POST_FLOP_PER_FRAME))  # per rank, tcgen05 kernel only
+    conv_flops_step = B * frames * FLOP_PER_FRAME  # per rank; every conv of the path runs in a tcgen05 kernel (conv_post too)
     conv_ms_step = conv_ms / args.steps
     achieved = conv_flops_step / (conv_ms_step / 1e3) / 1e12
     launches_conv = conv_launches // max(1, args.steps)
@@ -271,7 +270,7 @@ def main():
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor",
-                     "kernel": "conv_tc_kernel + conv_pair_kernel (tcgen05 implicit-GEMM convs: %d launches/step, "
+                     "kernel": "conv_tc_kernel + conv_pair_kernel + conv_pairf_kernel (tcgen05 implicit-GEMM convs: %d launches/step, "
                                ">98%% of step time; figures are per launch, averaged over them)" % launches_conv,
                      "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                      "frac_of_sustained": achieved / sustained, "peak_source": peak_src + ", bf16 dense burst",

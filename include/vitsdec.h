@@ -149,6 +149,40 @@ VITSDEC_API int vitsdec_op_conv_transpose1d(int device, const void* x_dev, const
                                 float out_slope, void* y_dev, int batch, int length, int c_in, int c_out, int k,
                                 int stride, int impl, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * The normalising flow that produces the decoder's latent: ResidualCouplingBlock.forward(x, x_mask, g, reverse)
+ * (/root/reference/models.py:179-209; SynthesizerTrn.infer calls it in reverse at models.py:521, voice_conversion in
+ * both directions at models.py:530-531).  Constructor arguments as models.py:449 passes them. */
+typedef struct vitsdec_flow vitsdec_flow;
+typedef struct vitsdec_flow_hparams {
+  int32_t channels;          /* inter_channels (192) */
+  int32_t hidden_channels;   /* 192 */
+  int32_t kernel_size;       /* 5 */
+  int32_t dilation_rate;     /* 1 */
+  int32_t n_layers;          /* 4 */
+  int32_t n_flows;           /* 4 */
+  int32_t gin_channels;      /* 0 = no speaker conditioning */
+} vitsdec_flow_hparams;
+
+VITSDEC_API int vitsdec_flow_create(const vitsdec_flow_hparams* hp, int device, vitsdec_flow** out);
+VITSDEC_API void vitsdec_flow_destroy(vitsdec_flow* flow);
+/* Parametrised sub-modules in state_dict order: "flows.<2i>.pre", "flows.<2i>.enc.in_layers.<l>",
+ * "flows.<2i>.enc.res_skip_layers.<l>", "flows.<2i>.enc.cond_layer" (gin_channels > 0), "flows.<2i>.post". */
+VITSDEC_API int vitsdec_flow_num_layers(const vitsdec_flow* flow);
+VITSDEC_API const char* vitsdec_flow_layer_name(const vitsdec_flow* flow, int index);
+/* Device fp32 tensors in the reference's shapes: weight (or weight_v), weight_g (NULL for pre / post, which carry no
+ * weight norm, modules.py:318-320) and bias.  Weight norm (dim 0) is folded here, once. */
+VITSDEC_API int vitsdec_flow_load_layer(vitsdec_flow* flow, const char* name, const float* w_dev, const float* wg_dev,
+                                        const float* bias_dev, void* stream);
+VITSDEC_API size_t vitsdec_flow_workspace_bytes(const vitsdec_flow* flow, int batch, int frames);
+/* x_dev: fp32 [batch, channels, frames] with element strides (x_stride_b, x_stride_c, 1); lengths_dev: int32 [batch]
+ * valid frames per utterance (x_mask as sequence lengths, commons.sequence_mask) or NULL = all frames; g_dev: fp32
+ * [batch, gin_channels] or NULL; out_dev: contiguous fp32 [batch, channels, frames].  reverse != 0 runs the inverse
+ * pass (models.py:207-209).  Asynchronous on `stream`. */
+VITSDEC_API int vitsdec_flow_apply(vitsdec_flow* flow, const float* x_dev, int64_t x_stride_b, int64_t x_stride_c,
+                                   const int32_t* lengths_dev, const float* g_dev, float* out_dev, int batch, int frames,
+                                   int reverse, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

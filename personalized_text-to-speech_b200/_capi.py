@@ -32,6 +32,12 @@ class HParams(ctypes.Structure):
     ]
 
 
+class FlowHParams(ctypes.Structure):
+    """struct vitsdec_flow_hparams"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("channels", "hidden_channels", "kernel_size", "dilation_rate", "n_layers",
+                                               "n_flows", "gin_channels")]
+
+
 class VitsdecError(RuntimeError):
     pass
 
@@ -60,6 +66,13 @@ SIGNATURES = {
     "vitsdec_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
     "vitsdec_debug_read": (_i, [_vp, _cp, _vp, _sz, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp]),
     "vitsdec_debug_set_trace": (_i, [_vp]),
+    "vitsdec_flow_create": (_i, [ctypes.POINTER(FlowHParams), _i, ctypes.POINTER(_vp)]),
+    "vitsdec_flow_destroy": (None, [_vp]),
+    "vitsdec_flow_num_layers": (_i, [_vp]),
+    "vitsdec_flow_layer_name": (_cp, [_vp, _i]),
+    "vitsdec_flow_load_layer": (_i, [_vp, _cp, _vp, _vp, _vp, _vp]),
+    "vitsdec_flow_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "vitsdec_flow_apply": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "vitsdec_op_conv1d": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vitsdec_op_resblock_pair": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "vitsdec_op_resblock_pair_folded": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),

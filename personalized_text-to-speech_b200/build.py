@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvitsdec.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["decoder.cu", "conv_tc.cu", "conv_pair.cu", "conv_pairf.cu", "conv_simt.cu", "pack.cu"]
+SOURCES = ["decoder.cu", "conv_tc.cu", "conv_pair.cu", "conv_pairf.cu", "conv_simt.cu", "pack.cu", "flow.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",

@@ -912,17 +912,17 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   }
   if (!launched && enqueue_steps(st)) return 1;
   launches += (int)plan->steps.size();
-  if (d->profile) {
-    VD_CUDA(cudaEventRecord(d->ev_conv1, st));
-    d->ev_pending = true;
-    d->prof_conv_launches += (long)plan->steps.size();
-  }
   if (plan->post_tc) {
     Step s = plan->post;
     s.ep.out_f32 = out;
     if (launch_conv_tc(s.tc, s.ep, st)) return 1;
   } else if (launch_conv_post(plan->x_final, d->layers[d->l_post].wf32, out, B, plan->L_final, plan->C_final, st)) {
     return 1;
+  }
+  if (d->profile) {  // the bracket covers every tcgen05 launch of the decode (conv_post included when it is one)
+    VD_CUDA(cudaEventRecord(d->ev_conv1, st));
+    d->ev_pending = true;
+    d->prof_conv_launches += (long)plan->steps.size() + (plan->post_tc ? 1 : 0);
   }
   ++launches;
   d->last_launches = launches;

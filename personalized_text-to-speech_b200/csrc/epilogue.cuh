@@ -35,6 +35,7 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 struct EpiItem {
   int b, n, rows_valid;
   long row0;       // b*L + t of lane 0's row
+  int t0;          // t of lane 0's row (time-as-M items)
   long base;       // channels-as-M: element offset of (first row of the item, this warp's first channel)
   uint32_t tcol;   // TMEM column of the item inside its accumulator buffer
 };
@@ -127,6 +128,12 @@ __device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const flo
 template <int EPI>
 __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int n_total,
                                           int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
+  if (EPI == 0 && ep.lens) {  // sequence mask: rows past the utterance's own length hold zeros
+    if (it.t0 + lane >= __ldg(ep.lens + it.b)) {
+#pragma unroll
+      for (int j = 0; j < kIW; ++j) v[j] = 0.f;
+    }
+  }
   if (EPI == 0 && (ep.mrf_mode == 1 || ep.mrf_mode == 2)) {
     if (lane < it.rows_valid) {
       float4* mp = reinterpret_cast<float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);

@@ -7,13 +7,18 @@ built is enough for ``cmd_inference.py`` / ``VC_inference.py`` / ``SynthesizerTr
 import importlib
 import sys
 
+from .flow import ResidualCouplingBlock
 from .generator import Generator
 
 _saved = {}
+_saved_flow = {}
 
 
-def patch_reference(module_names=("models", "models_infer")):
-    """Replace ``<module>.Generator`` in every importable reference module.  Returns the patched names."""
+def patch_reference(module_names=("models", "models_infer"), flow=False):
+    """Replace ``<module>.Generator`` in every importable reference module.  Returns the patched names.
+
+    ``flow=True`` also replaces ``<module>.ResidualCouplingBlock`` (resolved the same way at models.py:449), so that
+    ``SynthesizerTrn.infer`` runs flow(reverse) -> dec natively.  Inference only: training needs autograd through it."""
     done = []
     for name in module_names:
         mod = sys.modules.get(name)
@@ -22,6 +27,9 @@ def patch_reference(module_names=("models", "models_infer")):
                 mod = importlib.import_module(name)
             except Exception:
                 continue
+        if flow and getattr(mod, "ResidualCouplingBlock", None) is not ResidualCouplingBlock:
+            _saved_flow[name] = getattr(mod, "ResidualCouplingBlock", None)
+            mod.ResidualCouplingBlock = ResidualCouplingBlock
         if getattr(mod, "Generator", None) is Generator:
             done.append(name)
             continue
@@ -37,3 +45,8 @@ def unpatch_reference():
         if mod is not None and orig is not None:
             mod.Generator = orig
         del _saved[name]
+    for name, orig in list(_saved_flow.items()):
+        mod = sys.modules.get(name)
+        if mod is not None and orig is not None:
+            mod.ResidualCouplingBlock = orig
+        del _saved_flow[name]

@@ -9,6 +9,7 @@ if _root not in sys.path:
 _pkg = importlib.import_module("personalized_text-to-speech_b200")
 
 Generator = _pkg.Generator
+ResidualCouplingBlock = _pkg.ResidualCouplingBlock
 patch_reference = _pkg.patch_reference
 unpatch_reference = _pkg.unpatch_reference
 shard_range = _pkg.shard_range
