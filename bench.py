@@ -240,6 +240,25 @@ def main():
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
+        # the stage before the decoder: flow(z_p, reverse) on the same batch, timed separately -- it is
+        # not part of the metric, which is the Generator decode alone
+        Fl = vitsdec.ResidualCouplingBlock(cargs[0], 192, 5, 1, 4, gin_channels=ckw["gin_channels"])
+        for name, p in Fl.named_parameters():
+            if name.endswith("post.weight"):
+                p.uniform_(-0.07, 0.07)  # the reference zero-initialises post: give the couplings something to do
+        Fl = Fl.to(dev).eval()
+        Fl.assume_frozen = True
+        ymask = torch.ones((B, 1, frames), device=dev)
+        for _ in range(3):
+            zf = Fl(z, ymask, g=g, reverse=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            zf = Fl(z, ymask, g=g, reverse=True)
+        e1.record()
+        barrier()
+        flow_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
         gather_ms = None
         if world > 1:  # the optional final waveform gather (north_star): timed separately, not on the data path
             full = torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev)
@@ -281,6 +300,7 @@ def main():
                      "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"},
         "clocks": clocks,
     }
+    line["flow_reverse_ms_per_step"] = flow_ms
     if gather_ms is not None:
         line["waveform_gather_ms"] = gather_ms
     if rank == 0:

@@ -175,12 +175,12 @@ VITSDEC_API const char* vitsdec_flow_layer_name(const vitsdec_flow* flow, int in
 VITSDEC_API int vitsdec_flow_load_layer(vitsdec_flow* flow, const char* name, const float* w_dev, const float* wg_dev,
                                         const float* bias_dev, void* stream);
 VITSDEC_API size_t vitsdec_flow_workspace_bytes(const vitsdec_flow* flow, int batch, int frames);
-/* x_dev: fp32 [batch, channels, frames] with element strides (x_stride_b, x_stride_c, 1); lengths_dev: int32 [batch]
- * valid frames per utterance (x_mask as sequence lengths, commons.sequence_mask) or NULL = all frames; g_dev: fp32
+/* x_dev: fp32 [batch, channels, frames] with element strides (x_stride_b, x_stride_c, 1); x_mask_dev: fp32
+ * [batch, frames] (the reference's x_mask [B,1,T], binary: commons.sequence_mask) or NULL = all ones; g_dev: fp32
  * [batch, gin_channels] or NULL; out_dev: contiguous fp32 [batch, channels, frames].  reverse != 0 runs the inverse
  * pass (models.py:207-209).  Asynchronous on `stream`. */
 VITSDEC_API int vitsdec_flow_apply(vitsdec_flow* flow, const float* x_dev, int64_t x_stride_b, int64_t x_stride_c,
-                                   const int32_t* lengths_dev, const float* g_dev, float* out_dev, int batch, int frames,
+                                   const float* x_mask_dev, const float* g_dev, float* out_dev, int batch, int frames,
                                    int reverse, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

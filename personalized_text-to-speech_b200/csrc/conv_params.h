@@ -62,8 +62,8 @@ struct ConvEpilogue {
   float mrf_scale;
   float out_slope;             // 1.0f = identity
   __nv_bfloat16* out;          // [B][L][n_total]
-  const int* lens;             // optional [B]: rows t >= lens[b] are written as zero (x_mask of the flow; time-as-M
-                               // tiles with the generic epilogue only)
+  const float* rowmask;        // optional [B][L]: every output row is multiplied by its mask value (x_mask of the
+                               // flow, modules.py:171,176; time-as-M tiles with the generic epilogue only)
   float* out_f32;              // mrf_mode 4: waveform [B][L * n_total / post_c]
   int post_c;                  // mrf_mode 4: real channels per time sample (n_total = r * post_c)
 };

@@ -301,7 +301,6 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         e.n = nt * BN + c0;
         e.rows_valid = min(32, max(0, L - t));
         e.row0 = (long)e.b * L + t;
-        e.t0 = t;
         e.tcol = acc * BN + c0;
       }
     };
@@ -508,7 +507,7 @@ template <int BN, int KC, bool SPECIALISED>
 static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
   const ConvEpilogue& e = pl.p.ep;
   if constexpr (SPECIALISED) {
-    const bool simple = e.bias_b == nullptr && e.lens == nullptr &&
+    const bool simple = e.bias_b == nullptr && e.rowmask == nullptr &&
                         (e.mrf_mode == 0 || (e.mrf_mode == 3 && e.mrf == nullptr));
     if (simple && e.mrf_mode == 0 && e.nres == 0) return launch_one<BN, KC, 1>(pl, stream);
     if (simple && e.mrf_mode == 0 && e.nres == 1) return launch_one<BN, KC, 2>(pl, stream);
@@ -650,7 +649,7 @@ int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) 
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
   pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch && pl.p.rho_d == 1) ? 1 : 0;
   if (pl.swap) {
-    VD_CHECK(ep.lens == nullptr, "conv_tc: the sequence mask needs a time-as-M plan (allow_swap = false)");
+    VD_CHECK(ep.rowmask == nullptr, "conv_tc: the row mask needs a time-as-M plan (allow_swap = false)");
     VD_CHECK(ep.mrf == nullptr, "conv_tc: the channels-as-M variant has no fp32 MRF accumulator path");
     return launch_swapped(pl, stream);
   }

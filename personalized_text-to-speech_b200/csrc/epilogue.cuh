@@ -35,7 +35,6 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 struct EpiItem {
   int b, n, rows_valid;
   long row0;       // b*L + t of lane 0's row
-  int t0;          // t of lane 0's row (time-as-M items)
   long base;       // channels-as-M: element offset of (first row of the item, this warp's first channel)
   uint32_t tcol;   // TMEM column of the item inside its accumulator buffer
 };
@@ -128,11 +127,10 @@ __device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const flo
 template <int EPI>
 __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int n_total,
                                           int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
-  if (EPI == 0 && ep.lens) {  // sequence mask: rows past the utterance's own length hold zeros
-    if (it.t0 + lane >= __ldg(ep.lens + it.b)) {
+  if (EPI == 0 && ep.rowmask) {  // `* x_mask`: one mask value per (utterance, time) row
+    const float mk = lane < it.rows_valid ? __ldg(ep.rowmask + it.row0 + lane) : 0.f;
 #pragma unroll
-      for (int j = 0; j < kIW; ++j) v[j] = 0.f;
-    }
+    for (int j = 0; j < kIW; ++j) v[j] *= mk;
   }
   if (EPI == 0 && (ep.mrf_mode == 1 || ep.mrf_mode == 2)) {
     if (lane < it.rows_valid) {

@@ -7,8 +7,8 @@
 // (models.py:530-531).  SURVEY.md section 8f ranks it first among the callers of the decoder path.
 //
 // Data layout: the latent stays fp32 channels-last X[B][T][C] for the whole block (the coupling x1 -/+= m is exact in
-// fp32); convolution operands are bf16 channels-last like the decoder's.  x_mask is a per-utterance length: every conv
-// epilogue writes zeros for rows t >= lens[b] (ConvEpilogue::lens), which is what `* x_mask` after every layer means.
+// fp32); convolution operands are bf16 channels-last like the decoder's.  `* x_mask` after every layer is a per-row
+// multiply in the conv epilogues (ConvEpilogue::rowmask; the mask is binary in the reference, commons.sequence_mask).
 // One coupling layer:
 //   flip_split   X <- flip(X) (reverse) ; X0 = bf16(X[:, :C/2])
 //   pre          H = (W_pre X0 + b) * mask                                               modules.py:326
@@ -105,26 +105,21 @@ __global__ void flow_gate_kernel(const bf16* __restrict__ xin, bf16* __restrict_
 }
 
 // x1 = (x1 - m) * mask (reverse) or m + x1 * mask (forward); m is already masked (modules.py:328, 335-343, logs = 0)
-__global__ void flow_couple_kernel(float* __restrict__ x, const float* __restrict__ m, const int* __restrict__ lens,
-                                   int T, long rows, int C, int reverse) {
+__global__ void flow_couple_kernel(float* __restrict__ x, const float* __restrict__ m, const float* __restrict__ mask,
+                                   long rows, int C, int reverse) {
   const int half = C / 2;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < rows * half; i += (long)gridDim.x * blockDim.x) {
     const long r = i / half;
     const int c = i % half;
-    const bool in = (int)(r % T) < lens[r / T];
+    const float mk = mask[r];
     float* p = x + r * C + half + c;
     const float mv = m[i];
-    *p = reverse ? (in ? *p - mv : 0.f) : (mv + (in ? *p : 0.f));
+    *p = reverse ? (*p - mv) * mk : mv + *p * mk;
   }
 }
 
-__global__ void flow_fill_lens_kernel(int* lens, int B, int T) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) lens[i] = T;
-}
-__global__ void flow_clamp_lens_kernel(const int* in, int* lens, int B, int T) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) lens[i] = min(max(in[i], 0), T);
+__global__ void flow_fill_mask_kernel(float* mask, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) mask[i] = 1.f;
 }
 
 // cb[l][b][n] = cond.bias[l*N + n] + sum_ci w[l*N + n][ci] * g[b][ci]   (one warp per output; N = 2*hidden)
@@ -197,7 +192,15 @@ struct FlowStep {
 };
 
 struct FlowPlan {            // per (B, T, workspace): tensor maps of every conv launch, in execution order per coupling
+  ~FlowPlan() {
+    for (cudaGraphExec_t e : graph_exec)
+      if (e) cudaGraphExecDestroy(e);
+  }
   std::vector<std::vector<FlowStep>> steps;   // [coupling][launch]
+  // the whole block between the input and output transposes replays as one CUDA graph (it only touches workspace
+  // pointers); index = reverse * 2 + has_g
+  cudaGraphExec_t graph_exec[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool graph_failed = false;
 };
 
 static size_t fl_align(size_t v) { return (v + 1023) / 1024 * 1024; }
@@ -214,12 +217,13 @@ struct vitsdec_flow {
   float* scale_scratch = nullptr;
   std::mutex mu;
   std::list<std::pair<std::tuple<int, int, const void*>, std::shared_ptr<FlowPlan>>> plans;
+  cudaStream_t cstream = nullptr;   // capture-only stream
 };
 
 namespace vd {
 
 struct FlowWs {
-  size_t x, x0, h0, h1, xin, act, s, outb, m, cb, lens, total;
+  size_t x, x0, h0, h1, xin, act, s, outb, m, cb, mask, g, total;
 };
 
 static FlowWs flow_ws(const vitsdec_flow* f, int B, int T) {
@@ -236,7 +240,8 @@ static FlowWs flow_ws(const vitsdec_flow* f, int B, int T) {
   w.outb = o; o += fl_align(rows * H * 2);
   w.m = o; o += fl_align(rows * (C / 2) * 4);
   w.cb = o; o += fl_align((size_t)f->hp.n_layers * B * 2 * H * 4);
-  w.lens = o; o += fl_align((size_t)B * 4);
+  w.mask = o; o += fl_align(rows * 4);
+  w.g = o; o += fl_align((size_t)B * (f->hp.gin_channels > 0 ? f->hp.gin_channels : 1) * 4);
   w.total = o + 4096;
   return w;
 }
@@ -262,7 +267,7 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
   bf16* OUTB = reinterpret_cast<bf16*>(ws + w.outb);
   float* M = reinterpret_cast<float*>(ws + w.m);
   float* CB = reinterpret_cast<float*>(ws + w.cb);
-  const int* lens = reinterpret_cast<const int*>(ws + w.lens);
+  const float* mask = reinterpret_cast<const float*>(ws + w.mask);
   pl.steps.resize(f->cpl.size());
   for (size_t ci = 0; ci < f->cpl.size(); ++ci) {
     FlowCoupling& c = f->cpl[ci];
@@ -271,7 +276,7 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
       ConvGeom g = cv.geom;
       g.B = B; g.L = T;
       e.bias = cv.bias;
-      e.lens = lens;
+      e.rowmask = mask;
       e.res_gain = 1.f;
       if (e.out_slope == 0.f) e.out_slope = 1.f;
       if (e.mrf_scale == 0.f) e.mrf_scale = 1.f;
@@ -396,6 +401,8 @@ void vitsdec_flow_destroy(vitsdec_flow* f) {
     cudaFree(c.cond_w); cudaFree(c.cond_b);
   }
   cudaFree(f->scale_scratch);
+  f->plans.clear();
+  if (f->cstream) cudaStreamDestroy(f->cstream);
   delete f;
 }
 
@@ -465,7 +472,7 @@ size_t vitsdec_flow_workspace_bytes(const vitsdec_flow* f, int batch, int frames
   return flow_ws(f, batch, frames).total;
 }
 
-int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc, const int32_t* lengths, const float* g,
+int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc, const float* x_mask, const float* g,
                        float* out, int B, int T, int reverse, void* ws, size_t ws_bytes, void* stream) {
   VD_CHECK(f && x && out && ws, "vitsdec_flow_apply: null argument");
   VD_CHECK(B > 0 && T > 0 && B <= 65535, "vitsdec_flow_apply: bad batch / frames");
@@ -505,44 +512,76 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
   bf16* ACT = reinterpret_cast<bf16*>(base + w.act);
   float* M = reinterpret_cast<float*>(base + w.m);
   float* CB = reinterpret_cast<float*>(base + w.cb);
-  int* lens = reinterpret_cast<int*>(base + w.lens);
-  if (lengths) flow_clamp_lens_kernel<<<(B + 255) / 256, 256, 0, st>>>(lengths, lens, B, T);
-  else flow_fill_lens_kernel<<<(B + 255) / 256, 256, 0, st>>>(lens, B, T);
+  float* mask = reinterpret_cast<float*>(base + w.mask);
+  float* gws = reinterpret_cast<float*>(base + w.g);
+  // per-call inputs are staged into the workspace so that everything in between is pointer-stable (graph replay)
+  if (x_mask) VD_CUDA(cudaMemcpyAsync(mask, x_mask, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
+  else flow_fill_mask_kernel<<<grid1d(rows), 256, 0, st>>>(mask, rows);
+  if (g) VD_CUDA(cudaMemcpyAsync(gws, g, (size_t)B * f->hp.gin_channels * 4, cudaMemcpyDeviceToDevice, st));
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
     flow_in_kernel<<<grid, block, 0, st>>>(x, xsb, xsc, X, C, T);
   }
   VD_CUDA(cudaGetLastError());
   // reverse: Flip, coupling n-1, Flip, coupling n-2, ...   forward: coupling 0, Flip, coupling 1, Flip, ...
-  for (int step = 0; step < nf; ++step) {
-    const int ci = reverse ? nf - 1 - step : step;
-    FlowCoupling& c = f->cpl[ci];
-    const int flip_now = reverse ? 1 : (step > 0 ? 1 : 0);
-    flow_flip_split_kernel<<<grid1d(rows * (C / 2)), 256, 0, st>>>(X, X0, rows, C, flip_now);
-    if (g) {
-      dim3 grid((nl * 2 * H * 32 + 255) / 256, B);
-      flow_cond_kernel<<<grid, 256, 0, st>>>(c.cond_w, c.cond_b, g, CB, B, 2 * H, nl, f->hp.gin_channels);
-    }
-    VD_CUDA(cudaGetLastError());
-    std::vector<FlowStep>& steps = plan->steps[ci];
-    size_t si = 0;
-    auto run = [&](bool with_cond) -> int {
-      FlowStep s = steps[si++];   // copy: per-call fields, re-entrant across threads
-      if (!with_cond) s.ep.bias_b = nullptr;
-      return launch_conv_tc(s.tc, s.ep, st);
-    };
-    if (run(false)) return 1;                               // pre
-    for (int l = 0; l < nl; ++l) {
-      if (run(g != nullptr)) return 1;                      // in_layer (+ cond)
-      flow_gate_kernel<<<grid1d(rows * (H / 2)), 256, 0, st>>>(XIN, ACT, rows, H);
+  auto enqueue = [&](cudaStream_t qs) -> int {
+    for (int step = 0; step < nf; ++step) {
+      const int ci = reverse ? nf - 1 - step : step;
+      FlowCoupling& c = f->cpl[ci];
+      const int flip_now = reverse ? 1 : (step > 0 ? 1 : 0);
+      flow_flip_split_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, X0, rows, C, flip_now);
+      if (g) {
+        dim3 grid((nl * 2 * H * 32 + 255) / 256, B);
+        flow_cond_kernel<<<grid, 256, 0, qs>>>(c.cond_w, c.cond_b, gws, CB, B, 2 * H, nl, f->hp.gin_channels);
+      }
       VD_CUDA(cudaGetLastError());
-      if (c.layers[l].has_res && run(false)) return 1;      // residual half
-      if (run(false)) return 1;                             // skip half
+      std::vector<FlowStep>& steps = plan->steps[ci];
+      size_t si = 0;
+      auto run = [&](bool with_cond) -> int {
+        FlowStep s = steps[si++];   // copy: per-call fields, re-entrant across threads
+        if (!with_cond) s.ep.bias_b = nullptr;
+        return launch_conv_tc(s.tc, s.ep, qs);
+      };
+      if (run(false)) return 1;                               // pre
+      for (int l = 0; l < nl; ++l) {
+        if (run(g != nullptr)) return 1;                      // in_layer (+ cond)
+        flow_gate_kernel<<<grid1d(rows * (H / 2)), 256, 0, qs>>>(XIN, ACT, rows, H);
+        VD_CUDA(cudaGetLastError());
+        if (c.layers[l].has_res && run(false)) return 1;      // residual half
+        if (run(false)) return 1;                             // skip half
+      }
+      if (run(false)) return 1;                               // post -> M
+      flow_couple_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, M, mask, rows, C, reverse ? 1 : 0);
+      VD_CUDA(cudaGetLastError());
     }
-    if (run(false)) return 1;                               // post -> M
-    flow_couple_kernel<<<grid1d(rows * (C / 2)), 256, 0, st>>>(X, M, lens, T, rows, C, reverse ? 1 : 0);
-    VD_CUDA(cudaGetLastError());
+    return 0;
+  };
+  bool launched = false;
+  if (!plan->graph_failed) {
+    std::lock_guard<std::mutex> lock(f->mu);
+    cudaGraphExec_t& exec = plan->graph_exec[(reverse ? 2 : 0) + (g ? 1 : 0)];
+    if (!exec) {
+      if (!f->cstream) VD_CUDA(cudaStreamCreateWithFlags(&f->cstream, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      bool ok = cudaStreamBeginCapture(f->cstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        const int rc = enqueue(f->cstream);
+        ok = cudaStreamEndCapture(f->cstream, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+      }
+      if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok) {
+        cudaGetLastError();
+        exec = nullptr;
+        plan->graph_failed = true;  // plain launches for this plan from now on
+      }
+    }
+    if (exec) {
+      VD_CUDA(cudaGraphLaunch(exec, st));
+      launched = true;
+    }
   }
+  if (!launched && enqueue(st)) return 1;
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
     flow_out_kernel<<<grid, block, 0, st>>>(X, out, C, T, reverse ? 0 : 1);   // forward ends with a Flip

@@ -130,8 +130,8 @@ class ResidualCouplingBlock(nn.Module):
             pass
 
     def forward(self, x, x_mask, g=None, reverse=False):
-        """x: [B, channels, T] float on a CUDA device; x_mask: [B, 1, T] sequence mask (commons.sequence_mask: ones up
-        to each utterance's length); g: [B, gin_channels, 1] or None.  Returns [B, channels, T] (models.py:203-210)."""
+        """x: [B, channels, T] float on a CUDA device; x_mask: [B, 1, T] binary mask (commons.sequence_mask) or None;
+        g: [B, gin_channels, 1] or None.  Returns [B, channels, T] (models.py:203-210)."""
         if x.dim() != 3 or x.shape[1] != self.channels:
             raise RuntimeError("ResidualCouplingBlock.forward: expected x of shape [B, %d, T], got %s"
                                % (self.channels, tuple(x.shape)))
@@ -150,14 +150,12 @@ class ResidualCouplingBlock(nn.Module):
         xf = x if x.dtype == torch.float32 else x.float()
         if xf.stride(2) != 1:
             xf = xf.contiguous()
-        lens = None
+        mk = None
         if x_mask is not None:
-            m = x_mask.to(device=device).reshape(B, T)
-            lens = (m != 0).sum(dim=1).to(torch.int32)
-            # the native block takes x_mask as sequence lengths: anything but a prefix mask is outside the contract
-            if not bool(((torch.arange(T, device=device)[None, :] < lens[:, None]) == (m != 0)).all()):
-                raise RuntimeError("ResidualCouplingBlock.forward: x_mask must be a sequence (prefix) mask")
-            lens = lens.contiguous()
+            if x_mask.numel() != B * T:
+                raise RuntimeError("ResidualCouplingBlock.forward: expected x_mask of shape [%d, 1, %d], got %s"
+                                   % (B, T, tuple(x_mask.shape)))
+            mk = x_mask.to(device=device, dtype=torch.float32).reshape(B, T).contiguous()
         gf = None
         if g is not None:
             gf = g.to(device=device, dtype=torch.float32).reshape(B, self.gin_channels).contiguous()
@@ -170,7 +168,7 @@ class ResidualCouplingBlock(nn.Module):
             out = torch.empty((B, self.channels, T), dtype=torch.float32, device=device)
             stream = torch.cuda.current_stream(device).cuda_stream
             _capi.check(lib.vitsdec_flow_apply(self._handle, xf.data_ptr(), xf.stride(0), xf.stride(1),
-                                               None if lens is None else lens.data_ptr(),
+                                               None if mk is None else mk.data_ptr(),
                                                None if gf is None else gf.data_ptr(), out.data_ptr(), B, T,
                                                1 if reverse else 0, ws.data_ptr(), nbytes, stream), "vitsdec_flow_apply")
         return out if out_dtype == torch.float32 else out.to(out_dtype)

@@ -96,10 +96,15 @@ def test_no_speaker_conditioning_and_half_input():
         yh = F(x.to(DEV).half(), m.to(DEV), g=None, reverse=True)
     check(flow_forward_torch(hp, sd, x, m, None, reverse=True), y)
     assert yh.dtype == torch.float16
-    with torch.no_grad(), pytest.raises(RuntimeError, match="prefix"):
-        bad = m.clone()
-        bad[0, 0, 3] = 0
-        F(x.to(DEV), bad.to(DEV), reverse=True)
+    # any binary mask, not only a sequence mask: `* x_mask` is applied row by row like the reference does
+    holes = m.clone()
+    holes[0, 0, 3] = 0
+    holes[1, 0, 10:14] = 0
+    with torch.no_grad():
+        yh2 = F(x.to(DEV), holes.to(DEV), g=None, reverse=True).cpu()
+        y_none = F(x.to(DEV), None, g=None, reverse=True).cpu()
+    check(flow_forward_torch(hp, sd, x, holes, None, reverse=True), yh2)
+    check(flow_forward_torch(hp, sd, x, torch.ones_like(m), None, reverse=True), y_none)
 
 
 def test_flow_then_decoder_matches_the_reference_chain():
