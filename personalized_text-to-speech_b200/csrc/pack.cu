@@ -44,7 +44,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
 // j - (k-1)/2 = r*(s_min+s) + psi - phi.
 __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                       __nv_bfloat16* __restrict__ wp, int C, int c_out, int k, int r, int s_min,
-                                      int ntaps) {
+                                      int ntaps, int lo_part) {
   const int rc = r * C;
   const long total = (long)ntaps * rc * rc;
   const int hk = (k - 1) / 2;
@@ -56,6 +56,8 @@ __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* 
     const int j = r * s + psi - phi + hk;
     float val = 0.f;
     if (j >= 0 && j < k && co < c_out) val = w[((long)co * C + ci) * k + j] * (scale ? scale[co] : 1.f);
+    // lo_part: the bf16 remainder of the weight, for layers that run with two-term (hi + lo) weights
+    if (lo_part) val -= __bfloat162float(__float2bfloat16_rn(val));
     wp[i] = __float2bfloat16_rn(val);
   }
 }
@@ -208,13 +210,13 @@ int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int 
   return 0;
 }
 int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp, int C, int c_out, int k, int r,
-                          cudaStream_t st) {
+                          cudaStream_t st, int lo_part) {
   const int hk = (k - 1) / 2;
   const int s_min = -((hk + r - 1) / r), s_max = (r - 1 + hk) / r;  // floor(-hk/r), floor((r-1+hk)/r)
   const int ntaps = s_max - s_min + 1;
   const long total = (long)ntaps * r * C * r * C;
   pack_conv_fold_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, C, c_out, k, r,
-                                                                                        s_min, ntaps);
+                                                                                        s_min, ntaps, lo_part);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
