@@ -521,6 +521,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   const bool force_streaming = (desc_mode & 2) != 0;  // test knob: exercise the streamed-weights path everywhere
   pl->no_res_prefetch = (desc_mode & 4) != 0;        // experiment knob: skip the TMA L2 prefetch of residual tiles
   const bool force_no_swap = (desc_mode & 8) != 0;   // test knob: keep wide layers on the time-as-M form
+  const int na_stream = (desc_mode & 32) ? 3 : ((desc_mode & 64) ? 4 : 2);  // experiment knob: activation stages when streaming
   desc_mode &= 1;
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
   VD_CHECK(g.n_total % 32 == 0, "conv_tc: output columns must be a multiple of 32");
@@ -608,7 +609,8 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   } else {
     p.na_stages = 2;
     VD_CHECK(2 * p.a_stage_bytes + 2 * b_stage <= kSmemBudget, "conv_tc: dilation halo too large for shared memory");
-    p.nb_stages = std::min(kMaxNB, (kSmemBudget - 2 * p.a_stage_bytes) / b_stage);
+    if (na_stream * p.a_stage_bytes + 3 * b_stage <= kSmemBudget) p.na_stages = na_stream;
+    p.nb_stages = std::min(kMaxNB, (kSmemBudget - p.na_stages * p.a_stage_bytes) / b_stage);
     p.b_region_bytes = p.nb_stages * b_stage;
   }
   pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + 8192 + 16384;

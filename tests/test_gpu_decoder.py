@@ -228,3 +228,39 @@ def test_time_folded_schedule_tracks_the_unfolded_one():
     for y in (a, b, c, e):
         check(ref, y.cpu())
     assert snr_db(b.cpu(), a.cpu()) > 45.0 and snr_db(b.cpu(), c.cpu()) > 45.0 and snr_db(b.cpu(), e.cpu()) > 45.0
+
+
+def test_large_batch_matches_small_batches_bitwise():
+    """BASELINE config 4's per-GPU shard on two GPUs (128 x 10 s = 18 GB of workspace): index arithmetic at 2^31-scale
+    element counts.  Utterances are independent, so slices of the big batch equal the same utterances decoded alone."""
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 42)
+    B, T = 128, 862
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    z = torch.randn(B, hp.initial_channel, T, device=DEV, generator=gen)
+    g = torch.randn(B, hp.gin_channels, 1, device=DEV, generator=gen)
+    with torch.no_grad():
+        y = G(z, g)
+        assert y.shape == (B, 1, T * 256) and torch.isfinite(y).all()
+        for lo in (0, 63, 127):
+            assert torch.equal(y[lo:lo + 1], G(z[lo:lo + 1], g[lo:lo + 1]))
+    del y
+    torch.cuda.empty_cache()
+
+
+def test_sixty_second_utterance_chunked_at_config5_size():
+    """BASELINE config 5: one 60 s utterance (T = 5168), 512-frame chunks with 12-frame halos vs the unchunked decode."""
+    hp = oracle.UMA_TRILINGUAL
+    G, sd = build(hp, 43)
+    T = 5168
+    z = torch.randn(1, hp.initial_channel, T, device=DEV)
+    g = torch.randn(1, hp.gin_channels, 1, device=DEV)
+    with torch.no_grad():
+        full = G(z, g)
+        chunked = vitsdec.decode_chunked(G, z, g, chunk_frames=512, halo=12, hop=hp.hop)
+    assert chunked.shape == full.shape == (1, 1, T * 256)
+    assert snr_db(full.cpu(), chunked.cpu()) > 42.0
+    # utterance-level check against the fp32 restatement on a window (the full 60 s takes minutes on the CPU)
+    w0, w1 = 2000, 2200
+    ref = generator_forward_torch(hp, to_torch_state_dict(sd), z[:, :, w0 - 12:w1 + 12].cpu(), g.cpu())
+    check(ref[:, :, 12 * 256:-12 * 256], chunked[:, :, w0 * 256:w1 * 256].cpu())
