@@ -122,6 +122,15 @@ def cpu_reference(batch, frames, steps, warmup, threads=None):
 
 
 def main():
+    # stdout carries exactly ONE line, the JSON record.  Native libraries print there too (NCCL's "NCCL version ..."
+    # banner is a C-level printf): point fd 1 at stderr for the whole run and keep the real stdout for emit().
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(record):
+        os.write(real_stdout, (json.dumps(record) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -157,7 +166,7 @@ def main():
                                  "sample": "1 of the %d utterances (B=1, T=%d) per step, torch CPU eager fp32, "
                                            "weight-norm recomputed per forward like the reference" % (B, frames)},
                 "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import numpy as np
@@ -167,8 +176,6 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    # NCCL's version / debug lines go to stdout by default: keep stdout for the ONE JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -311,7 +318,7 @@ def main():
             line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                     "sample": "1 of the %d utterances (B=1, T=%d), 2 timed passes after 1 warm-up, "
                                               "torch CPU eager fp32 (oracle/generator_torch.py)" % (B, frames)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
