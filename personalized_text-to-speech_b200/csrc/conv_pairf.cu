@@ -265,6 +265,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     ConvEpilogue ep{};
     ep.res[0] = p.x;
     ep.out = p.out;
+    ep.epi_smem = 1;
 
     for (int i = 0; i < my_tiles; ++i) {
       const uint32_t tile = blockIdx.x + i * gridDim.x;

@@ -64,6 +64,8 @@ struct ConvEpilogue {
   __nv_bfloat16* out;          // [B][L][n_total]
   const float* rowmask;        // optional [B][L]: every output row is multiplied by its mask value (x_mask of the
                                // flow, modules.py:171,176; time-as-M tiles with the generic epilogue only)
+  int epi_smem;                // channels-as-M epilogue: 1 = transpose through shared memory (ldmatrix/stmatrix; default),
+                               // 0 = register transposes (movmatrix) and 4-byte global accesses (slower, kept as a knob)
   float* out_f32;              // mrf_mode 4: waveform [B][L * n_total / post_c]
   int post_c;                  // mrf_mode 4: real channels per time sample (n_total = r * post_c)
 };

@@ -521,6 +521,10 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   const bool force_streaming = (desc_mode & 2) != 0;  // test knob: exercise the streamed-weights path everywhere
   pl->no_res_prefetch = (desc_mode & 4) != 0;        // experiment knob: skip the TMA L2 prefetch of residual tiles
   const bool force_no_swap = (desc_mode & 8) != 0;   // test knob: keep wide layers on the time-as-M form
+  // experiment knob: channels-as-M epilogue with register transposes (movmatrix) and 4-byte global accesses instead
+  // of the shared-memory transposition.  It removes ~15 % of the SM's shared-memory traffic but its partial-sector
+  // loads/stores cost far more: 11.97 vs 10.52 ms per 16 x 10 s step.
+  pl->epi_smem = (desc_mode & 128) == 0;
   const int na_stream = (desc_mode & 32) ? 3 : ((desc_mode & 64) ? 4 : 2);  // experiment knob: activation stages when streaming
   desc_mode &= 1;
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
@@ -648,6 +652,7 @@ int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep) {
 
 int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) {
   pl.p.ep = ep;
+  pl.p.ep.epi_smem = pl.epi_smem ? 1 : 0;
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
   pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch && pl.p.rho_d == 1) ? 1 : 0;
   if (pl.swap) {

@@ -68,6 +68,7 @@ struct ConvTcPlan {
   int bn, kc;
   int grid;
   bool no_res_prefetch;
+  bool epi_smem;    // channels-as-M epilogue transposes through shared memory instead of registers (experiment knob)
   bool swap;        // channels-as-M variant (128 channels x 256 time rows per tile)
   size_t smem;
 };

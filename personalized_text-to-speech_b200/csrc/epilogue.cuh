@@ -181,9 +181,21 @@ __device__ __forceinline__ void epiT_issue_loads(const ConvEpilogue& ep, const E
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int row = 8 * j + (lane >> 2);
-        if (row < it.rows_valid)
-          ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + it.base + (long)row * rowstride) +
-                                      (lane & 3));
+        if (ep.epi_smem) {
+          if (row < it.rows_valid)
+            ld.res[i][j] = ld_stream_u4(reinterpret_cast<const uint4*>(ep.res[i] + it.base + (long)row * rowstride) +
+                                        (lane & 3));
+        } else {
+          // 8x8 blocks (time rows 8j + lane/4, channels 8m + 2(lane%4), +1) in the fragment layout of the [time][channel]
+          // matrix: a register transpose (movmatrix) turns each into the accumulator's [channel][time] fragment
+          uint32_t r[4] = {0u, 0u, 0u, 0u};
+          if (row < it.rows_valid) {
+            const __nv_bfloat16* p = ep.res[i] + it.base + (long)row * rowstride + 2 * (lane & 3);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) r[m] = ld_stream_u32(p + 8 * m);
+          }
+          ld.res[i][j] = make_uint4(r[0], r[1], r[2], r[3]);
+        }
       }
     }
   }
@@ -217,15 +229,24 @@ __device__ __forceinline__ void epiT_accumulate(const ConvEpilogue& ep, const fl
 #pragma unroll
   for (int i = 0; i < kMaxRes; ++i) {
     if (epi_has_res<EPI>(ep, i)) {
-      // coalesced registers -> scratch rows [time][32 channels] -> fragment registers (ldmatrix .trans)
+      if (ep.epi_smem) {
+        // coalesced registers -> scratch rows [time][32 channels] -> fragment registers (ldmatrix .trans)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        *reinterpret_cast<uint4*>(scratch + scrT_off(8 * j + (lane >> 2), lane & 3)) = ld.res[i][j];
-      __syncwarp();
+        for (int j = 0; j < 2; ++j)
+          *reinterpret_cast<uint4*>(scratch + scrT_off(8 * j + (lane >> 2), lane & 3)) = ld.res[i][j];
+        __syncwarp();
+      }
 #pragma unroll
       for (int cg = 0; cg < 2; ++cg) {
         uint32_t r[4];
-        ldmatrix_x4_trans(sbase + scrT_off(cg * 8 + (lane & 7), lane >> 3), r);
+        if (ep.epi_smem) {
+          ldmatrix_x4_trans(sbase + scrT_off(cg * 8 + (lane & 7), lane >> 3), r);
+        } else {
+          r[0] = movmatrix_trans(ld.res[i][cg].x);
+          r[1] = movmatrix_trans(ld.res[i][cg].y);
+          r[2] = movmatrix_trans(ld.res[i][cg].z);
+          r[3] = movmatrix_trans(ld.res[i][cg].w);
+        }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const float a0 = __uint_as_float(r[m] << 16), a1 = __uint_as_float(r[m] & 0xffff0000u);
@@ -234,7 +255,7 @@ __device__ __forceinline__ void epiT_accumulate(const ConvEpilogue& ep, const fl
           v[frag_idx(m, cg, 1)] += fminf(a1, a1 * res_gain);
         }
       }
-      __syncwarp();
+      if (ep.epi_smem) __syncwarp();
     }
   }
 }
@@ -256,8 +277,20 @@ __device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scra
       const __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(x0, x0 * out_slope), fmaxf(x1, x1 * out_slope));  // slope in (0,1]
       pk[m] = *reinterpret_cast<const uint32_t*>(&o);
     }
-    stmatrix_x4_trans(sbase + scrT_off(cg * 8 + (lane & 7), lane >> 3), pk[0], pk[1], pk[2], pk[3]);
+    if (ep.epi_smem) {
+      stmatrix_x4_trans(sbase + scrT_off(cg * 8 + (lane & 7), lane >> 3), pk[0], pk[1], pk[2], pk[3]);
+    } else {
+      // register transpose: afterwards this thread holds (time cg*8 + lane/4, channels 8m + 2(lane%4), +1)
+      const int row = cg * 8 + (lane >> 2);
+      __nv_bfloat16* p = ep.out + it.base + (long)row * rowstride + 2 * (lane & 3);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const uint32_t t = movmatrix_trans(pk[m]);
+        if (row < it.rows_valid) *reinterpret_cast<uint32_t*>(p + 8 * m) = t;
+      }
+    }
   }
+  if (!ep.epi_smem) return;
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 2; ++j) {

@@ -194,6 +194,19 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[
                : "memory");
 }
 
+// Register-to-register transpose of an 8x8 b16 matrix held in the mma-fragment layout (thread t: row t/4, columns
+// 2(t%4), 2(t%4)+1): afterwards thread t holds the same positions of the TRANSPOSED matrix.  No shared memory.
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
 // Shared-memory matrix descriptor, K-major operand, swizzled rows (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows)
 //   [46,48) version=1 | [49,52) base offset | [61,64) layout (2 = SW128, 4 = SW64, 6 = SW32)
