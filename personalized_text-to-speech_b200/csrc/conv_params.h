@@ -64,6 +64,8 @@ struct ConvEpilogue {
   __nv_bfloat16* out;          // [B][L][n_total]
   const float* rowmask;        // optional [B][L]: every output row is multiplied by its mask value (x_mask of the
                                // flow, modules.py:171,176; time-as-M tiles with the generic epilogue only)
+  int gate;                    // 1: columns are (a_j, b_j) pairs; out[b,t,j] = tanh(a_j) * sigmoid(b_j), n_total/2 output
+                               // columns (WN's fused_add_tanh_sigmoid_multiply, commons.py:103-110; generic time-as-M only)
   int epi_smem;                // channels-as-M epilogue: 1 = transpose through shared memory (ldmatrix/stmatrix; default),
                                // 0 = register transposes (movmatrix) and 4-byte global accesses (slower, kept as a knob)
   float* out_f32;              // mrf_mode 4: waveform [B][L * n_total / post_c]

@@ -507,7 +507,7 @@ template <int BN, int KC, bool SPECIALISED>
 static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
   const ConvEpilogue& e = pl.p.ep;
   if constexpr (SPECIALISED) {
-    const bool simple = e.bias_b == nullptr && e.rowmask == nullptr &&
+    const bool simple = e.bias_b == nullptr && e.rowmask == nullptr && !e.gate &&
                         (e.mrf_mode == 0 || (e.mrf_mode == 3 && e.mrf == nullptr));
     if (simple && e.mrf_mode == 0 && e.nres == 0) return launch_one<BN, KC, 1>(pl, stream);
     if (simple && e.mrf_mode == 0 && e.nres == 1) return launch_one<BN, KC, 2>(pl, stream);
@@ -656,7 +656,7 @@ int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) 
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
   pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch && pl.p.rho_d == 1) ? 1 : 0;
   if (pl.swap) {
-    VD_CHECK(ep.rowmask == nullptr, "conv_tc: the row mask needs a time-as-M plan (allow_swap = false)");
+    VD_CHECK(ep.rowmask == nullptr && !ep.gate, "conv_tc: row mask / gate need a time-as-M plan (allow_swap = false)");
     VD_CHECK(ep.mrf == nullptr, "conv_tc: the channels-as-M variant has no fp32 MRF accumulator path");
     return launch_swapped(pl, stream);
   }

@@ -132,6 +132,21 @@ __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scrat
 #pragma unroll
     for (int j = 0; j < kIW; ++j) v[j] *= mk;
   }
+  if (EPI == 0 && ep.gate) {
+    // gated activation of the flow's WN: the layer's output channels were interleaved at pack time so that this
+    // thread's 16 columns are 8 (tanh input, sigmoid input) pairs -> 8 bf16 outputs = one 16-byte store per row
+    uint4 ov;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float g0 = tanhf(v[4 * e]) * (1.f / (1.f + __expf(-v[4 * e + 1])));
+      const float g1 = tanhf(v[4 * e + 2]) * (1.f / (1.f + __expf(-v[4 * e + 3])));
+      o2[e] = __floats2bfloat162_rn(g0, g1);
+    }
+    if (lane < it.rows_valid)
+      *reinterpret_cast<uint4*>(ep.out + (it.row0 + lane) * (n_total / 2) + it.n / 2) = ov;
+    return;
+  }
   if (EPI == 0 && (ep.mrf_mode == 1 || ep.mrf_mode == 2)) {
     if (lane < it.rows_valid) {
       float4* mp = reinterpret_cast<float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);

@@ -13,8 +13,9 @@
 //   flip_split   X <- flip(X) (reverse) ; X0 = bf16(X[:, :C/2])
 //   pre          H = (W_pre X0 + b) * mask                                               modules.py:326
 //   cond         CB[l][b] = cond_layer(g)[l]            (weight-normed 1x1 conv = GEMV)   modules.py:153-154
-//   per layer l  XIN = in_l(H) + b + CB[l][b]    (conv k, dilation rate^l)               modules.py:157
-//                ACT = tanh(XIN[:, :Hc]) * sigmoid(XIN[:, Hc:])                          commons.py:105-110
+//   per layer l  ACT = tanh(a) * sigmoid(b),  (a | b) = in_l(H) + bias + CB[l][b]        modules.py:157, commons.py:105-110
+//                (conv k, dilation rate^l; the gate runs in the conv's epilogue: in_l's output channels are packed
+//                interleaved, (a_j, b_j) in adjacent columns, so one thread holds both halves of a pair)
 //                H   = (W_res ACT + b_res + H) * mask        (not for the last layer)    modules.py:171-172
 //                S  += W_skip ACT + b_skip                   (fp32 accumulator)          modules.py:173-175
 //   post         M = (W_post bf16(S * mask) + b) * mask                (fp32)            modules.py:328
@@ -90,20 +91,6 @@ __global__ void flow_flip_split_kernel(float* __restrict__ x, bf16* __restrict__
   }
 }
 
-// acts = tanh(a) * sigmoid(b) over the two halves of XIN's columns (commons.py:105-110)
-__global__ void flow_gate_kernel(const bf16* __restrict__ xin, bf16* __restrict__ act, long rows, int H) {
-  const int hv = H / 2;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < rows * hv; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / hv;
-    const int c = (i % hv) * 2;
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xin + r * 2 * H + c));
-    const float2 s = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xin + r * 2 * H + H + c));
-    const float o0 = tanhf(a.x) * (1.f / (1.f + __expf(-s.x)));
-    const float o1 = tanhf(a.y) * (1.f / (1.f + __expf(-s.y)));
-    *reinterpret_cast<__nv_bfloat162*>(act + r * H + c) = __floats2bfloat162_rn(o0, o1);
-  }
-}
-
 // x1 = (x1 - m) * mask (reverse) or m + x1 * mask (forward); m is already masked (modules.py:328, 335-343, logs = 0)
 __global__ void flow_couple_kernel(float* __restrict__ x, const float* __restrict__ m, const float* __restrict__ mask,
                                    long rows, int C, int reverse) {
@@ -131,7 +118,9 @@ __global__ void flow_cond_kernel(const float* __restrict__ wc, const float* __re
   float s = 0.f;
   for (int i = lane; i < gin; i += 32) s = fmaf(wc[(long)warp * gin + i], g[(long)b * gin + i], s);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) cb[((long)(warp / N) * B + b) * N + warp % N] = s + bc[warp];
+  // column order of the interleaved in_layer: output o < N/2 (tanh half) -> 2o, o >= N/2 (sigmoid half) -> 2(o-N/2)+1
+  const int o = warp % N, col = o < N / 2 ? 2 * o : 2 * (o - N / 2) + 1;
+  if (lane == 0) cb[((long)(warp / N) * B + b) * N + col] = s + bc[warp];
 }
 
 // w_eff = v * g / ||v|| kept in fp32 (cond_layer: used by the GEMV above, not by the tensor cores)
@@ -223,7 +212,7 @@ struct vitsdec_flow {
 namespace vd {
 
 struct FlowWs {
-  size_t x, x0, h0, h1, xin, act, s, outb, m, cb, mask, g, total;
+  size_t x, x0, h0, h1, act, s, outb, m, cb, mask, g, total;
 };
 
 static FlowWs flow_ws(const vitsdec_flow* f, int B, int T) {
@@ -234,7 +223,6 @@ static FlowWs flow_ws(const vitsdec_flow* f, int B, int T) {
   w.x0 = o; o += fl_align(rows * (C / 2) * 2);
   w.h0 = o; o += fl_align(rows * H * 2);
   w.h1 = o; o += fl_align(rows * H * 2);
-  w.xin = o; o += fl_align(rows * 2 * H * 2);
   w.act = o; o += fl_align(rows * H * 2);
   w.s = o; o += fl_align(rows * H * 4);
   w.outb = o; o += fl_align(rows * H * 2);
@@ -261,7 +249,6 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
   const int H = f->hp.hidden_channels, nl = f->hp.n_layers;
   bf16* X0 = reinterpret_cast<bf16*>(ws + w.x0);
   bf16* Hb[2] = {reinterpret_cast<bf16*>(ws + w.h0), reinterpret_cast<bf16*>(ws + w.h1)};
-  bf16* XIN = reinterpret_cast<bf16*>(ws + w.xin);
   bf16* ACT = reinterpret_cast<bf16*>(ws + w.act);
   float* S = reinterpret_cast<float*>(ws + w.s);
   bf16* OUTB = reinterpret_cast<bf16*>(ws + w.outb);
@@ -297,7 +284,8 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
       FlowLayer& ly = c.layers[l];
       {
         ConvEpilogue e{};
-        e.out = XIN;
+        e.out = ACT;
+        e.gate = 1;
         if (f->hp.gin_channels) e.bias_b = CB + (size_t)l * B * 2 * H;  // only used when g is given
         if (push(ly.in, Hb[cur], e)) return 1;
       }
@@ -440,7 +428,9 @@ int vitsdec_flow_load_layer(vitsdec_flow* f, const char* name, const float* w, c
     FlowConv& cv = c.layers[li].in;
     VD_CHECK(cv.c_out <= 8192, "flow: too many channels");
     if (launch_wn_scale(w, wg, f->scale_scratch, cv.c_out, cv.c_in * cv.k, st)) return 1;
-    if (load_conv(cv, w, f->scale_scratch, bias)) return 1;
+    // gate pairs side by side: packed row 2j = tanh-half row j, 2j+1 = sigmoid-half row H + j (ConvEpilogue::gate)
+    if (launch_pack_conv(w, f->scale_scratch, cv.w, cv.c_out, cv.c_in, cv.k, st, /*interleave=*/1)) return 1;
+    if (launch_interleave_bias(bias, cv.bias, cv.c_out, st)) return 1;
   } else if (sscanf(rest.c_str(), "enc.res_skip_layers.%d", &li) == 1 && li >= 0 && li < nl) {
     FlowLayer& ly = c.layers[li];
     const int rows = ly.has_res ? 2 * H : H;
@@ -508,8 +498,6 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
   const long rows = (long)B * T;
   float* X = reinterpret_cast<float*>(base + w.x);
   bf16* X0 = reinterpret_cast<bf16*>(base + w.x0);
-  bf16* XIN = reinterpret_cast<bf16*>(base + w.xin);
-  bf16* ACT = reinterpret_cast<bf16*>(base + w.act);
   float* M = reinterpret_cast<float*>(base + w.m);
   float* CB = reinterpret_cast<float*>(base + w.cb);
   float* mask = reinterpret_cast<float*>(base + w.mask);
@@ -544,9 +532,7 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
       };
       if (run(false)) return 1;                               // pre
       for (int l = 0; l < nl; ++l) {
-        if (run(g != nullptr)) return 1;                      // in_layer (+ cond)
-        flow_gate_kernel<<<grid1d(rows * (H / 2)), 256, 0, qs>>>(XIN, ACT, rows, H);
-        VD_CUDA(cudaGetLastError());
+        if (run(g != nullptr)) return 1;                      // in_layer (+ cond) with the gate in its epilogue
         if (c.layers[l].has_res && run(false)) return 1;      // residual half
         if (run(false)) return 1;                             // skip half
       }

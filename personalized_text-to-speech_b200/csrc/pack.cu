@@ -27,13 +27,15 @@ __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __rest
   }
 }
 
-// Conv1d weight [co][ci][k] -> packed [tap][co][ci] bf16 (B operand rows = co, K = ci contiguous)
+// Conv1d weight [co][ci][k] -> packed [tap][co][ci] bf16 (B operand rows = co, K = ci contiguous).
+// interleave != 0: packed row 2j holds weight row j, packed row 2j+1 weight row c_out/2 + j (gate pairs, ConvEpilogue::gate)
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                 __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int k) {
+                                 __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int k, int interleave) {
   const long total = (long)k * c_out * c_in;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int ci = i % c_in;
-    const int co = (i / c_in) % c_out;
+    int co = (i / c_in) % c_out;
+    if (interleave) co = (co & 1) ? c_out / 2 + (co >> 1) : (co >> 1);
     const int j = i / ((long)c_in * c_out);
     wp[i] = __float2bfloat16_rn(w[((long)co * c_in + ci) * k + j] * scale[co]);
   }
@@ -84,6 +86,10 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __re
 __global__ void replicate_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int c_out, int reps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c_out * reps) out[i] = b ? b[i % c_out] : 0.f;
+}
+__global__ void interleave_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int c_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c_out) out[i] = b[(i & 1) ? c_out / 2 + (i >> 1) : (i >> 1)];
 }
 
 // combined bias of a fused MRF launch: sum of the member layers' biases
@@ -202,10 +208,16 @@ int launch_wn_scale(const float* v, const float* g, float* scale, int rows, int 
   VD_CUDA(cudaGetLastError());
   return 0;
 }
+int launch_interleave_bias(const float* b, float* out, int c_out, cudaStream_t st) {
+  interleave_bias_kernel<<<(c_out + 255) / 256, 256, 0, st>>>(b, out, c_out);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
 int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int c_out, int c_in, int k,
-                     cudaStream_t st) {
+                     cudaStream_t st, int interleave) {
   const long total = (long)k * c_out * c_in;
-  pack_conv_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_out, c_in, k);
+  pack_conv_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_out, c_in, k,
+                                                                                   interleave);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

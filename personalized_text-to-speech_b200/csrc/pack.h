@@ -8,7 +8,8 @@
 namespace vd {
 int launch_wn_scale(const float* v, const float* g, float* scale, int rows, int inner, cudaStream_t st);
 int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int c_out, int c_in, int k,
-                     cudaStream_t st);
+                     cudaStream_t st, int interleave = 0);
+int launch_interleave_bias(const float* b, float* out, int c_out, cudaStream_t st);
 int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp, int C, int c_out, int k, int r,
                           cudaStream_t st, int lo_part = 0);
 int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int c_in, int c_out, int k, int s, int p,
