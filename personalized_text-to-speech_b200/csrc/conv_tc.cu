@@ -345,15 +345,19 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         // conv_post: this lane's folded column is (phase, channel) = ((32q + lane) / C, (32q + lane) % C); only
         // channel 0 is a real output.  Columns of the item are consecutive folded rows: samples r apart.
         const int pc = ep.post_c;
-        if ((q * 32) % pc == 0 && lane < 4) {  // fragment layout: lanes 0..3 hold channel 32q, four columns each
+        if ((q * 32) % pc == 0) {  // warp-uniform: this warp's first channel is channel 0 of phase 32q / C
+          // fragment layout: lanes 0..3 hold channel 0 (bf16(w) sums), lanes 4..7 channel 1 (the weights' bf16
+          // remainders), four columns each: add the two rows, then tanh
           const int r = n_total / pc;
           float* o = ep.out_f32 + cur.row0 * r + (q * 32) / pc;
 #pragma unroll
           for (int cg = 0; cg < 2; ++cg)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int col = cg * 8 + 2 * lane + e;
-              if (col < cur.rows_valid) o[(long)col * r] = tanhf(__uint_as_float(acc[frag_idx(0, cg, e)]));
+              const float hi = __uint_as_float(acc[frag_idx(0, cg, e)]);
+              const float x = hi + __shfl_down_sync(0xffffffffu, hi, 4);
+              const int col = cg * 8 + 2 * (lane & 3) + e;
+              if (lane < 4 && col < cur.rows_valid) o[(long)col * r] = tanhf(x);
             }
         }
       } else if constexpr (SWAP) epiT_accumulate<EPI>(ep, bias4, scratch, cur, n_total, lane, res_gain, acc, ld, v);

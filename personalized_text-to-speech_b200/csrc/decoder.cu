@@ -615,10 +615,10 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
       fg = ConvGeom{};
       fg.c_in = fg.n_total = r * lp.c_in;
       // Two-term weights: conv_post sums 7*C products that largely cancel (the waveform is small next to the last
-      // stage's activations), so the bf16 rounding of its weights alone cost 0.5-1.7 dB of waveform SNR.  The taps are
-      // laid down twice, bf16(w) and bf16(w - bf16(w)); the launch is HBM-bound, the extra MMAs are free.
-      const int nt = fold_taps(lp.c_in, lp.k, r, fg, 0);
-      fg.ntaps = nt + fold_taps(lp.c_in, lp.k, r, fg, nt);
+      // stage's activations), so the bf16 rounding of its weights alone cost 0.5-1.7 dB of waveform SNR.  Only channel
+      // 0 of each phase is a real output, so channel 1 carries bf16(w - bf16(w)) and the epilogue adds the two rows:
+      // no extra MMAs (doubling the taps instead made the launch 157 us instead of 89).
+      fg.ntaps = fold_taps(lp.c_in, lp.k, r, fg, 0);
       fg.nseg = 1;
       fg.seg_tap_end[0] = fg.ntaps;
     }
@@ -797,11 +797,9 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
   } else {
     VD_CHECK(wg == nullptr, "conv_post / cond are not weight-normed in the reference (models.py:264,268)");
     VD_CUDA(cudaMemcpyAsync(l.wf32, w, (size_t)l.c_out * l.c_in * l.k * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (l.kind == kPost && l.fold_r) {  // hi and lo parts of the two-term weights
-      const size_t half = (size_t)(l.fgeom.ntaps / 2) * l.fgeom.n_total * l.fgeom.c_in;
-      if (launch_pack_conv_fold(w, nullptr, l.wfold, l.c_in, 1, l.k, l.fold_r, st, 0)) return 1;
-      if (launch_pack_conv_fold(w, nullptr, l.wfold + half, l.c_in, 1, l.k, l.fold_r, st, 1)) return 1;
-    }
+    // two-term weights: virtual channel 0 = bf16(w), channel 1 = bf16(w - bf16(w))
+    if (l.kind == kPost && l.fold_r && launch_pack_conv_fold(w, nullptr, l.wfold, l.c_in, 1, l.k, l.fold_r, st, 1))
+      return 1;
     if (l.kind == kCond) {
       VD_CHECK(bias != nullptr, "cond needs a bias");
       VD_CUDA(cudaMemcpyAsync(l.bias, bias, (size_t)l.c_out * sizeof(float), cudaMemcpyDeviceToDevice, st));

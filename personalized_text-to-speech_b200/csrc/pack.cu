@@ -57,9 +57,11 @@ __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* 
     const int psi = cc / C, ci = cc % C, phi = nn / C, co = nn % C;
     const int j = r * s + psi - phi + hk;
     float val = 0.f;
-    if (j >= 0 && j < k && co < c_out) val = w[((long)co * C + ci) * k + j] * (scale ? scale[co] : 1.f);
-    // lo_part: the bf16 remainder of the weight, for layers that run with two-term (hi + lo) weights
-    if (lo_part) val -= __bfloat162float(__float2bfloat16_rn(val));
+    // lo_part (two-term weights of a single-output layer): output row 0 holds bf16(w), row 1 the bf16 remainder
+    // w - bf16(w) of the SAME source row; the epilogue adds the two accumulator rows
+    const int src = lo_part ? 0 : co;
+    if (j >= 0 && j < k && co < (lo_part ? 2 : c_out)) val = w[((long)src * C + ci) * k + j] * (scale ? scale[src] : 1.f);
+    if (lo_part && co == 1) val -= __bfloat162float(__float2bfloat16_rn(val));
     wp[i] = __float2bfloat16_rn(val);
   }
 }
