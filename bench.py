@@ -268,6 +268,18 @@ def main():
         barrier()
         flow_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
+        # BASELINE config 2 (batch 1, 2 s latent): latency of one decode, launch- and prologue-bound (extra key)
+        z1, g1 = z[:1, :, :173].contiguous(), g[:1]
+        for _ in range(5):
+            G(z1, g1)
+        barrier()
+        e0.record()
+        for _ in range(50):
+            G(z1, g1)
+        e1.record()
+        barrier()
+        lat_ms = max_over_ranks(e0.elapsed_time(e1)) / 50
+
         gather_ms = None
         if world > 1:  # the optional final waveform gather (north_star): timed separately, not on the data path
             full = torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev)
@@ -310,6 +322,7 @@ def main():
         "clocks": clocks,
     }
     line["flow_reverse_ms_per_step"] = flow_ms
+    line["latency_b1_2s_ms"] = lat_ms
     if gather_ms is not None:
         line["waveform_gather_ms"] = gather_ms
     if rank == 0:

@@ -136,3 +136,54 @@ def test_polyphase_transposed_conv_derivation():
                         if 0 <= i + off < L:
                             y[0, :, s * i + r] += w[:, :, j].T @ x[0, :, i + off]
         assert ref.shape == y.shape and np.abs(ref - y).max() < 1e-12
+
+
+def _fold_weights(w, r):
+    """numpy restatement of pack_conv_fold_kernel (csrc/pack.cu): W'[s][phi*C+co][psi*C+ci] = W[co][ci][j],
+    j - (k-1)/2 = r*s + psi - phi."""
+    co_n, ci_n, k = w.shape
+    hk = (k - 1) // 2
+    s_min, s_max = -((hk + r - 1) // r), (r - 1 + hk) // r
+    out = np.zeros((s_max - s_min + 1, r * co_n, r * ci_n))
+    for si, s in enumerate(range(s_min, s_max + 1)):
+        for phi in range(r):
+            for psi in range(r):
+                j = r * s + psi - phi + hk
+                if 0 <= j < k:
+                    out[si, phi * co_n:(phi + 1) * co_n, psi * ci_n:(psi + 1) * ci_n] = w[:, :, j]
+    return out, s_min
+
+
+def test_time_folded_conv_derivation():
+    """The time-folded form of decoder.cu fold_geom: a k-tap conv on [L][C] equals a conv over folded rows [L/r][r*C]
+    with block-Toeplitz weights; a dilation-d conv equals the same folded conv on each sub-sequence t = d*q + rho
+    (zero padding at both ends, ragged last row of a sub-sequence treated as zeros)."""
+    from oracle.generator_np import conv1d
+    rs = np.random.RandomState(1)
+    for (C, k, r, d, L) in ((4, 3, 4, 1, 24), (3, 7, 2, 1, 18), (4, 11, 4, 1, 40), (4, 3, 4, 3, 29), (3, 7, 2, 5, 31),
+                            (2, 11, 4, 2, 5)):
+        x = rs.standard_normal((1, C, L))
+        w = rs.standard_normal((C, C, k))
+        ref = conv1d(x, w, None, dilation=d, padding=(k - 1) // 2 * d)[0].T        # [L][C]
+        wf, s_min = _fold_weights(w, r)
+        y = np.zeros((L, C))
+        rows = -(-L // (d * r))
+        for rho in range(d):
+            # folded rows of sub-sequence rho: row n, phase phi <-> sample t = d*(r*n + phi) + rho  (zeros past the end)
+            xf = np.zeros((rows, r * C))
+            for n in range(rows):
+                for phi in range(r):
+                    t = d * (r * n + phi) + rho
+                    if t < L:
+                        xf[n, phi * C:(phi + 1) * C] = x[0, :, t]
+            for n in range(rows):
+                acc = np.zeros(r * C)
+                for si in range(wf.shape[0]):
+                    m = n + s_min + si
+                    if 0 <= m < rows:
+                        acc += wf[si] @ xf[m]
+                for phi in range(r):
+                    t = d * (r * n + phi) + rho
+                    if t < L:
+                        y[t] = acc[phi * C:(phi + 1) * C]
+        assert np.abs(ref - y).max() < 1e-12, (C, k, r, d, L)

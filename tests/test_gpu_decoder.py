@@ -264,3 +264,40 @@ def test_sixty_second_utterance_chunked_at_config5_size():
     w0, w1 = 2000, 2200
     ref = generator_forward_torch(hp, to_torch_state_dict(sd), z[:, :, w0 - 12:w1 + 12].cpu(), g.cpu())
     check(ref[:, :, 12 * 256:-12 * 256], chunked[:, :, w0 * 256:w1 * 256].cpu())
+
+
+def test_concurrent_forward_from_worker_threads():
+    """Gradio calls tts_fn from worker threads (VC_inference.py:38-53): forward on one module from several threads, each
+    on its own stream, must give the single-threaded results (per-call workspace, plan building behind a mutex)."""
+    import threading
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 44)
+    shapes = [(1, 40), (2, 33), (1, 40), (3, 21)]
+    zs = [torch.randn(b, hp.initial_channel, t, device=DEV) for b, t in shapes]
+    gs = [torch.randn(b, hp.gin_channels, 1, device=DEV) for b, _ in shapes]
+    with torch.no_grad():
+        want = [G(z, g).clone() for z, g in zip(zs, gs)]
+    torch.cuda.synchronize()
+    got = [None] * len(shapes)
+    errs = []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream(device=DEV)
+            with torch.no_grad(), torch.cuda.stream(s):
+                for _ in range(5):
+                    y = G(zs[i], gs[i])
+                got[i] = y.clone()
+            s.synchronize()
+        except Exception as e:  # surfaced below
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(shapes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errs, errs
+    for w, y in zip(want, got):
+        assert torch.equal(w, y)
