@@ -99,7 +99,8 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
  *          "fuse_pairs" = 0 run every ResBlock conv as its own launch (default 1: fused pairs where they fit);
  *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph);
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
- *          "pairf" = 0 keeps fused pairs on conv_pair.cu (default 1: time-folded conv_pairf.cu). */
+ *          "pairf" = 0 keeps fused pairs on conv_pair.cu (default 1: time-folded conv_pairf.cu where it is faster);
+ *          "par" = 0 serial MRF branches, 2 always concurrent (default 1: concurrent under the graph for small decodes). */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
 

@@ -179,6 +179,7 @@ struct Step {           // one launch of the conv primitive
   PairPlan pair;
   bool is_pairf = false;    // time-folded fused pair (conv_pairf.cu)
   PairFPlan pairf;
+  int branch = -1;          // MRF branch this launch belongs to (-1: trunk), for concurrent branches under the graph
   bf16* dbg_dst = nullptr;  // debug_keep: copy ep.out here after the launch
   size_t dbg_bytes = 0;
 };
@@ -192,6 +193,10 @@ struct Plan {
   // with this plan); index 0: no speaker conditioning, 1: conv_pre adds the per-utterance cond bias
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   bool graph_failed = false;
+  // Concurrent MRF branches: small decodes (a 2 s utterance has 12-170 tiles per launch for 148 SMs) are bound by
+  // launch latency and under-filled kernels; the three branches of a stage are independent, so under the CUDA graph
+  // they run on forked streams.  Large batches fill the machine with one launch and stay serial.
+  bool par = false;
   std::vector<Step> steps;
   bf16* a0;          // packed latent
   float* cb;         // cond bias [B][C]
@@ -220,8 +225,10 @@ struct vitsdec_decoder {
   std::vector<int> stage_ch;
   int hop = 1;
   float* scale_scratch = nullptr;
-  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1;
+  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1, par = 1;
   cudaStream_t cstream = nullptr;  // capture-only stream (the caller's may be the legacy default stream)
+  cudaStream_t bstream[VITSDEC_MAX_KERNELS] = {};  // capture-only streams of MRF branches 1.. (Plan::par)
+  cudaEvent_t ev_fork = nullptr, ev_join[VITSDEC_MAX_KERNELS] = {};
   std::map<std::pair<int, int>, int> l_pair;  // (resblock index, pair index) -> kPair virtual layer id
   int last_launches = 0;
   // profile=1: CUDA events around the convolution launches of every decode, accumulated on read
@@ -295,6 +302,7 @@ struct WsLayout {
 
 // Slot map.  0: X (stage in/out)  1: U (upsampled)  2: T1 (c1 output of non-final pairs)  3: T2 (pair ping-pong)
 //   fused MRF:  4+j: P_j (input + residual of branch j's last pair)   4+nk+j: H_j (c1 output of that last pair)
+//               4+2nk+2(j-1), +1: T1_j, T2_j of branches j >= 1 (branches may run concurrently, see Plan::par)
 //   fp32-accumulator MRF (fallback):  4: P   5,6: S (one fp32 tensor)
 static bool all_fused(const vitsdec_decoder* d) {
   for (int id : d->l_mrf)
@@ -318,7 +326,8 @@ static WsLayout ws_layout(const vitsdec_decoder* d, int B, int T) {
   w.slot = slot;
   w.off_a0 = o; o += align_up((size_t)B * T * d->hp.initial_channel * 2, 1024);
   w.off_cb = o; o += align_up((size_t)B * d->hp.upsample_initial_channel * 4, 1024);
-  w.nslots = all_fused(d) ? 4 + 2 * d->hp.num_kernels : std::max(7, 4 + 2 * d->hp.num_kernels);
+  w.nslots = all_fused(d) ? 4 + 2 * d->hp.num_kernels + 2 * (d->hp.num_kernels - 1)
+                          : std::max(7, 4 + 2 * d->hp.num_kernels);
   w.off_slots = o; o += (size_t)w.nslots * slot;
   w.off_dbg = o;
   if (d->debug_keep) o += align_up(dbg, 1024);
@@ -416,7 +425,12 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
       const int nconv = (int)convs.size();
       const int npairs = d->hp.resblock == 1 ? nconv / 2 : nconv;
       bf16* Pj = fused ? slot(4 + j) : slot(4);
+      // private temporaries per branch (fused schedule): the branches of a stage are independent between `ups` and
+      // the MRF launch and may run concurrently
+      bf16* T1j = (fused && j > 0) ? slot(4 + 2 * nk + 2 * (j - 1)) : T1;
+      bf16* T2j = (fused && j > 0) ? slot(4 + 2 * nk + 2 * (j - 1) + 1) : T2;
       bf16* Hj = fused ? slot(4 + nk + j) : T1;
+      const size_t first_step = pl.steps.size();
       const bf16* cur = U;
       for (int m = 0; m < npairs; ++m) {
         const bool last = m == npairs - 1;
@@ -431,7 +445,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
         const bool pair_p = pit != d->l_pair.end() && d->layers[pit->second].pair_plain;
         if (!last && d->impl == 0 && d->fuse_pairs && (pair_f || pair_p)) {
           // whole pair in one launch: h stays in shared memory
-          bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2;
+          bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2j;
           Step s{};
           s.layer = pit->second;
           s.L = L;
@@ -453,7 +467,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
         }
         if (d->hp.resblock == 1) {
           ConvEpilogue e1 = ep0(convs[2 * m]);
-          e1.out = last ? Hj : T1;
+          e1.out = last ? Hj : T1j;
           if (push1(convs[2 * m], cur, L, e1)) return 1;
           conv_in = e1.out;
           lid = convs[2 * m + 1];
@@ -469,7 +483,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
         e.res[0] = cur;
         e.nres = 1;
         // ping-pong so that the input of the last pair lands in P_j
-        bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2;
+        bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2j;
         if (!last) {
           e.out = dst;
         } else {
@@ -485,6 +499,8 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
         if (push1(lid, conv_in, L, e)) return 1;
         cur = dst;
       }
+      if (fused)
+        for (size_t si = first_step; si < pl.steps.size(); ++si) pl.steps[si].branch = j;
     }
     if (fused) {
       // models.py:279-284: x = (rb0(x) + rb1(x) + rb2(x)) / nk -- the three last convs accumulate in one TMEM tile
@@ -503,6 +519,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   pl.x_final = X;
   pl.L_final = L;
   pl.C_final = d->stage_ch.back();
+  pl.par = all_fused(d) && nk > 1 && (d->par == 2 || (d->par == 1 && (long)B * T <= 1024));
   pl.post_tc = false;
   Layer& lp = d->layers[d->l_post];
   if (d->impl == 0 && d->fold && lp.fold_r && L % lp.fold_r == 0) {
@@ -737,6 +754,11 @@ void vitsdec_destroy(vitsdec_decoder* d) {
   d->plans.clear();
   d->last_plan.reset();
   if (d->cstream) cudaStreamDestroy(d->cstream);
+  for (int j = 0; j < VITSDEC_MAX_KERNELS; ++j) {
+    if (d->bstream[j]) cudaStreamDestroy(d->bstream[j]);
+    if (d->ev_join[j]) cudaEventDestroy(d->ev_join[j]);
+  }
+  if (d->ev_fork) cudaEventDestroy(d->ev_fork);
   if (d->ev_conv0) cudaEventDestroy(d->ev_conv0);
   if (d->ev_conv1) cudaEventDestroy(d->ev_conv1);
   delete d;
@@ -842,7 +864,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, d->desc_mode * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
+    const PlanKey key{B, T, d->impl, d->desc_mode * 128 + d->par * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -881,12 +903,33 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     }
     VD_CUDA(cudaEventRecord(d->ev_conv0, st));
   }
-  auto enqueue_steps = [&](cudaStream_t qs) -> int {
+  auto enqueue_steps = [&](cudaStream_t qs, bool fork) -> int {
+    int prev = -1;
+    unsigned open_branches = 0;   // branches >= 1 that have launches since the last join
     for (size_t i = 0; i < plan->steps.size(); ++i) {
       Step s = plan->steps[i];  // copy: per-call epilogue fields, re-entrant across threads
       if (i == 0) s.ep.bias_b = g ? plan->cb : nullptr;
-      if (run_conv(d, s, qs)) return 1;
-      if (s.dbg_dst) VD_CUDA(cudaMemcpyAsync(s.dbg_dst, s.ep.out, s.dbg_bytes, cudaMemcpyDeviceToDevice, qs));
+      cudaStream_t ls = qs;
+      if (fork) {
+        const int b = s.branch;
+        if (b == 0 && prev < 0) VD_CUDA(cudaEventRecord(d->ev_fork, qs));   // the point right after `ups`
+        if (b > 0) {
+          if (prev != b) VD_CUDA(cudaStreamWaitEvent(d->bstream[b], d->ev_fork, 0));
+          ls = d->bstream[b];
+          open_branches |= 1u << b;
+        }
+        if (b < 0 && open_branches) {   // back on the trunk (the MRF launch): join
+          for (int j = 1; j < VITSDEC_MAX_KERNELS; ++j)
+            if ((open_branches >> j) & 1u) {
+              VD_CUDA(cudaEventRecord(d->ev_join[j], d->bstream[j]));
+              VD_CUDA(cudaStreamWaitEvent(qs, d->ev_join[j], 0));
+            }
+          open_branches = 0;
+        }
+        prev = b;
+      }
+      if (run_conv(d, s, ls)) return 1;
+      if (s.dbg_dst) VD_CUDA(cudaMemcpyAsync(s.dbg_dst, s.ep.out, s.dbg_bytes, cudaMemcpyDeviceToDevice, ls));
     }
     return 0;
   };
@@ -897,10 +940,17 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     cudaGraphExec_t& exec = plan->graph_exec[g ? 1 : 0];
     if (!exec) {
       if (!d->cstream) VD_CUDA(cudaStreamCreateWithFlags(&d->cstream, cudaStreamNonBlocking));
+      if (plan->par && !d->ev_fork) {
+        VD_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+        for (int j = 1; j < d->hp.num_kernels; ++j) {
+          VD_CUDA(cudaStreamCreateWithFlags(&d->bstream[j], cudaStreamNonBlocking));
+          VD_CUDA(cudaEventCreateWithFlags(&d->ev_join[j], cudaEventDisableTiming));
+        }
+      }
       cudaGraph_t graph = nullptr;
       bool ok = cudaStreamBeginCapture(d->cstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
       if (ok) {
-        const int rc = enqueue_steps(d->cstream);
+        const int rc = enqueue_steps(d->cstream, plan->par);
         ok = cudaStreamEndCapture(d->cstream, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
       }
       if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
@@ -916,7 +966,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
       launched = true;
     }
   }
-  if (!launched && enqueue_steps(st)) return 1;
+  if (!launched && enqueue_steps(st, false)) return 1;
   launches += (int)plan->steps.size();
   if (plan->post_tc) {
     Step s = plan->post;
@@ -979,6 +1029,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "graph")) d->use_graph = value ? 1 : 0;
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
+  else if (!strcmp(key, "par")) d->par = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "profile")) {
     d->profile = value ? 1 : 0;
     d->prof_conv_ms = 0.0;
@@ -1013,6 +1064,7 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   else if (!strcmp(key, "graph")) *value = d->use_graph;
   else if (!strcmp(key, "fold")) *value = d->fold;
   else if (!strcmp(key, "pairf")) *value = d->pairf;
+  else if (!strcmp(key, "par")) *value = d->par;
   else if (!strcmp(key, "hop")) *value = d->hop;
   else if (!strcmp(key, "num_sms")) *value = d->num_sms;
   else { set_error(std::string("unknown option ") + key); return 1; }
