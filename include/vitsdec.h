@@ -100,7 +100,7 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
  *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph);
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
  *          "pairf" = 0 keeps fused pairs on conv_pair.cu (default 1: time-folded conv_pairf.cu where it is faster);
- *          "par" = 0 serial MRF branches, 2 always concurrent (default 1: concurrent under the graph for small decodes). */
+ *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph). */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
 

@@ -195,7 +195,8 @@ struct Plan {
   bool graph_failed = false;
   // Concurrent MRF branches: small decodes (a 2 s utterance has 12-170 tiles per launch for 148 SMs) are bound by
   // launch latency and under-filled kernels; the three branches of a stage are independent, so under the CUDA graph
-  // they run on forked streams.  Large batches fill the machine with one launch and stay serial.
+  // they run on forked streams: 0.84 -> 0.53 ms at 173 frames, 1.19 -> 0.96 ms at 862, neutral to -1.5 % at 16 x 862
+  // (tools/par_sweep.py), so it is always on (option par = 0 serialises).
   bool par = false;
   std::vector<Step> steps;
   bf16* a0;          // packed latent
@@ -519,7 +520,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   pl.x_final = X;
   pl.L_final = L;
   pl.C_final = d->stage_ch.back();
-  pl.par = all_fused(d) && nk > 1 && (d->par == 2 || (d->par == 1 && (long)B * T <= 1024));
+  pl.par = all_fused(d) && nk > 1 && d->par != 0;
   pl.post_tc = false;
   Layer& lp = d->layers[d->l_post];
   if (d->impl == 0 && d->fold && lp.fold_r && L % lp.fold_r == 0) {
@@ -1029,7 +1030,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "graph")) d->use_graph = value ? 1 : 0;
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
-  else if (!strcmp(key, "par")) d->par = value < 0 ? 0 : (value > 2 ? 2 : value);
+  else if (!strcmp(key, "par")) d->par = value ? 1 : 0;
   else if (!strcmp(key, "profile")) {
     d->profile = value ? 1 : 0;
     d->prof_conv_ms = 0.0;

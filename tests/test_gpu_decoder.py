@@ -304,14 +304,14 @@ def test_concurrent_forward_from_worker_threads():
 
 
 def test_concurrent_branches_equal_the_serial_schedule():
-    """Option par: the MRF branches of a stage on forked streams under the CUDA graph (auto for small decodes)."""
+    """Option par: the MRF branches of a stage on forked streams under the CUDA graph (default on)."""
     hp = oracle.FINETUNE_SPEAKER
     G, sd = build(hp, 45)
     for B, T in ((1, 173), (2, 600)):
         z = torch.randn(B, hp.initial_channel, T, device=DEV)
         g = torch.randn(B, hp.gin_channels, 1, device=DEV)
         outs = []
-        for par in (0, 2, 1):
+        for par in (0, 1):
             G.set_option("par", par)
             with torch.no_grad():
                 outs.append(G(z, g).clone())
