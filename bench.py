@@ -236,15 +236,18 @@ def main():
         G.set_option("profile", 0)
         launches = G.last_launch_count() * args.steps
 
-        # ---- end to end through the public API with HOST buffers (pinned): H2D + decode + D2H every step
-        for _ in range(2):
-            out_host.copy_(G(z_host.to(dev, non_blocking=True), g_host.to(dev, non_blocking=True)), non_blocking=True)
+        # ---- end to end through the public API with HOST buffers (pinned): H2D + decode + D2H every step, two batches
+        # in flight (vitsdec.HostPipeline: the copies of neighbouring steps overlap the decode of the current one)
+        pipe = vitsdec.HostPipeline(G, depth=2)
+        outs_host = [out_host, torch.empty_like(out_host).pin_memory()]
+        for i in range(4):
+            pipe.submit(z_host, g_host, outs_host[i % 2])
+        pipe.wait_all()
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            zz = z_host.to(dev, non_blocking=True)
-            gg = g_host.to(dev, non_blocking=True)
-            out_host.copy_(G(zz, gg), non_blocking=True)
+        for i in range(args.steps):
+            pipe.submit(z_host, g_host, outs_host[i % 2])
+        pipe.join()
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))

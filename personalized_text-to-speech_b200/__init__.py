@@ -11,8 +11,9 @@ from .flow import ResidualCouplingBlock  # noqa: F401
 from .patch import patch_reference, unpatch_reference  # noqa: F401
 from .sharding import shard_range, decode_sharded  # noqa: F401
 from .chunked import decode_chunked  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 from .build import build  # noqa: F401
 from .hparams import generator_args, generator_args_from_config  # noqa: F401
 
 __all__ = ["Generator", "ResidualCouplingBlock", "patch_reference", "unpatch_reference", "shard_range", "decode_sharded",
-           "decode_chunked", "build", "generator_args", "generator_args_from_config"]
+           "decode_chunked", "HostPipeline", "build", "generator_args", "generator_args_from_config"]

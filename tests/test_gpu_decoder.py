@@ -318,3 +318,22 @@ def test_concurrent_branches_equal_the_serial_schedule():
                 outs.append(G(z, g).clone())   # graph replay
         for y in outs[1:]:
             assert torch.equal(outs[0], y)
+
+
+def test_host_pipeline_matches_direct_forward():
+    """vitsdec.HostPipeline: pinned host buffers in, pinned waveforms out, several batches in flight."""
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 46)
+    B, T = 2, 90
+    zs = [torch.randn(B, hp.initial_channel, T).pin_memory() for _ in range(5)]
+    gs = [torch.randn(B, hp.gin_channels, 1).pin_memory() for _ in range(5)]
+    outs = [torch.empty(B, 1, T * hp.hop).pin_memory() for _ in range(5)]
+    pipe = vitsdec.HostPipeline(G, depth=2)
+    for z, g, o in zip(zs, gs, outs):
+        pipe.submit(z, g, o)
+    pipe.wait_all()
+    with torch.no_grad():
+        for z, g, o in zip(zs, gs, outs):
+            assert torch.equal(o, G(z.to(DEV), g.to(DEV)).cpu())
+    with pytest.raises(RuntimeError, match="pinned"):
+        pipe.submit(torch.randn(B, hp.initial_channel, T), gs[0], outs[0])

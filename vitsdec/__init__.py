@@ -15,6 +15,7 @@ unpatch_reference = _pkg.unpatch_reference
 shard_range = _pkg.shard_range
 decode_sharded = _pkg.decode_sharded
 decode_chunked = _pkg.decode_chunked
+HostPipeline = _pkg.HostPipeline
 build = _pkg.build
 generator_args = _pkg.generator_args
 generator_args_from_config = _pkg.generator_args_from_config
