@@ -105,8 +105,9 @@ def cpu_reference(batch, frames, steps, warmup, threads=None):
     import torch
     import oracle
     from oracle.generator_torch import generator_forward_torch, to_torch_state_dict
-    if threads:
-        torch.set_num_threads(threads)
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the
+    # reference to one thread)
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     hp = oracle.FINETUNE_SPEAKER
     sd = to_torch_state_dict(oracle.synth_state_dict(hp, 0, gain=2.0))
     rs = np.random.RandomState(1)
