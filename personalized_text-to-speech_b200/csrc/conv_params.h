@@ -64,6 +64,10 @@ struct ConvEpilogue {
   __nv_bfloat16* out;          // [B][L][n_total]
   const float* rowmask;        // optional [B][L]: every output row is multiplied by its mask value (x_mask of the
                                // flow, modules.py:171,176; time-as-M tiles with the generic epilogue only)
+  int split_col;               // > 0 (generic time-as-M only): ONE launch, two epilogues.  Columns [0, split_col) take the
+                               // residual res[0] and the bf16 store to `out` (both with split_col columns per row);
+                               // columns [split_col, n_total) go to the fp32 accumulator `mrf` (n_total - split_col
+                               // columns per row, mrf_mode 1 = store / 2 = add).  WN's res_skip_layers, modules.py:169-173
   int gate;                    // 1: columns are (a_j, b_j) pairs; out[b,t,j] = tanh(a_j) * sigmoid(b_j), n_total/2 output
                                // columns (WN's fused_add_tanh_sigmoid_multiply, commons.py:103-110; generic time-as-M only)
   int epi_smem;                // channels-as-M epilogue: 1 = transpose through shared memory (ldmatrix/stmatrix; default),

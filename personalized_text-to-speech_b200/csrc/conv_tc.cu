@@ -511,7 +511,7 @@ template <int BN, int KC, bool SPECIALISED>
 static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
   const ConvEpilogue& e = pl.p.ep;
   if constexpr (SPECIALISED) {
-    const bool simple = e.bias_b == nullptr && e.rowmask == nullptr && !e.gate &&
+    const bool simple = e.bias_b == nullptr && e.rowmask == nullptr && !e.gate && !e.split_col &&
                         (e.mrf_mode == 0 || (e.mrf_mode == 3 && e.mrf == nullptr));
     if (simple && e.mrf_mode == 0 && e.nres == 0) return launch_one<BN, KC, 1>(pl, stream);
     if (simple && e.mrf_mode == 0 && e.nres == 1) return launch_one<BN, KC, 2>(pl, stream);
@@ -643,7 +643,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
 
 int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep) {
   VD_CHECK(ep.nres >= 0 && ep.nres <= kMaxSeg - 1, "conv_tc: at most 3 residual tensors");
-  if (pl.p.rho_d > 1) return 0;  // dilated folded view: residual rows are strided, no L2 prefetch maps
+  if (pl.p.rho_d > 1 || ep.split_col) return 0;  // strided / split residual rows: no L2 prefetch maps
   for (int i = 0; i < ep.nres; ++i) {
     if (pl.res_bound[i] != ep.res[i]) {
       if (encode_3d(&pl.tm.r[i], ep.res[i], pl.p.g.n_total, pl.p.g.L, pl.p.g.B, pl.bn < 64 ? pl.bn : 64, 64, false))
@@ -658,9 +658,10 @@ int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) 
   pl.p.ep = ep;
   pl.p.ep.epi_smem = pl.epi_smem ? 1 : 0;
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
-  pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch && pl.p.rho_d == 1) ? 1 : 0;
+  pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch && pl.p.rho_d == 1 && !ep.split_col) ? 1 : 0;
   if (pl.swap) {
-    VD_CHECK(ep.rowmask == nullptr && !ep.gate, "conv_tc: row mask / gate need a time-as-M plan (allow_swap = false)");
+    VD_CHECK(ep.rowmask == nullptr && !ep.gate && !ep.split_col,
+             "conv_tc: row mask / gate / split epilogue need a time-as-M plan (allow_swap = false)");
     VD_CHECK(ep.mrf == nullptr, "conv_tc: the channels-as-M variant has no fp32 MRF accumulator path");
     return launch_swapped(pl, stream);
   }

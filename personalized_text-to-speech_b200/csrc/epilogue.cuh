@@ -55,6 +55,10 @@ __device__ __forceinline__ bool epi_has_res(const ConvEpilogue& ep, int i) {
 template <int EPI>
 __device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, const EpiItem& it, int n_total, int lane,
                                                 EpiLoads& ld) {
+  if (EPI == 0 && ep.split_col) {   // split launch: only the low columns carry a residual, with their own row stride
+    if (it.n >= ep.split_col) return;
+    n_total = ep.split_col;
+  }
 #pragma unroll
   for (int i = 0; i < kMaxRes; ++i) {
     if (epi_has_res<EPI>(ep, i)) {
@@ -90,9 +94,10 @@ __device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const flo
       v[j + 0] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
     }
   }
+  const bool split_hi = EPI == 0 && ep.split_col && it.n >= ep.split_col;
 #pragma unroll
   for (int i = 0; i < kMaxRes; ++i) {
-    if (epi_has_res<EPI>(ep, i)) {
+    if (epi_has_res<EPI>(ep, i) && !split_hi) {
       // coalesced registers -> scratch -> row-owner registers
 #pragma unroll
       for (int j = 0; j < 2; ++j)
@@ -113,6 +118,18 @@ __device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const flo
         }
       }
     }
+  }
+  if (EPI == 0 && ep.split_col) {
+    if (split_hi && ep.mrf_mode == 2 && lane < it.rows_valid) {
+      const float4* mp = reinterpret_cast<const float4*>(ep.mrf + (it.row0 + lane) * (n_total - ep.split_col) + it.n -
+                                                         ep.split_col);
+#pragma unroll
+      for (int j = 0; j < kIW / 4; ++j) {
+        const float4 m = mp[j];
+        v[4 * j] += m.x; v[4 * j + 1] += m.y; v[4 * j + 2] += m.z; v[4 * j + 3] += m.w;
+      }
+    }
+    return;
   }
   if (EPI == 0 && (ep.mrf_mode == 2 || (ep.mrf_mode == 3 && ep.mrf)) && lane < it.rows_valid) {  // fp32 fallback path
     const float4* mp = reinterpret_cast<const float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
@@ -147,7 +164,17 @@ __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scrat
       *reinterpret_cast<uint4*>(ep.out + (it.row0 + lane) * (n_total / 2) + it.n / 2) = ov;
     return;
   }
-  if (EPI == 0 && (ep.mrf_mode == 1 || ep.mrf_mode == 2)) {
+  if (EPI == 0 && ep.split_col) {
+    if (it.n >= ep.split_col) {   // skip half: fp32 accumulator
+      if (lane < it.rows_valid) {
+        float4* mp = reinterpret_cast<float4*>(ep.mrf + (it.row0 + lane) * (n_total - ep.split_col) + it.n - ep.split_col);
+#pragma unroll
+        for (int j = 0; j < kIW / 4; ++j) mp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      return;
+    }
+    n_total = ep.split_col;       // residual half: the ordinary bf16 store below, with its own row stride
+  } else if (EPI == 0 && (ep.mrf_mode == 1 || ep.mrf_mode == 2)) {
     if (lane < it.rows_valid) {
       float4* mp = reinterpret_cast<float4*>(ep.mrf + (it.row0 + lane) * n_total + it.n);
 #pragma unroll

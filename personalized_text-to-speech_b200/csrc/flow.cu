@@ -16,12 +16,11 @@
 //   per layer l  ACT = tanh(a) * sigmoid(b),  (a | b) = in_l(H) + bias + CB[l][b]        modules.py:157, commons.py:105-110
 //                (conv k, dilation rate^l; the gate runs in the conv's epilogue: in_l's output channels are packed
 //                interleaved, (a_j, b_j) in adjacent columns, so one thread holds both halves of a pair)
-//                H   = (W_res ACT + b_res + H) * mask        (not for the last layer)    modules.py:171-172
-//                S  += W_skip ACT + b_skip                   (fp32 accumulator)          modules.py:173-175
+//                RS  = res_skip_l(ACT): ONE launch with a split epilogue (ConvEpilogue::split_col) --
+//                H   = (RS[:, :Hc] + H) * mask               (bf16, not for the last layer)   modules.py:171-172
+//                S  += RS[:, Hc:]                            (fp32 accumulator)               modules.py:173-175
 //   post         M = (W_post bf16(S * mask) + b) * mask                (fp32)            modules.py:328
 //   couple       X[:, C/2:] = (X[:, C/2:] - M) * mask  (reverse)  |  M + X[:, C/2:] * mask (forward)   modules.py:335-343
-// res_skip_layers' rows [0, Hc) / [Hc, 2Hc) are packed as two separate 1x1 convs so that the fp32 accumulation of the
-// skip half and the bf16 residual update of the other half are plain epilogue modes of conv_tc.cu.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -138,7 +137,7 @@ struct FlowConv {             // one tensor-core convolution of the block
 };
 
 struct FlowLayer {            // one WN layer
-  FlowConv in, res, skip;     // res unused for the last layer
+  FlowConv in, rs;            // rs: res_skip_layers[l], 2*Hc outputs (Hc for the last layer: skip only)
   bool has_res = false;
 };
 
@@ -289,25 +288,22 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
         if (f->hp.gin_channels) e.bias_b = CB + (size_t)l * B * 2 * H;  // only used when g is given
         if (push(ly.in, Hb[cur], e)) return 1;
       }
-      if (ly.has_res) {
-        ConvEpilogue e{};
-        e.res[0] = Hb[cur];
-        e.nres = 1;
-        e.out = Hb[cur ^ 1];
-        if (push(ly.res, ACT, e)) return 1;
-        cur ^= 1;
-      }
       {
         ConvEpilogue e{};
         e.mrf = S;
-        if (l == nl - 1) {          // last layer: bf16(S + v) is post's operand
+        if (ly.has_res) {           // residual half -> next H (bf16), skip half -> S (fp32), one launch
+          e.split_col = H;
+          e.res[0] = Hb[cur];
+          e.nres = 1;
+          e.out = Hb[cur ^ 1];
+          e.mrf_mode = l == 0 ? 1 : 2;
+        } else {                    // last layer: bf16(S + v) is post's operand
           e.mrf_mode = 3;
           if (nl == 1) e.mrf = nullptr;
           e.out = OUTB;
-        } else {
-          e.mrf_mode = l == 0 ? 1 : 2;
         }
-        if (push(ly.skip, ACT, e)) return 1;
+        if (push(ly.rs, ACT, e)) return 1;
+        if (ly.has_res) cur ^= 1;
       }
     }
     {  // post: fp32 store of m
@@ -359,8 +355,7 @@ int vitsdec_flow_create(const vitsdec_flow_hparams* hp, int device, vitsdec_flow
       VD_CHECK((hp->kernel_size - 1) / 2 * dil < 4096, "flow: dilation too large");
       if (flow_conv_alloc(ly.in, H, 2 * H, hp->kernel_size, dil)) return 1;
       ly.has_res = l < nl - 1;
-      if (ly.has_res && flow_conv_alloc(ly.res, H, H, 1, 1)) return 1;
-      if (flow_conv_alloc(ly.skip, H, H, 1, 1)) return 1;
+      if (flow_conv_alloc(ly.rs, H, ly.has_res ? 2 * H : H, 1, 1)) return 1;
       dil *= hp->dilation_rate;
     }
     for (int l = 0; l < nl; ++l) f->names.push_back(p + "enc.in_layers." + std::to_string(l));
@@ -385,7 +380,7 @@ void vitsdec_flow_destroy(vitsdec_flow* f) {
   auto drop = [](FlowConv& c) { cudaFree(c.w); cudaFree(c.bias); };
   for (FlowCoupling& c : f->cpl) {
     drop(c.pre); drop(c.post);
-    for (FlowLayer& l : c.layers) { drop(l.in); drop(l.res); drop(l.skip); }
+    for (FlowLayer& l : c.layers) { drop(l.in); drop(l.rs); }
     cudaFree(c.cond_w); cudaFree(c.cond_b);
   }
   cudaFree(f->scale_scratch);
@@ -436,12 +431,9 @@ int vitsdec_flow_load_layer(vitsdec_flow* f, const char* name, const float* w, c
     const int rows = ly.has_res ? 2 * H : H;
     VD_CHECK(rows <= 8192, "flow: too many channels");
     if (launch_wn_scale(w, wg, f->scale_scratch, rows, H, st)) return 1;
-    if (ly.has_res) {  // rows [0, H) update the residual stream, rows [H, 2H) feed the skip sum (modules.py:170-173)
-      if (load_conv(ly.res, w, f->scale_scratch, bias)) return 1;
-      if (load_conv(ly.skip, w + (size_t)H * H, f->scale_scratch + H, bias + H)) return 1;
-    } else {
-      if (load_conv(ly.skip, w, f->scale_scratch, bias)) return 1;
-    }
+    // rows [0, H) update the residual stream, rows [H, 2H) feed the skip sum (modules.py:170-173): one conv, the
+    // epilogue splits at column H
+    if (load_conv(ly.rs, w, f->scale_scratch, bias)) return 1;
   } else if (rest == "enc.cond_layer" && gin > 0) {
     const int rows = nl * 2 * H;
     VD_CHECK(rows <= 8192, "flow: too many conditioning channels");
@@ -533,8 +525,7 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
       if (run(false)) return 1;                               // pre
       for (int l = 0; l < nl; ++l) {
         if (run(g != nullptr)) return 1;                      // in_layer (+ cond) with the gate in its epilogue
-        if (c.layers[l].has_res && run(false)) return 1;      // residual half
-        if (run(false)) return 1;                             // skip half
+        if (run(false)) return 1;                             // res_skip (split epilogue)
       }
       if (run(false)) return 1;                               // post -> M
       flow_couple_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, M, mask, rows, C, reverse ? 1 : 0);
