@@ -223,3 +223,34 @@ def test_time_folded_fused_pair_matches_torch(case):
     h = ops.conv1d_cl(x, w1, b1, dilation=d, out_slope=0.1)
     y2 = ops.conv1d_cl(h, w2, b2, dilation=1, res=x, res_gain=10.0, out_slope=0.1)
     assert rel_err(y, y2) < 1.5e-2
+
+
+def test_randomised_conv_shapes():
+    """Seeded sweep over the supported shape space (channels, taps, dilation, ragged lengths, residual on/off, plain and
+    time-folded forms): every case against torch on the same bf16 operands."""
+    import numpy as np
+    rs = np.random.RandomState(2024)
+    dev = torch.device("cuda:0")
+    n_fold = 0
+    for case in range(48):
+        ci = int(rs.choice([32, 64, 96, 128, 192, 256]))
+        co = ci if rs.rand() < 0.7 else int(rs.choice([32, 64, 128, 256]))
+        k = int(rs.choice([1, 3, 5, 7, 11]))
+        d = int(rs.choice([1, 1, 2, 3, 5]))
+        B = int(rs.randint(1, 4))
+        L = int(rs.randint(1, 700))
+        use_res = bool(rs.rand() < 0.5)
+        fold = ci == co and ci in (32, 64) and rs.rand() < 0.6
+        if fold and d == 1:
+            L = max(4, L // 4 * 4)          # the dilation-1 folded form needs whole folded rows
+        torch.manual_seed(case)
+        x = torch.randn(B, L, ci, device=dev).bfloat16()
+        w = torch.randn(co, ci, k, device=dev) / (ci * k) ** 0.5
+        b = torch.randn(co, device=dev) * 0.1
+        res = torch.randn(B, L, co, device=dev).bfloat16() if use_res else None
+        y = ops.conv1d_cl(x, w, b, dilation=d, res=res, res_gain=10.0, out_slope=0.1, impl=0, desc_mode=16 if fold else 0)
+        torch.cuda.synchronize()
+        err = rel_err(y, ref_conv(x, w, b, d, res, 10.0, 0.1))
+        assert torch.isfinite(y.float()).all() and err < REL_TOL, (case, B, L, ci, co, k, d, use_res, fold, err)
+        n_fold += int(fold)
+    assert n_fold >= 5
