@@ -522,6 +522,7 @@ static int launch_inst(const ConvTcPlan& pl, cudaStream_t stream) {
 
 int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* xs, const __nv_bfloat16* w,
                  int num_sms, int desc_mode, bool allow_swap) {
+  const int raw_desc_mode = desc_mode;
   const bool force_streaming = (desc_mode & 2) != 0;  // test knob: exercise the streamed-weights path everywhere
   pl->no_res_prefetch = (desc_mode & 4) != 0;        // experiment knob: skip the TMA L2 prefetch of residual tiles
   const bool force_no_swap = (desc_mode & 8) != 0;   // test knob: keep wide layers on the time-as-M form
@@ -547,6 +548,13 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   int bn = 32;
   for (int c : {256, 128, 64}) {
     if (g.n_total % c == 0) { bn = c; break; }
+  }
+  // Small problems (the flow's frame-rate convs): with 256 x 128 tiles a launch may have barely more tiles than SMs (162
+  // on 148 = two rounds, the second almost empty); halving the tile width evens the rounds out.
+  if (!allow_swap && bn == 128) {
+    const long tiles128 = (long)g.B * ((g.L + 255) / 256) * (g.n_total / 128);
+    const long r128 = (tiles128 + num_sms - 1) / num_sms, r64 = (2 * tiles128 + num_sms - 1) / num_sms;
+    if (tiles128 <= 4L * num_sms && r64 < 2 * r128 && !(raw_desc_mode & 256)) bn = 64;
   }
   // Wide layers whose weights do not stay resident run channels-as-M (128 channels x 256 time rows): at N=128 the
   // time-as-M form is bound by shared-memory operand bandwidth, at N=256 by L2 weight streaming.
