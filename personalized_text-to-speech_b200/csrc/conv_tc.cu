@@ -51,6 +51,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
   using C = TcCfg<BN, KC>;
   constexpr int NACC = C::NACC, ROWB = C::ROWB, B_STAGE = C::B_STAGE, ACC_COLS = C::ACC_COLS;
   constexpr int BM = 128 * NACC;
+  // channels-as-M tiles cover swap_rows (256, 128 or 64) time rows: small decodes use narrower tiles to occupy more SMs
+  const int BMr = SWAP ? p.swap_rows : BM;
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern is a function of the shared-memory address bits
@@ -115,13 +117,13 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         p.div_m.divmod(mb, bq, mt);
         p.div_rho.divmod(bq, bu, rho);
         const int b = bu;
-        const int t0 = mt * BM;
+        const int t0 = mt * BMr;
         const int n0 = nt * BN;
         if (p.res_prefetch) {
           // the residual tiles this tile's epilogue will read: start them towards L2 now (the producer runs NA
           // activation stages ahead of the MMAs, so this is early enough to hide the DRAM latency)
           for (int i = 0; i < p.ep.nres; ++i)
-            for (int r = 0; r < BM; r += 64)
+            for (int r = 0; r < BMr; r += 64)
               for (int c = 0; c < BN; c += C::RBOXC) tma_prefetch_3d(&tm.r[i], n0 + c, t0 + r, b);
         }
         int tap0 = 0;
@@ -163,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     // SWAP: D[channel, time] = W[channel, ci] * X[time, ci]^T -- the 128 output channels are the MMA's M, the 256 time
     // rows its N, so one instruction reads 4 KB of weights + 8 KB of activations per 128 cycles (96 B/cycle of
     // shared-memory operand traffic) instead of 2 x (4 KB + 4 KB) per 2 x 64 cycles (128 B/cycle, the smem limit).
-    constexpr uint32_t idesc = umma_idesc_f16(SWAP ? 256 : BN, false);
+    const uint32_t idesc = umma_idesc_f16(SWAP ? p.swap_rows : BN, false);
     constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
     const uint32_t leader = elect_one();
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), b_lo0 = umma_desc_lo(smem_u32(smemB));
@@ -203,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
           // that one row of the staged tile before the MMAs read it.
           const int rem = p.L_real - (int)rho_ - p.rho_d * kc;  // K-chunk == phase of the row's samples
           const int nlim = rem > 0 ? (int)p.div_dr.quot(rem + p.rho_d * p.r_fold - 1) : 0;
-          const int idx = p.g.L - 1 - ((int)mt_ * BM + p.seg_halo_lo[sg]);
+          const int idx = p.g.L - 1 - ((int)mt_ * BMr + p.seg_halo_lo[sg]);
           if (nlim < p.g.L && idx >= 0 && idx < p.seg_nboxes[sg] * 64) {
             if (lane < ROWB / 16)
               *reinterpret_cast<uint4*>(smemA + sa * p.a_stage_bytes + idx * ROWB + lane * 16) = make_uint4(0, 0, 0, 0);
@@ -263,8 +265,9 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     const FastDiv div_rho = p.div_rho, div_dr = p.div_dr;
     const int rho_d = p.rho_d, c_shift = p.c_shift, r_fold = p.r_fold, L_real = p.L_real, rowstride = p.rowstride;
     const long bstride = p.bstride;
-    constexpr int CHUNKS = BN / kIW, NITEMS = SWAP ? 256 / kIW : NACC * CHUNKS, NW = kEpiWarps / 4;
-    static_assert(NITEMS >= NW, "every epilogue warp needs at least one item per tile");
+    constexpr int CHUNKS = BN / kIW, NW = kEpiWarps / 4;
+    static_assert(NACC * CHUNKS >= NW, "every epilogue warp needs at least one item per tile");
+    const int NITEMS = SWAP ? p.swap_rows / kIW : NACC * CHUNKS;   // swap_rows >= 64: at least one item per warp
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
     uint8_t* scratch = reinterpret_cast<uint8_t*>(sbias) + 8192 + (warp - 2) * 1024;
@@ -279,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       div_m.divmod(mb, bq, mt);
       e.b = bq;
       if constexpr (SWAP) {
-        const int t = mt * BM + it * kIW;       // item = 16 time rows (TMEM columns) x this warp's 32 channels
+        const int t = mt * BMr + it * kIW;      // item = 16 time rows (TMEM columns) x this warp's 32 channels
         e.n = nt * BN + q * 32;
         // utterance x sub-sequence -> (utterance, rho); the warp's 32 columns are channels [c, c+32) of phase phi
         uint32_t bu, rho;
@@ -563,9 +566,17 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   pl->swap = want_swap;
   VD_CHECK(rho_d == 1 || want_swap, "conv_tc: a dilated folded view runs channels-as-M only");
   const int nacc = bn >= 256 ? 1 : 2;
-  const int bm = 128 * nacc;
+  int bm = 128 * nacc;
+  if (want_swap) {
+    // Small decodes: a 2 s utterance has 6-44 tiles of 256 rows per launch in stages 0-1 for 148 SMs (x3 with the
+    // MRF branches running concurrently).  Narrower tiles (N = 128 / 64 per MMA) are less efficient per MAC but put
+    // the launch on more SMs; large batches keep 256 rows.
+    while (bm > 64 && 3L * g.B * rho_d * ((g.L + bm - 1) / bm) * (g.n_total / bn) <= num_sms) bm /= 2;
+    if (raw_desc_mode & 512) bm = 256;   // experiment knob: always 256-row tiles
+  }
   ConvTcParams& p = pl->p;
   p.g = g;
+  p.swap_rows = bm;
   p.a_stage_bytes = 0;
   int tap0 = 0;
   for (int sg = 0; sg < g.nseg; ++sg) {

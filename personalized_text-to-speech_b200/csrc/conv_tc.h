@@ -42,6 +42,7 @@ struct ConvTcParams {
   FastDiv div_n, div_m;       // tile -> (n-tile, m-block) -> (utterance x sub-sequence, m-tile)
   FastDiv div_rho;            // (utterance x sub-sequence) -> (utterance, rho)
   FastDiv div_dr;             // division by rho_d * r (rows of a dilated folded view)
+  int swap_rows;              // time rows per channels-as-M tile (256, or 128 / 64 for small decodes)
   int rho_d;                  // sub-sequences per utterance (1 = ordinary view), see ConvGeom
   int c_shift;                // log2(channels per time sample) of a dilated folded view (5 otherwise)
   int r_fold;                 // time samples per folded row
