@@ -97,7 +97,8 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
  *          "desc_mode" = debug knob of the UMMA descriptor (0 is the correct setting);
  *          "debug_keep" = 1 keep named intermediates for vitsdec_debug_read; "profile" = 1 see below;
  *          "fuse_pairs" = 0 run every ResBlock conv as its own launch (default 1: fused pairs where they fit);
- *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph);
+ *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph from the
+ *          plan's third use on; 2: capture at the first use);
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
  *          "pairf" = 0 keeps fused pairs on conv_pair.cu (default 1: time-folded conv_pairf.cu where it is faster);
  *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph). */

@@ -642,7 +642,13 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   }
   pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + 8192 + 16384;
   for (int sg = 0; sg < kMaxSeg; ++sg) {
-    const void* x = xs[sg < g.nseg ? sg : 0];
+    if (sg >= g.nseg) {   // unused segments: valid placeholders without another driver call (an encode costs ~5 us)
+      pl->tm.a[sg] = pl->tm.a[0];
+      pl->tm.r[sg] = pl->tm.r[0];
+      pl->res_bound[sg] = nullptr;
+      continue;
+    }
+    const void* x = xs[sg];
     if (rho_d > 1) {
       // [C][rho][phase][row][utterance]: sample t = rho_d*(r*row + phase) + rho
       if (encode_act(&pl->tm.a[sg], x, kc, rho_d, g.c_real, p.r_fold, (uint64_t)rho_d * g.c_real, g.L,

@@ -193,6 +193,10 @@ struct Plan {
   // with this plan); index 0: no speaker conditioning, 1: conv_pre adds the per-utterance cond bias
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   bool graph_failed = false;
+  // Capturing + instantiating the graph costs ~12 ms (a batch-1 decode takes 0.5 ms): a plan is replayed as a graph
+  // only from its third use on, so a serving loop whose shape changes every call (tools/shape_churn.py: 12.1 ms per
+  // new shape with eager capture, 1.3 ms with plain launches) never pays for graphs it will not reuse.
+  int uses = 0;
   // Concurrent MRF branches: small decodes (a 2 s utterance has 12-170 tiles per launch for 148 SMs) are bound by
   // launch latency and under-filled kernels; the three branches of a stage are independent, so under the CUDA graph
   // they run on forked streams: 0.84 -> 0.53 ms at 173 frames, 1.19 -> 0.96 ms at 862, neutral to -1.5 % at 16 x 862
@@ -877,7 +881,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
       plan = std::make_shared<Plan>();
       if (build_plan(d, *plan, B, T, static_cast<uint8_t*>(ws))) return 1;
       d->plans.emplace_front(key, plan);
-      if (d->plans.size() > 16) d->plans.pop_back();
+      if (d->plans.size() > 64) d->plans.pop_back();
     }
     d->last_plan = plan;
   }
@@ -935,7 +939,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     return 0;
   };
   bool launched = false;
-  if (d->use_graph && !d->debug_keep && !plan->graph_failed) {
+  if (d->use_graph && !d->debug_keep && !plan->graph_failed && (++plan->uses >= 3 || d->use_graph == 2)) {
     // one graph launch instead of ~60 kernel launches: what makes a 2 s / batch-1 decode launch-bound otherwise
     std::lock_guard<std::mutex> lock(d->mu);
     cudaGraphExec_t& exec = plan->graph_exec[g ? 1 : 0];
@@ -1027,7 +1031,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "desc_mode")) d->desc_mode = value;
   else if (!strcmp(key, "debug_keep")) d->debug_keep = value ? 1 : 0;
   else if (!strcmp(key, "fuse_pairs")) d->fuse_pairs = value ? 1 : 0;
-  else if (!strcmp(key, "graph")) d->use_graph = value ? 1 : 0;
+  else if (!strcmp(key, "graph")) d->use_graph = value < 0 ? 0 : (value > 2 ? 2 : value);  // 2: capture on first use
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "par")) d->par = value ? 1 : 0;

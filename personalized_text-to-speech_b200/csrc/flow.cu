@@ -189,6 +189,7 @@ struct FlowPlan {            // per (B, T, workspace): tensor maps of every conv
   // pointers); index = reverse * 2 + has_g
   cudaGraphExec_t graph_exec[4] = {nullptr, nullptr, nullptr, nullptr};
   bool graph_failed = false;
+  int uses = 0;   // the graph is captured at the third use of a plan (capture + instantiate ~10 ms, see decoder.cu Plan)
 };
 
 static size_t fl_align(size_t v) { return (v + 1023) / 1024 * 1024; }
@@ -483,7 +484,7 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
       plan = std::make_shared<FlowPlan>();
       if (flow_build_plan(f, *plan, B, T, base)) return 1;
       f->plans.emplace_front(key, plan);
-      if (f->plans.size() > 8) f->plans.pop_back();
+      if (f->plans.size() > 32) f->plans.pop_back();
     }
   }
   const int C = f->hp.channels, H = f->hp.hidden_channels, nl = f->hp.n_layers, nf = f->hp.n_flows;
@@ -534,7 +535,7 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
     return 0;
   };
   bool launched = false;
-  if (!plan->graph_failed) {
+  if (!plan->graph_failed && ++plan->uses >= 3) {
     std::lock_guard<std::mutex> lock(f->mu);
     cudaGraphExec_t& exec = plan->graph_exec[(reverse ? 2 : 0) + (g ? 1 : 0)];
     if (!exec) {
