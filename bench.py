@@ -284,6 +284,20 @@ def main():
         barrier()
         lat_ms = max_over_ranks(e0.elapsed_time(e1)) / 50
 
+        # option "fp16" (fp16 instead of bf16 operands / stored activations; same kernels, same FLOPs): a short timed
+        # loop as an extra key.  The headline above is the bf16 mode BASELINE.json names.
+        G.set_option("fp16", 1)
+        for _ in range(4):
+            G(z, g)
+        barrier()
+        e0.record()
+        for _ in range(5):
+            G(z, g)
+        e1.record()
+        barrier()
+        fp16_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
+        G.set_option("fp16", 0)
+
         gather_ms = None
         if world > 1:  # the optional final waveform gather (north_star): timed separately, not on the data path
             full = torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev)
@@ -327,6 +341,7 @@ def main():
     }
     line["flow_reverse_ms_per_step"] = flow_ms
     line["latency_b1_2s_ms"] = lat_ms
+    line["fp16_mode_ms_per_step"] = fp16_ms
     if gather_ms is not None:
         line["waveform_gather_ms"] = gather_ms
     if rank == 0:

@@ -101,7 +101,11 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
  *          plan's third use on; 2: capture at the first use);
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
  *          "pairf" = 0 keeps fused pairs on conv_pair.cu (default 1: time-folded conv_pairf.cu where it is faster);
- *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph). */
+ *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph);
+ *          "fp16" = 1 packs weights and stores activations as IEEE fp16 instead of bf16 (default 0).  Same tensor-core
+ *          rate (tcgen05 kind::f16), fp32 accumulation, 10 instead of 7 stored mantissa bits; stored activations saturate
+ *          at +-65504.  Changing it invalidates the loaded weights: every vitsdec_load_layer must be repeated before the
+ *          next decode (vitsdec_decode fails with "no weights loaded" otherwise). */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
 
@@ -126,7 +130,8 @@ VITSDEC_API int vitsdec_debug_set_trace(void* trace_dev);
 /* Single fused convolution on channels-last bf16 activations (per-kernel parity tests):
  *   y[b,t,co] = lrelu( bias[co] + sum_j sum_ci w[co,ci,j] * x[b, t + (j-(k-1)/2)*dilation, ci] (+ res), out_slope )
  *   x_dev / res_dev / y_dev: bf16 [batch, length, channels]; w_dev fp32 [c_out, c_in, k]; bias fp32 [c_out].
- *   res (optional) is stored post-leaky-relu with slope 1/res_gain.  impl: 0 tcgen05, 1 CUDA cores. */
+ *   res (optional) is stored post-leaky-relu with slope 1/res_gain.  impl: 0 tcgen05, 1 CUDA cores.
+ *   desc_mode bit 1024: x / res / y are fp16 instead of bf16 (the decoder's "fp16" option); other bits: test knobs. */
 VITSDEC_API int vitsdec_op_conv1d(int device, const void* x_dev, const float* w_dev, const float* bias_dev, const void* res_dev,
                       float res_gain, float out_slope, void* y_dev, int batch, int length, int c_in, int c_out,
                       int k, int dilation, int impl, int desc_mode, void* stream);
@@ -176,6 +181,9 @@ VITSDEC_API const char* vitsdec_flow_layer_name(const vitsdec_flow* flow, int in
  * weight norm, modules.py:318-320) and bias.  Weight norm (dim 0) is folded here, once. */
 VITSDEC_API int vitsdec_flow_load_layer(vitsdec_flow* flow, const char* name, const float* w_dev, const float* wg_dev,
                                         const float* bias_dev, void* stream);
+/* Options: "fp16" = 1 conv operands and stored activations are fp16 instead of bf16 (as the decoder's option; the latent
+ * itself stays fp32 either way).  Changing it invalidates the loaded weights: load every layer again. */
+VITSDEC_API int vitsdec_flow_set_option(vitsdec_flow* flow, const char* key, int value);
 VITSDEC_API size_t vitsdec_flow_workspace_bytes(const vitsdec_flow* flow, int batch, int frames);
 /* x_dev: fp32 [batch, channels, frames] with element strides (x_stride_b, x_stride_c, 1); x_mask_dev: fp32
  * [batch, frames] (the reference's x_mask [B,1,T], binary: commons.sequence_mask) or NULL = all ones; g_dev: fp32

@@ -71,6 +71,7 @@ SIGNATURES = {
     "vitsdec_flow_num_layers": (_i, [_vp]),
     "vitsdec_flow_layer_name": (_cp, [_vp, _i]),
     "vitsdec_flow_load_layer": (_i, [_vp, _cp, _vp, _vp, _vp, _vp]),
+    "vitsdec_flow_set_option": (_i, [_vp, _cp, _i]),
     "vitsdec_flow_workspace_bytes": (_sz, [_vp, _i, _i]),
     "vitsdec_flow_apply": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "vitsdec_op_conv1d": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t swz_row(int row) {  // chunk XOR term of the
   return ROWB == 128 ? (row & 7) : ((row >> 1) & 3);
 }
 
-template <int CH, int KC, int NACC>
+template <int CH, int KC, int NACC, bool F16>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ PairParams p) {
@@ -122,7 +122,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform; elected lane issues)
-    constexpr uint32_t idesc = umma_idesc_f16(CH, false);
+    constexpr uint32_t idesc = umma_idesc_f16(CH, F16);
     constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
     const uint32_t leader = elect_one();
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), w_lo0 = umma_desc_lo(smem_u32(smemW));
@@ -223,7 +223,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint4 o[2];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o[h2]);
+          uint32_t* o2 = reinterpret_cast<uint32_t*>(&o[h2]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = h2 * 8 + e * 2;
@@ -232,7 +232,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v1 = __uint_as_float(a[j + 1]) + ((j & 3) == 0 ? bq.y : bq.w);
             v0 = inside ? fmaxf(v0, v0 * slope) : 0.f;
             v1 = inside ? fmaxf(v1, v1 * slope) : 0.f;
-            o2[e] = __floats2bfloat162_rn(v0, v1);
+            o2[e] = pack_act2<F16>(v0, v1);
           }
         }
         if (!h_free) {  // the c2 that last read this h buffer must have retired before it is overwritten
@@ -283,17 +283,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rx[h2]);
+          const uint32_t* r2 = reinterpret_cast<const uint32_t*>(&rx[h2]);
           uint4 ov;
-          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+          uint32_t* o2 = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = h2 * 8 + e * 2;
             const float4 bq = bv[j >> 2];
-            const float2 xr = __bfloat1622float2(r2[e]);
+            const float2 xr = unpack_act2<F16>(r2[e]);
             float v0 = __uint_as_float(a[j]) + ((j & 3) == 0 ? bq.x : bq.z) + (xr.x >= 0.f ? xr.x : xr.x * res_gain);
             float v1 = __uint_as_float(a[j + 1]) + ((j & 3) == 0 ? bq.y : bq.w) + (xr.y >= 0.f ? xr.y : xr.y * res_gain);
-            o2[e] = __floats2bfloat162_rn(fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope));
+            o2[e] = pack_act2<F16>(fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope));
           }
           *reinterpret_cast<uint4*>(scratch + lane * 32 + ((h2 ^ ((lane >> 2) & 1)) << 4)) = ov;
         }
@@ -387,21 +387,27 @@ int plan_conv_pair(PairPlan* pl, int B, int L, int channels, int k, int dil, con
   return 0;
 }
 
-template <int CH, int NACC>
-static int launch_pair_inst(const PairPlan& pl, cudaStream_t stream) {
+template <int CH, int NACC, bool F16>
+static int launch_pair_typed(const PairPlan& pl, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CUDA(cudaFuncSetAttribute(conv_pair_kernel<CH, CH, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VD_CUDA(cudaFuncSetAttribute(conv_pair_kernel<CH, CH, NACC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024));
     attr_set = true;
   }
-  conv_pair_kernel<CH, CH, NACC><<<pl.grid, kPairThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
+  conv_pair_kernel<CH, CH, NACC, F16><<<pl.grid, kPairThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
 
+template <int CH, int NACC>
+static int launch_pair_inst(const PairPlan& pl, cudaStream_t stream) {
+  return pl.p.f16 ? launch_pair_typed<CH, NACC, true>(pl, stream) : launch_pair_typed<CH, NACC, false>(pl, stream);
+}
+
 int launch_conv_pair(PairPlan& pl, const float* bias1, const float* bias2, float slope, __nv_bfloat16* out,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int f16) {
+  pl.p.f16 = f16;
   pl.p.bias1 = bias1;
   pl.p.bias2 = bias2;
   pl.p.slope = slope;

@@ -23,6 +23,7 @@ struct PairParams {
   float slope, res_gain;
   __nv_bfloat16* out;
   unsigned long long* trace;
+  int f16;               // 1: fp16 storage instead of bf16 (ConvEpilogue::f16)
 };
 
 struct PairPlan {
@@ -40,6 +41,6 @@ bool pair_supported(int channels, int k, int dil);
 int plan_conv_pair(PairPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
                    const __nv_bfloat16* w_pair, int num_sms);
 int launch_conv_pair(PairPlan& pl, const float* bias1, const float* bias2, float slope, __nv_bfloat16* out,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int f16 = 0);
 
 }  // namespace vd

@@ -35,7 +35,7 @@ constexpr int kPfThreads = 96 + 32 * kPfEpiWarps;  // warp 0: weight producer, 1
 // K-chunks are always 64 virtual channels = 128-byte rows (SWIZZLE_128B): with 64-byte rows (one 32-channel phase
 // per chunk) the 32-byte K=16 slices of 8 consecutive rows fall on the same banks twice and every MMA ran at half
 // rate (320 vs 160 cycles at N=256, profiles/r01_trace_pairf.txt).  For C = 32 a chunk is two time phases.
-template <int CH>
+template <int CH, bool F16>
 __global__ void __launch_bounds__(kPfThreads, 1)
 conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ PairFParams p) {
@@ -142,7 +142,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform; elected lane issues)
-    const uint32_t idesc1 = umma_idesc_f16(p.N1, false), idesc2 = umma_idesc_f16(p.WO, false);
+    const uint32_t idesc1 = umma_idesc_f16(p.N1, F16), idesc2 = umma_idesc_f16(p.WO, F16);
     constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
     const uint32_t leader = elect_one();
     const uint32_t x_lo0 = umma_desc_lo(smem_u32(XS)), h_lo0 = umma_desc_lo(smem_u32(HS));
@@ -335,8 +335,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             float v1 = __uint_as_float(a[frag_idx(m, cg, 1)]) + b1f[m];
             v0 = inside[cg][0] ? fmaxf(v0, v0 * slope) : 0.f;
             v1 = inside[cg][1] ? fmaxf(v1, v1 * slope) : 0.f;
-            const __nv_bfloat162 o = __floats2bfloat162_rn(v0, v1);
-            pk[m] = *reinterpret_cast<const uint32_t*>(&o);
+            pk[m] = pack_act2<F16>(v0, v1);
           }
           stmatrix_x4_trans(haddr[cg], pk[0], pk[1], pk[2], pk[3]);
         }
@@ -357,7 +356,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         __syncwarp();
         tmem_ld_frag(tmem_base + ((uint32_t)(q * 32) << 16) + cur.tcol, acc);
         tmem_ld_wait();
-        epiT_accumulate<2>(ep, b2f, scratch, cur, 128, lane, res_gain, acc, ld, v);
+        epiT_accumulate<2, F16>(ep, b2f, scratch, cur, 128, lane, res_gain, acc, ld, v);
         const bool last = it + 4 >= n_oitems;
         if (last) {  // accumulator fully read by this warp: hand D2 back before the stores
           tc_fence_before();
@@ -369,7 +368,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           ocoords(it + 4, cur);
           epiT_issue_loads<2>(ep, cur, 128, lane, ld);
         }
-        epiT_store<2>(ep, scratch, done, 128, lane, slope, 1.f, v);
+        epiT_store<2, F16>(ep, scratch, done, 128, lane, slope, 1.f, v);
       }
       if (tr) p.trace[i * 12 + 7] = clock64();
       if (sub >= n_oitems) {  // a warp without output items still owes its arrival
@@ -484,20 +483,26 @@ int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, c
   return 0;
 }
 
-template <int CH>
-static int launch_pairf_inst(const PairFPlan& pl, cudaStream_t stream) {
+template <int CH, bool F16>
+static int launch_pairf_typed(const PairFPlan& pl, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CUDA(cudaFuncSetAttribute(conv_pairf_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VD_CUDA(cudaFuncSetAttribute(conv_pairf_kernel<CH, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_pairf_kernel<CH><<<pl.grid, kPfThreads, pl.smem, stream>>>(pl.tmX, pl.tmW, pl.p);
+  conv_pairf_kernel<CH, F16><<<pl.grid, kPfThreads, pl.smem, stream>>>(pl.tmX, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
 
+template <int CH>
+static int launch_pairf_inst(const PairFPlan& pl, cudaStream_t stream) {
+  return pl.p.f16 ? launch_pairf_typed<CH, true>(pl, stream) : launch_pairf_typed<CH, false>(pl, stream);
+}
+
 int launch_conv_pairf(PairFPlan& pl, const float* bias1, const float* bias2, float slope, __nv_bfloat16* out,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int f16) {
+  pl.p.f16 = f16;
   pl.p.bias1 = bias1;
   pl.p.bias2 = bias2;
   pl.p.slope = slope;

@@ -28,6 +28,7 @@ struct PairFParams {
   const __nv_bfloat16* x;
   __nv_bfloat16* out;
   unsigned long long* trace;  // debug (VITSDEC_TRACE=1 builds): per-tile clock64 stamps of CTA 0, [tile][12]
+  int f16;               // 1: fp16 storage instead of bf16 (ConvEpilogue::f16)
 };
 
 struct PairFPlan {
@@ -46,7 +47,7 @@ bool pairf_preferred(int channels, int k, int dil);
 int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
                     const __nv_bfloat16* w_fold, int num_sms);
 int launch_conv_pairf(PairFPlan& pl, const float* bias1, const float* bias2, float slope, __nv_bfloat16* out,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int f16 = 0);
 
 int encode_tmap_act(CUtensorMap* m, const void* base, uint32_t kc, uint64_t d1, uint64_t s1, uint64_t d2, uint64_t s2,
                     uint64_t rows, uint64_t srow, uint64_t B, uint64_t sb, uint32_t box_rows, uint32_t box_d2 = 1);

@@ -74,6 +74,9 @@ struct ConvEpilogue {
                                // 0 = register transposes (movmatrix) and 4-byte global accesses (slower, kept as a knob)
   float* out_f32;              // mrf_mode 4: waveform [B][L * n_total / post_c]
   int post_c;                  // mrf_mode 4: real channels per time sample (n_total = r * post_c)
+  int f16;                     // 1: operands, residuals and the stored output are IEEE fp16 instead of bf16 (option
+                               // "fp16"): same tensor-core rate (kind::f16), 3 more mantissa bits per stored activation;
+                               // stores saturate at +-65504.  Pointers stay typed __nv_bfloat16 (opaque 16-bit storage).
 };
 
 }  // namespace vd

@@ -29,17 +29,17 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvGeom g, ConvEpilogue
     const uint4* wr = reinterpret_cast<const uint4*>(w + ((long)tap * g.n_total + n) * g.c_in);
     for (int c8 = 0; c8 < g.c_in / 8; ++c8) {
       const uint4 wv = __ldg(wr + c8);
-      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+      const uint32_t* w2 = reinterpret_cast<const uint32_t*>(&wv);
 #pragma unroll
       for (int r = 0; r < kSimtRows; ++r) {
         const int ti = t0 + r + g.tap_off[tap];
         if (ti < 0 || ti >= g.L) continue;
         const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + ((long)b * g.L + ti) * g.c_in) + c8);
-        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+        const uint32_t* x2 = reinterpret_cast<const uint32_t*>(&xv);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 wf = __bfloat1622float2(w2[q]);
-          const float2 xf = __bfloat1622float2(x2[q]);
+          const float2 wf = ep.f16 ? unpack_act2<true>(w2[q]) : unpack_act2<false>(w2[q]);
+          const float2 xf = ep.f16 ? unpack_act2<true>(x2[q]) : unpack_act2<false>(x2[q]);
           acc[r] = fmaf(wf.x, xf.x, acc[r]);
           acc[r] = fmaf(wf.y, xf.y, acc[r]);
         }

@@ -44,7 +44,7 @@ struct TcCfg {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
-template <int BN, int KC, int EPI, bool SWAP>
+template <int BN, int KC, int EPI, bool SWAP, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ ConvTcParams p) {
@@ -165,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     // SWAP: D[channel, time] = W[channel, ci] * X[time, ci]^T -- the 128 output channels are the MMA's M, the 256 time
     // rows its N, so one instruction reads 4 KB of weights + 8 KB of activations per 128 cycles (96 B/cycle of
     // shared-memory operand traffic) instead of 2 x (4 KB + 4 KB) per 2 x 64 cycles (128 B/cycle, the smem limit).
-    const uint32_t idesc = umma_idesc_f16(SWAP ? p.swap_rows : BN, false);
+    const uint32_t idesc = umma_idesc_f16(SWAP ? p.swap_rows : BN, F16);
     constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
     const uint32_t leader = elect_one();
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), b_lo0 = umma_desc_lo(smem_u32(smemB));
@@ -363,8 +363,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
               if (lane < 4 && col < cur.rows_valid) o[(long)col * r] = tanhf(x);
             }
         }
-      } else if constexpr (SWAP) epiT_accumulate<EPI>(ep, bias4, scratch, cur, n_total, lane, res_gain, acc, ld, v);
-      else epi_accumulate<EPI>(ep, bv, scratch, cur, n_total, lane, res_gain, acc, ld, v);
+      } else if constexpr (SWAP) epiT_accumulate<EPI, F16>(ep, bias4, scratch, cur, n_total, lane, res_gain, acc, ld, v);
+      else epi_accumulate<EPI, F16>(ep, bv, scratch, cur, n_total, lane, res_gain, acc, ld, v);
       if (tr) p.trace[itt * 12 + 6] = clock64();
       if (last) {  // accumulator fully read: hand the TMEM buffer back before the stores
         tc_fence_before();
@@ -383,8 +383,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       }
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 9] = clock64();
       if constexpr (EPI == 4) { (void)done; }
-      else if constexpr (SWAP) epiT_store<EPI>(ep, scratch, done, rowstride, lane, out_slope, mrf_scale, v);
-      else epi_store<EPI>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
+      else if constexpr (SWAP) epiT_store<EPI, F16>(ep, scratch, done, rowstride, lane, out_slope, mrf_scale, v);
+      else epi_store<EPI, F16>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 7] = clock64();
       tile = ntile; it = nit;
     }
@@ -479,17 +479,25 @@ int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, u
   return encode_3d(m, base, d0, d1, d2, b0, b1, swizzle);
 }
 
-template <int BN, int KC, int EPI, bool SWAP = false>
-static int launch_one(const ConvTcPlan& pl, cudaStream_t stream) {
+template <int BN, int KC, int EPI, bool SWAP, bool F16>
+static int launch_typed(const ConvTcPlan& pl, cudaStream_t stream) {
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
-    VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, EPI, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, EPI, SWAP, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KC, EPI, SWAP><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
+  conv_tc_kernel<BN, KC, EPI, SWAP, F16><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
+}
+
+// ConvEpilogue::f16 selects the fp16-storage instance of the same kernel (operand format bits of the instruction
+// descriptor and the epilogue's 16-bit conversions are compile-time)
+template <int BN, int KC, int EPI, bool SWAP = false>
+static int launch_one(const ConvTcPlan& pl, cudaStream_t stream) {
+  return pl.p.ep.f16 ? launch_typed<BN, KC, EPI, SWAP, true>(pl, stream)
+                     : launch_typed<BN, KC, EPI, SWAP, false>(pl, stream);
 }
 
 // channels-as-M variant (128 channels x 256 time rows per tile); never with the fp32 MRF fallback

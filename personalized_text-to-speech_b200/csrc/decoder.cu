@@ -231,6 +231,7 @@ struct vitsdec_decoder {
   int hop = 1;
   float* scale_scratch = nullptr;
   int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1, par = 1;
+  int fp16 = 0;  // option "fp16": weights and stored activations are IEEE fp16 instead of bf16 (ConvEpilogue::f16)
   cudaStream_t cstream = nullptr;  // capture-only stream (the caller's may be the legacy default stream)
   cudaStream_t bstream[VITSDEC_MAX_KERNELS] = {};  // capture-only streams of MRF branches 1.. (Plan::par)
   cudaEvent_t ev_fork = nullptr, ev_join[VITSDEC_MAX_KERNELS] = {};
@@ -398,6 +399,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     e.res_gain = 1.f / kSlope;
     e.out_slope = kSlope;
     e.mrf_scale = 1.f;
+    e.f16 = d->fp16;
     return e;
   };
 
@@ -538,6 +540,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     s.ep.mrf_mode = 4;
     s.ep.post_c = lp.c_in;
     s.ep.res_gain = s.ep.out_slope = s.ep.mrf_scale = 1.f;
+    s.ep.f16 = d->fp16;
     s.tc.p.g = g;
     if (plan_conv_tc(&s.tc, g, s.xs, lp.wfold, d->num_sms, d->desc_mode, true)) return 1;
     VD_CHECK(s.tc.swap, "conv_post: folded launch must be channels-as-M");
@@ -551,9 +554,10 @@ static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
   Layer& ly = d->layers[s.layer];
   if (s.is_pairf)
     return launch_conv_pairf(s.pairf, d->layers[ly.members[0]].bias, d->layers[ly.members[1]].bias, kSlope, s.ep.out,
-                             st);
+                             st, d->fp16);
   if (s.is_pair)
-    return launch_conv_pair(s.pair, d->layers[ly.members[0]].bias, d->layers[ly.members[1]].bias, kSlope, s.ep.out, st);
+    return launch_conv_pair(s.pair, d->layers[ly.members[0]].bias, d->layers[ly.members[1]].bias, kSlope, s.ep.out, st,
+                            d->fp16);
   if (d->impl == 0) return launch_conv_tc(s.tc, s.ep, st);
   return launch_conv_simt(s.tc.p.g, s.ep, s.xs, ly.w, st);
 }
@@ -787,45 +791,46 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
   if (l.kind == kConv) {
     VD_CHECK(l.c_out <= 4096, "too many channels");
     if (launch_wn_scale(w, wg, d->scale_scratch, l.c_out, l.c_in * l.k, st)) return 1;
-    if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st)) return 1;
+    if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st, 0, d->fp16)) return 1;
     if (launch_replicate_bias(bias, l.bias, l.c_out, 1, st)) return 1;
     if (l.fold_r) {
-      if (launch_pack_conv_fold(w, d->scale_scratch, l.wfold, l.c_in, l.c_out, l.k, l.fold_r, st)) return 1;
+      if (launch_pack_conv_fold(w, d->scale_scratch, l.wfold, l.c_in, l.c_out, l.k, l.fold_r, st, 0, d->fp16)) return 1;
       if (launch_replicate_bias(bias, l.bias_fold, l.c_out, l.fold_r, st)) return 1;
     }
     if (l.mrf_group >= 0) {
       Layer& v = d->layers[l.mrf_group];
       if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.mrf_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
-                           st))
+                           st, 0, d->fp16))
         return 1;
       if (v.fold_r &&
           launch_pack_conv_fold(w, d->scale_scratch,
                                 v.wfold + (size_t)l.mrf_ftap_base * v.fgeom.n_total * v.fgeom.c_in, l.c_in, l.c_out,
-                                l.k, v.fold_r, st))
+                                l.k, v.fold_r, st, 0, d->fp16))
         return 1;
       v.bias_dirty = true;
     }
     if (l.pair_group >= 0) {
       Layer& v = d->layers[l.pair_group];
       if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.pair_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
-                           st))
+                           st, 0, d->fp16))
         return 1;
       if (v.fold_r && launch_pack_conv_fold(w, d->scale_scratch, v.wfold + (size_t)l.pair_ftap_base * 128 * 128, l.c_in,
-                                            l.c_out, l.k, v.fold_r, st))
+                                            l.c_out, l.k, v.fold_r, st, 0, d->fp16))
         return 1;
     }
   } else if (l.kind == kConvT) {
     VD_CHECK(l.c_in <= 4096, "too many channels");
     if (launch_wn_scale(w, wg, d->scale_scratch, l.c_in, l.c_out * l.k, st)) return 1;  // dim 0 of [C_in,C_out,k]
     if (launch_pack_convT(w, d->scale_scratch, l.w, l.c_in, l.c_out, l.k, l.stride, (l.k - l.stride) / 2,
-                          l.geom.ntaps, l.geom.tap_off[0], st))
+                          l.geom.ntaps, l.geom.tap_off[0], st, d->fp16))
       return 1;
     if (launch_replicate_bias(bias, l.bias, l.c_out, l.stride, st)) return 1;
   } else {
     VD_CHECK(wg == nullptr, "conv_post / cond are not weight-normed in the reference (models.py:264,268)");
     VD_CUDA(cudaMemcpyAsync(l.wf32, w, (size_t)l.c_out * l.c_in * l.k * sizeof(float), cudaMemcpyDeviceToDevice, st));
     // two-term weights: virtual channel 0 = bf16(w), channel 1 = bf16(w - bf16(w))
-    if (l.kind == kPost && l.fold_r && launch_pack_conv_fold(w, nullptr, l.wfold, l.c_in, 1, l.k, l.fold_r, st, 1))
+    if (l.kind == kPost && l.fold_r && launch_pack_conv_fold(w, nullptr, l.wfold, l.c_in, 1, l.k, l.fold_r, st, 1,
+                                                                     d->fp16))
       return 1;
     if (l.kind == kCond) {
       VD_CHECK(bias != nullptr, "cond needs a bias");
@@ -887,7 +892,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   }
 
   int launches = 0;
-  if (launch_pack_z(z, zsb, zsc, plan->a0, B, d->hp.initial_channel, T, st)) return 1;
+  if (launch_pack_z(z, zsb, zsc, plan->a0, B, d->hp.initial_channel, T, st, d->fp16)) return 1;
   ++launches;
   if (g) {
     const Layer& lc = d->layers[d->l_cond];
@@ -977,7 +982,8 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     Step s = plan->post;
     s.ep.out_f32 = out;
     if (launch_conv_tc(s.tc, s.ep, st)) return 1;
-  } else if (launch_conv_post(plan->x_final, d->layers[d->l_post].wf32, out, B, plan->L_final, plan->C_final, st)) {
+  } else if (launch_conv_post(plan->x_final, d->layers[d->l_post].wf32, out, B, plan->L_final, plan->C_final, st,
+                              d->fp16)) {
     return 1;
   }
   if (d->profile) {  // the bracket covers every tcgen05 launch of the decode (conv_post included when it is one)
@@ -1035,6 +1041,17 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "par")) d->par = value ? 1 : 0;
+  else if (!strcmp(key, "fp16")) {
+    // the 16-bit storage format of weights AND activations: packed weights of the other format are useless, so every
+    // layer must be loaded again (the Python Generator re-folds by itself) and cached plans are dropped
+    const int v = value ? 1 : 0;
+    if (v != d->fp16) {
+      d->fp16 = v;
+      for (int i = 0; i < d->num_real_layers; ++i) d->layers[i].loaded = false;
+      d->plans.clear();
+      d->last_plan.reset();
+    }
+  }
   else if (!strcmp(key, "profile")) {
     d->profile = value ? 1 : 0;
     d->prof_conv_ms = 0.0;
@@ -1070,6 +1087,7 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   else if (!strcmp(key, "fold")) *value = d->fold;
   else if (!strcmp(key, "pairf")) *value = d->pairf;
   else if (!strcmp(key, "par")) *value = d->par;
+  else if (!strcmp(key, "fp16")) *value = d->fp16;
   else if (!strcmp(key, "hop")) *value = d->hop;
   else if (!strcmp(key, "num_sms")) *value = d->num_sms;
   else { set_error(std::string("unknown option ") + key); return 1; }
@@ -1096,7 +1114,7 @@ int vitsdec_debug_read(vitsdec_decoder* d, const char* name, float* out, size_t 
       if (channels) *channels = C;
       if (length) *length = L;
       return launch_unpack_debug(std::get<0>(e.second), std::get<3>(e.second), out, B, L, C,
-                                 static_cast<cudaStream_t>(stream));
+                                 static_cast<cudaStream_t>(stream), d->fp16);
     }
   }
   set_error(std::string("vitsdec_debug_read: unknown or not-kept tensor ") + name + " (set option debug_keep=1)");
@@ -1112,6 +1130,7 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
   VD_CUDA(cudaGetDeviceProperties(&prop, device));
   VD_CHECK(prop.major == 10, "vitsdec needs an sm_100 (B200) device");
   const bool fold = (desc_mode & 16) != 0;  // test knob: run the time-folded form of a narrow dilation-1 layer
+  const int f16 = (desc_mode & 1024) ? 1 : 0;  // x / res / y are IEEE fp16 instead of bf16 (option "fp16" of the decoder)
   if (fold) {
     fold_geom(l);
     VD_CHECK(impl == 0 && l.fold_r && (L % l.fold_r == 0 || l.dil > 1), "op_conv: layer has no time-folded form");
@@ -1122,15 +1141,15 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
   int rc = 0;
   if (l.kind == kConv) {
     rc = launch_wn_scale(w, nullptr, scale, l.c_out, l.c_in * l.k, st) ||
-         launch_pack_conv(w, scale, l.w, l.c_out, l.c_in, l.k, st) ||
+         launch_pack_conv(w, scale, l.w, l.c_out, l.c_in, l.k, st, 0, f16) ||
          launch_replicate_bias(bias, l.bias, l.c_out, 1, st);
     if (!rc && fold)
-      rc = launch_pack_conv_fold(w, scale, l.wfold, l.c_in, l.c_out, l.k, l.fold_r, st) ||
+      rc = launch_pack_conv_fold(w, scale, l.wfold, l.c_in, l.c_out, l.k, l.fold_r, st, 0, f16) ||
            launch_replicate_bias(bias, l.bias_fold, l.c_out, l.fold_r, st);
   } else {
     rc = launch_wn_scale(w, nullptr, scale, l.c_in, l.c_out * l.k, st) ||
          launch_pack_convT(w, scale, l.w, l.c_in, l.c_out, l.k, l.stride, (l.k - l.stride) / 2, l.geom.ntaps,
-                           l.geom.tap_off[0], st) ||
+                           l.geom.tap_off[0], st, f16) ||
          launch_replicate_bias(bias, l.bias, l.c_out, l.stride, st);
   }
   if (!rc) {
@@ -1148,6 +1167,7 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
     e.out_slope = out_slope;
     e.mrf_scale = 1.f;
     e.out = static_cast<bf16*>(y);
+    e.f16 = f16;
     if (impl == 0) {
       ConvTcPlan pl{};
       const bf16* xs[kMaxSeg] = {static_cast<const bf16*>(x), nullptr, nullptr, nullptr};

@@ -74,7 +74,7 @@ __device__ __forceinline__ void epi_issue_loads(const ConvEpilogue& ep, const Ep
 }
 
 // v = acc + bias (+ per-utterance bias) (+ residuals) (+ MRF accumulator)
-template <int EPI>
+template <int EPI, bool F16 = false>
 __device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const float4 (&bias)[4], uint8_t* scratch,
                                                const EpiItem& it, int n_total, int lane, float res_gain,
                                                const uint32_t (&acc)[kIW], const EpiLoads& ld, float (&v)[kIW]) {
@@ -109,10 +109,10 @@ __device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const flo
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&mine[q]);
+        const uint32_t* r2 = reinterpret_cast<const uint32_t*>(&mine[q]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 a = __bfloat1622float2(r2[e]);
+          const float2 a = unpack_act2<F16>(r2[e]);
           v[q * 8 + e * 2 + 0] += a.x >= 0.f ? a.x : a.x * res_gain;
           v[q * 8 + e * 2 + 1] += a.y >= 0.f ? a.y : a.y * res_gain;
         }
@@ -141,7 +141,7 @@ __device__ __forceinline__ void epi_accumulate(const ConvEpilogue& ep, const flo
   }
 }
 
-template <int EPI>
+template <int EPI, bool F16 = false>
 __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int n_total,
                                           int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
   if (EPI == 0 && ep.rowmask) {  // `* x_mask`: one mask value per (utterance, time) row
@@ -153,12 +153,12 @@ __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scrat
     // gated activation of the flow's WN: the layer's output channels were interleaved at pack time so that this
     // thread's 16 columns are 8 (tanh input, sigmoid input) pairs -> 8 bf16 outputs = one 16-byte store per row
     uint4 ov;
-    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+    uint32_t* o2 = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float g0 = tanhf(v[4 * e]) * (1.f / (1.f + __expf(-v[4 * e + 1])));
       const float g1 = tanhf(v[4 * e + 2]) * (1.f / (1.f + __expf(-v[4 * e + 3])));
-      o2[e] = __floats2bfloat162_rn(g0, g1);
+      o2[e] = pack_act2<F16>(g0, g1);
     }
     if (lane < it.rows_valid)
       *reinterpret_cast<uint4*>(ep.out + (it.row0 + lane) * (n_total / 2) + it.n / 2) = ov;
@@ -190,11 +190,11 @@ __device__ __forceinline__ void epi_store(const ConvEpilogue& ep, uint8_t* scrat
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     uint4 ov;
-    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+    uint32_t* o2 = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      o2[e] = __floats2bfloat162_rn(fmaxf(v[q * 8 + e * 2], v[q * 8 + e * 2] * out_slope),
-                                    fmaxf(v[q * 8 + e * 2 + 1], v[q * 8 + e * 2 + 1] * out_slope));  // slope in (0,1]
+      o2[e] = pack_act2<F16>(fmaxf(v[q * 8 + e * 2], v[q * 8 + e * 2] * out_slope),
+                             fmaxf(v[q * 8 + e * 2 + 1], v[q * 8 + e * 2 + 1] * out_slope));  // slope in (0,1]
     *reinterpret_cast<uint4*>(scratch + scr_off(lane, q)) = ov;
   }
   __syncwarp();
@@ -252,7 +252,7 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t (&a)[kIW])
   tmem_ld_16x256b_x2(taddr + (16u << 16), &a[8]);
 }
 
-template <int EPI>
+template <int EPI, bool F16 = false>
 __device__ __forceinline__ void epiT_accumulate(const ConvEpilogue& ep, const float (&bias)[4], uint8_t* scratch,
                                                 const EpiItem& it, int n_total, int lane, float res_gain,
                                                 const uint32_t (&acc)[kIW], const EpiLoads& ld, float (&v)[kIW]) {
@@ -291,10 +291,10 @@ __device__ __forceinline__ void epiT_accumulate(const ConvEpilogue& ep, const fl
         }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const float a0 = __uint_as_float(r[m] << 16), a1 = __uint_as_float(r[m] & 0xffff0000u);
+          const float2 a = unpack_act2<F16>(r[m]);
           // a-form -> residual stream: a >= 0 ? a : a * res_gain  ==  min(a, a * res_gain) for res_gain >= 1
-          v[frag_idx(m, cg, 0)] += fminf(a0, a0 * res_gain);
-          v[frag_idx(m, cg, 1)] += fminf(a1, a1 * res_gain);
+          v[frag_idx(m, cg, 0)] += fminf(a.x, a.x * res_gain);
+          v[frag_idx(m, cg, 1)] += fminf(a.y, a.y * res_gain);
         }
       }
       if (ep.epi_smem) __syncwarp();
@@ -302,7 +302,7 @@ __device__ __forceinline__ void epiT_accumulate(const ConvEpilogue& ep, const fl
   }
 }
 
-template <int EPI>
+template <int EPI, bool F16 = false>
 __device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scratch, const EpiItem& it, int rowstride,
                                            int lane, float out_slope, float mrf_scale, float (&v)[kIW]) {
   if (EPI == 3 || (EPI == 0 && ep.mrf_mode == 3)) {
@@ -316,8 +316,7 @@ __device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scra
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const float x0 = v[frag_idx(m, cg, 0)], x1 = v[frag_idx(m, cg, 1)];
-      const __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(x0, x0 * out_slope), fmaxf(x1, x1 * out_slope));  // slope in (0,1]
-      pk[m] = *reinterpret_cast<const uint32_t*>(&o);
+      pk[m] = pack_act2<F16>(fmaxf(x0, x0 * out_slope), fmaxf(x1, x1 * out_slope));  // slope in (0,1]
     }
     if (ep.epi_smem) {
       stmatrix_x4_trans(sbase + scrT_off(cg * 8 + (lane & 7), lane >> 3), pk[0], pk[1], pk[2], pk[3]);

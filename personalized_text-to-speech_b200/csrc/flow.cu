@@ -73,7 +73,8 @@ __global__ void flow_out_kernel(const float* __restrict__ x, float* __restrict__
 }
 
 // X <- flip(X) over channels when `flip` (modules.py:272), then X0 = bf16(X[:, :C/2]): the coupling layer's conv operand
-__global__ void flow_flip_split_kernel(float* __restrict__ x, bf16* __restrict__ x0, long rows, int C, int flip) {
+__global__ void flow_flip_split_kernel(float* __restrict__ x, bf16* __restrict__ x0, long rows, int C, int flip,
+                                       int f16) {
   const int half = C / 2;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < rows * half; i += (long)gridDim.x * blockDim.x) {
     const long r = i / half;
@@ -86,7 +87,7 @@ __global__ void flow_flip_split_kernel(float* __restrict__ x, bf16* __restrict__
       row[C - 1 - c] = lo;
       lo = hi;
     }
-    x0[i] = __float2bfloat16_rn(lo);
+    x0[i] = pack_act_rt(lo, f16);
   }
 }
 
@@ -207,6 +208,7 @@ struct vitsdec_flow {
   std::mutex mu;
   std::list<std::pair<std::tuple<int, int, const void*>, std::shared_ptr<FlowPlan>>> plans;
   cudaStream_t cstream = nullptr;   // capture-only stream
+  int fp16 = 0;                     // vitsdec_flow_set_option("fp16"): conv operands / stored activations are fp16
 };
 
 namespace vd {
@@ -265,6 +267,7 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
       e.bias = cv.bias;
       e.rowmask = mask;
       e.res_gain = 1.f;
+      e.f16 = f->fp16;
       if (e.out_slope == 0.f) e.out_slope = 1.f;
       if (e.mrf_scale == 0.f) e.mrf_scale = 1.f;
       const bf16* xs[kMaxSeg] = {x, nullptr, nullptr, nullptr};
@@ -410,7 +413,7 @@ int vitsdec_flow_load_layer(vitsdec_flow* f, const char* name, const float* w, c
   const std::string rest = n.substr(pos);
   const int H = f->hp.hidden_channels, nl = f->hp.n_layers, gin = f->hp.gin_channels;
   auto load_conv = [&](FlowConv& cv, const float* wsrc, const float* scale, const float* b) -> int {
-    return launch_pack_conv(wsrc, scale, cv.w, cv.c_out, cv.c_in, cv.k, st) ||
+    return launch_pack_conv(wsrc, scale, cv.w, cv.c_out, cv.c_in, cv.k, st, 0, f->fp16) ||
            launch_replicate_bias(b, cv.bias, cv.c_out, 1, st);
   };
   int li = -1;
@@ -425,7 +428,8 @@ int vitsdec_flow_load_layer(vitsdec_flow* f, const char* name, const float* w, c
     VD_CHECK(cv.c_out <= 8192, "flow: too many channels");
     if (launch_wn_scale(w, wg, f->scale_scratch, cv.c_out, cv.c_in * cv.k, st)) return 1;
     // gate pairs side by side: packed row 2j = tanh-half row j, 2j+1 = sigmoid-half row H + j (ConvEpilogue::gate)
-    if (launch_pack_conv(w, f->scale_scratch, cv.w, cv.c_out, cv.c_in, cv.k, st, /*interleave=*/1)) return 1;
+    if (launch_pack_conv(w, f->scale_scratch, cv.w, cv.c_out, cv.c_in, cv.k, st, /*interleave=*/1, f->fp16))
+      return 1;
     if (launch_interleave_bias(bias, cv.bias, cv.c_out, st)) return 1;
   } else if (sscanf(rest.c_str(), "enc.res_skip_layers.%d", &li) == 1 && li >= 0 && li < nl) {
     FlowLayer& ly = c.layers[li];
@@ -448,6 +452,22 @@ int vitsdec_flow_load_layer(vitsdec_flow* f, const char* name, const float* w, c
   }
   c.loaded[rest] = true;
   return 0;
+}
+
+int vitsdec_flow_set_option(vitsdec_flow* f, const char* key, int value) {
+  VD_CHECK(f && key, "vitsdec_flow_set_option: null argument");
+  std::lock_guard<std::mutex> lock(f->mu);
+  if (!strcmp(key, "fp16")) {
+    const int v = value ? 1 : 0;
+    if (v != f->fp16) {   // packed weights of the other 16-bit format are useless: every layer must be loaded again
+      f->fp16 = v;
+      for (FlowCoupling& c : f->cpl) c.loaded.clear();
+      f->plans.clear();
+    }
+    return 0;
+  }
+  set_error(std::string("unknown option ") + key);
+  return 1;
 }
 
 size_t vitsdec_flow_workspace_bytes(const vitsdec_flow* f, int batch, int frames) {
@@ -510,7 +530,7 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
       const int ci = reverse ? nf - 1 - step : step;
       FlowCoupling& c = f->cpl[ci];
       const int flip_now = reverse ? 1 : (step > 0 ? 1 : 0);
-      flow_flip_split_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, X0, rows, C, flip_now);
+      flow_flip_split_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, X0, rows, C, flip_now, f->fp16);
       if (g) {
         dim3 grid((nl * 2 * H * 32 + 255) / 256, B);
         flow_cond_kernel<<<grid, 256, 0, qs>>>(c.cond_w, c.cond_b, gws, CB, B, 2 * H, nl, f->hp.gin_channels);

@@ -30,14 +30,14 @@ __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __rest
 // Conv1d weight [co][ci][k] -> packed [tap][co][ci] bf16 (B operand rows = co, K = ci contiguous).
 // interleave != 0: packed row 2j holds weight row j, packed row 2j+1 weight row c_out/2 + j (gate pairs, ConvEpilogue::gate)
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                 __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int k, int interleave) {
+                                 __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int k, int interleave, int f16) {
   const long total = (long)k * c_out * c_in;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int ci = i % c_in;
     int co = (i / c_in) % c_out;
     if (interleave) co = (co & 1) ? c_out / 2 + (co >> 1) : (co >> 1);
     const int j = i / ((long)c_in * c_out);
-    wp[i] = __float2bfloat16_rn(w[((long)co * c_in + ci) * k + j] * scale[co]);
+    wp[i] = pack_act_rt(w[((long)co * c_in + ci) * k + j] * scale[co], f16);
   }
 }
 
@@ -46,7 +46,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
 // j - (k-1)/2 = r*(s_min+s) + psi - phi.
 __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                       __nv_bfloat16* __restrict__ wp, int C, int c_out, int k, int r, int s_min,
-                                      int ntaps, int lo_part) {
+                                      int ntaps, int lo_part, int f16) {
   const int rc = r * C;
   const long total = (long)ntaps * rc * rc;
   const int hk = (k - 1) / 2;
@@ -61,8 +61,8 @@ __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* 
     // w - bf16(w) of the SAME source row; the epilogue adds the two accumulator rows
     const int src = lo_part ? 0 : co;
     if (j >= 0 && j < k && co < (lo_part ? 2 : c_out)) val = w[((long)src * C + ci) * k + j] * (scale ? scale[src] : 1.f);
-    if (lo_part && co == 1) val -= __bfloat162float(__float2bfloat16_rn(val));
-    wp[i] = __float2bfloat16_rn(val);
+    if (lo_part && co == 1) val -= unpack_act_rt(pack_act_rt(val, f16), f16);
+    wp[i] = pack_act_rt(val, f16);
   }
 }
 
@@ -70,7 +70,7 @@ __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* 
 // output sample s*i + r takes input rows i + off; the contributing kernel index is j = r + p - s*off.
 __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                   __nv_bfloat16* __restrict__ wp, int c_in, int c_out, int k, int s, int p,
-                                  int ntaps, int off0) {
+                                  int ntaps, int off0, int f16) {
   const long total = (long)ntaps * s * c_out * c_in;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int ci = i % c_in;
@@ -81,7 +81,7 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __re
     const int j = r + p - s * (off0 + tap);
     float val = 0.f;
     if (j >= 0 && j < k) val = w[((long)ci * c_out + co) * k + j] * scale[ci];
-    wp[i] = __float2bfloat16_rn(val);
+    wp[i] = pack_act_rt(val, f16);
   }
 }
 
@@ -109,7 +109,7 @@ __global__ void sum_bias_kernel(const float* __restrict__ b0, const float* __res
 
 // z fp32 [B][C][T] (strided) -> bf16 [B][T][C]
 __global__ void pack_z_kernel(const float* __restrict__ z, long sb, long sc, __nv_bfloat16* __restrict__ out, int C,
-                              int T) {
+                              int T, int f16) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -120,7 +120,7 @@ __global__ void pack_z_kernel(const float* __restrict__ z, long sb, long sc, __n
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int t = t0 + i, c = c0 + threadIdx.x;
-    if (t < T && c < C) out[((long)b * T + t) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    if (t < T && c < C) out[((long)b * T + t) * C + c] = pack_act_rt(tile[threadIdx.x][i], f16);
   }
 }
 
@@ -145,7 +145,7 @@ constexpr int kPostThreads = 128;
 template <int kPostPer>
 __global__ void __launch_bounds__(kPostThreads) conv_post_kernel(const __nv_bfloat16* __restrict__ x,
                                                                 const float* __restrict__ w, float* __restrict__ out,
-                                                                int L, int C) {
+                                                                int L, int C, int f16) {
   constexpr int kPostTile = kPostThreads * kPostPer;
   extern __shared__ uint8_t sm[];
   float* ws = reinterpret_cast<float*>(sm);                                  // [7][C]
@@ -173,9 +173,12 @@ __global__ void __launch_bounds__(kPostThreads) conv_post_kernel(const __nv_bflo
 #pragma unroll
       for (int o = 0; o < kPostPer; ++o) {
         const uint4 xv = *reinterpret_cast<const uint4*>(xs + (threadIdx.x + o * kPostThreads + j) * pitch + c);
-        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
-        const float2 f0 = __bfloat1622float2(x2[0]), f1 = __bfloat1622float2(x2[1]);
-        const float2 f2 = __bfloat1622float2(x2[2]), f3 = __bfloat1622float2(x2[3]);
+        float2 f0, f1, f2, f3;
+        if (f16) {
+          f0 = unpack_act2<true>(xv.x); f1 = unpack_act2<true>(xv.y); f2 = unpack_act2<true>(xv.z); f3 = unpack_act2<true>(xv.w);
+        } else {
+          f0 = unpack_act2<false>(xv.x); f1 = unpack_act2<false>(xv.y); f2 = unpack_act2<false>(xv.z); f3 = unpack_act2<false>(xv.w);
+        }
         float a = acc[o];
         a = fmaf(f0.x, w0.x, a); a = fmaf(f0.y, w0.y, a); a = fmaf(f1.x, w0.z, a); a = fmaf(f1.y, w0.w, a);
         a = fmaf(f2.x, w1.x, a); a = fmaf(f2.y, w1.y, a); a = fmaf(f3.x, w1.z, a); a = fmaf(f3.y, w1.w, a);
@@ -192,14 +195,14 @@ __global__ void __launch_bounds__(kPostThreads) conv_post_kernel(const __nv_bflo
 
 // a-form bf16 [B][L][C] -> residual-stream fp32 NCL [B][C][L]
 __global__ void unpack_debug_kernel(const __nv_bfloat16* __restrict__ a, float gain, float* __restrict__ out, int L,
-                                    int C) {
+                                    int C, int f16) {
   const long total = (long)gridDim.y * L * C;
   (void)total;
   const int b = blockIdx.y;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)L * C; i += (long)gridDim.x * blockDim.x) {
     const int c = i % C;
     const long t = i / C;
-    const float v = __bfloat162float(a[(long)b * L * C + i]);
+    const float v = unpack_act_rt(a[(long)b * L * C + i], f16);
     out[((long)b * C + c) * L + t] = v >= 0.f ? v : v * gain;
   }
 }
@@ -216,29 +219,29 @@ int launch_interleave_bias(const float* b, float* out, int c_out, cudaStream_t s
   return 0;
 }
 int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int c_out, int c_in, int k,
-                     cudaStream_t st, int interleave) {
+                     cudaStream_t st, int interleave, int f16) {
   const long total = (long)k * c_out * c_in;
   pack_conv_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_out, c_in, k,
-                                                                                   interleave);
+                                                                                   interleave, f16);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
 int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp, int C, int c_out, int k, int r,
-                          cudaStream_t st, int lo_part) {
+                          cudaStream_t st, int lo_part, int f16) {
   const int hk = (k - 1) / 2;
   const int s_min = -((hk + r - 1) / r), s_max = (r - 1 + hk) / r;  // floor(-hk/r), floor((r-1+hk)/r)
   const int ntaps = s_max - s_min + 1;
   const long total = (long)ntaps * r * C * r * C;
   pack_conv_fold_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, C, c_out, k, r,
-                                                                                        s_min, ntaps, lo_part);
+                                                                                        s_min, ntaps, lo_part, f16);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
 int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int c_in, int c_out, int k, int s, int p,
-                      int ntaps, int off0, cudaStream_t st) {
+                      int ntaps, int off0, cudaStream_t st, int f16) {
   const long total = (long)ntaps * s * c_out * c_in;
   pack_convT_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_in, c_out, k, s, p,
-                                                                                   ntaps, off0);
+                                                                                   ntaps, off0, f16);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -253,9 +256,10 @@ int launch_sum_bias(const float* b0, const float* b1, const float* b2, const flo
   VD_CUDA(cudaGetLastError());
   return 0;
 }
-int launch_pack_z(const float* z, long sb, long sc, __nv_bfloat16* out, int B, int C, int T, cudaStream_t st) {
+int launch_pack_z(const float* z, long sb, long sc, __nv_bfloat16* out, int B, int C, int T, cudaStream_t st,
+                  int f16) {
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  pack_z_kernel<<<grid, block, 0, st>>>(z, sb, sc, out, C, T);
+  pack_z_kernel<<<grid, block, 0, st>>>(z, sb, sc, out, C, T, f16);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -266,23 +270,25 @@ int launch_cond(const float* wc, const float* bc, const float* g, float* cb, int
   VD_CUDA(cudaGetLastError());
   return 0;
 }
-int launch_conv_post(const __nv_bfloat16* x, const float* w, float* out, int B, int L, int C, cudaStream_t st) {
+int launch_conv_post(const __nv_bfloat16* x, const float* w, float* out, int B, int L, int C, cudaStream_t st,
+                     int f16) {
   VD_CHECK(C % 8 == 0, "conv_post: channels must be a multiple of 8");
   auto smem_for = [&](int per) { return 7 * C * 4 + (size_t)(kPostThreads * per + 6) * (C + 8) * 2; };
   if (smem_for(4) <= 48 * 1024) {
     dim3 grid((L + kPostThreads * 4 - 1) / (kPostThreads * 4), B);
-    conv_post_kernel<4><<<grid, kPostThreads, smem_for(4), st>>>(x, w, out, L, C);
+    conv_post_kernel<4><<<grid, kPostThreads, smem_for(4), st>>>(x, w, out, L, C, f16);
   } else {
     VD_CHECK(smem_for(1) <= 48 * 1024, "conv_post: too many channels");
     dim3 grid((L + kPostThreads - 1) / kPostThreads, B);
-    conv_post_kernel<1><<<grid, kPostThreads, smem_for(1), st>>>(x, w, out, L, C);
+    conv_post_kernel<1><<<grid, kPostThreads, smem_for(1), st>>>(x, w, out, L, C, f16);
   }
   VD_CUDA(cudaGetLastError());
   return 0;
 }
-int launch_unpack_debug(const __nv_bfloat16* a, float gain, float* out, int B, int L, int C, cudaStream_t st) {
+int launch_unpack_debug(const __nv_bfloat16* a, float gain, float* out, int B, int L, int C, cudaStream_t st,
+                        int f16) {
   dim3 grid((unsigned)std::min<long>(((long)L * C + 255) / 256, 8192), B);
-  unpack_debug_kernel<<<grid, 256, 0, st>>>(a, gain, out, L, C);
+  unpack_debug_kernel<<<grid, 256, 0, st>>>(a, gain, out, L, C, f16);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -78,6 +78,17 @@ class ResidualCouplingBlock(nn.Module):
         self._loaded_fingerprint = None
         self._lock = threading.Lock()
         self.assume_frozen = False
+        self._options = {}
+
+    def set_option(self, key, value):
+        """fp16: 1 = fp16 instead of bf16 conv operands / stored activations (the latent stays fp32 either way);
+        the weights are re-folded on the next forward."""
+        changed = self._options.get(key) != int(value)
+        self._options[key] = int(value)
+        if self._handle is not None:
+            _capi.check(_capi.lib().vitsdec_flow_set_option(self._handle, key.encode(), int(value)), "flow set_option")
+        if changed:
+            self._loaded_fingerprint = None
 
     def _fingerprint(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -94,6 +105,8 @@ class ResidualCouplingBlock(nn.Module):
             index = device.index if device.index is not None else torch.cuda.current_device()
             _capi.check(lib.vitsdec_flow_create(ctypes.byref(hp), index, ctypes.byref(h)), "vitsdec_flow_create")
             self._handle, self._handle_device, self._loaded_fingerprint = h, device, None
+            for k, v in self._options.items():
+                _capi.check(lib.vitsdec_flow_set_option(self._handle, k.encode(), v), "flow set_option")
         fp = None
         if self._loaded_fingerprint is None or not self.assume_frozen:
             fp = self._fingerprint()

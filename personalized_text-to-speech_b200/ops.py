@@ -10,18 +10,22 @@ def _ptr(t):
 
 def conv1d_cl(x, w, bias=None, dilation=1, res=None, res_gain=10.0, out_slope=1.0, impl=0, desc_mode=0):
     """Fused conv on channels-last bf16 activations.  x: bf16 [B, L, C_in]; w: fp32 [C_out, C_in, k] (rounded to
-    bf16 inside); bias fp32 [C_out]; res: bf16 [B, L, C_out] stored post-leaky-relu(1/res_gain).  -> bf16 [B, L, C_out]."""
-    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
+    bf16 inside); bias fp32 [C_out]; res: bf16 [B, L, C_out] stored post-leaky-relu(1/res_gain).  -> bf16 [B, L, C_out].
+    A float16 x selects the fp16 storage mode (the decoder's "fp16" option): weights, res and y are fp16 as well."""
+    assert x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.is_contiguous()
+    assert res is None or res.dtype == x.dtype
+    if x.dtype == torch.float16:
+        desc_mode |= 1024
     B, L, c_in = x.shape
     c_out, c_in2, k = w.shape
     assert c_in2 == c_in
     w = w.float().contiguous()
     bias = None if bias is None else bias.float().contiguous()
-    y = torch.empty((B, L, c_out), dtype=torch.bfloat16, device=x.device)
+    y = torch.empty((B, L, c_out), dtype=x.dtype, device=x.device)
     if (desc_mode & 16) and dilation > 1:
         # the dilated folded view reads (and masks) up to dilation*r rows past the end of x: give it NaN slack, like
         # the decoder's workspace does with its tail bytes
-        buf = torch.full((x.numel() + 4096,), float("nan"), dtype=torch.bfloat16, device=x.device)
+        buf = torch.full((x.numel() + 4096,), float("nan"), dtype=x.dtype, device=x.device)
         buf[:x.numel()].copy_(x.reshape(-1))
         x = buf[:x.numel()].view(B, L, c_in)
     st = torch.cuda.current_stream(x.device).cuda_stream

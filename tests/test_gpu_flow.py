@@ -128,3 +128,50 @@ def test_flow_then_decoder_matches_the_reference_chain():
     o_ref = generator_forward_torch(ghp, to_torch_state_dict(gsd), z_ref * m, g)
     check(z_ref, z.cpu())
     check(o_ref, o, snr_min=30.0, frac=0.05)   # two bf16 stages in series
+
+
+@pytest.mark.parametrize("B,T,lens,reverse", [(3, 301, (301, 17, 150), True), (2, 1000, (1000, 999), False)])
+def test_fp16_mode_vs_fp32_restatement_and_back(B, T, lens, reverse):
+    """Option "fp16": fp16 conv operands / stored activations.  Stated tolerance for this mode: SNR >= 55 dB (the bf16
+    mode's bound is 35 dB, measured 45-50)."""
+    hp = FLOW_FINETUNE_SPEAKER
+    F, sd = build(hp, 60 + B)
+    rs = np.random.RandomState(B * 7 + T)
+    x = torch.from_numpy(rs.standard_normal((B, hp.channels, T)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((B, hp.gin_channels, 1)).astype(np.float32))
+    m = mask_of(lens, T)
+    ref = flow_forward_torch(hp, sd, x, m, g, reverse=reverse)
+    with torch.no_grad():
+        y_bf = F(x.to(DEV), m.to(DEV), g=g.to(DEV), reverse=reverse).cpu()
+        F.set_option("fp16", 1)
+        y_h = F(x.to(DEV), m.to(DEV), g=g.to(DEV), reverse=reverse).cpu()
+        F.set_option("fp16", 0)
+        y_bf2 = F(x.to(DEV), m.to(DEV), g=g.to(DEV), reverse=reverse).cpu()
+    s_bf, _ = check(ref, y_bf)
+    s_h, _ = check(ref, y_h, snr_min=55.0, frac=0.005)
+    assert s_h > s_bf + 10.0
+    assert torch.equal(y_bf, y_bf2)
+
+
+def test_fp16_mode_flow_then_decoder_chain():
+    fhp, ghp = FLOW_FINETUNE_SPEAKER, oracle.FINETUNE_SPEAKER
+    F, fsd = build(fhp, 72)
+    F.set_option("fp16", 1)
+    args, kw = ghp.ctor_args()
+    G = vitsdec.Generator(*args, **kw)
+    gsd = oracle.synth_state_dict(ghp, 73, gain=2.0)
+    G.load_state_dict({k: torch.from_numpy(v) for k, v in gsd.items()})
+    G = G.to(DEV).eval()
+    G.set_option("fp16", 1)
+    B, T = 2, 120
+    rs = np.random.RandomState(5)
+    z_p = torch.from_numpy(rs.standard_normal((B, fhp.channels, T)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((B, fhp.gin_channels, 1)).astype(np.float32))
+    m = mask_of([T, 77], T)
+    with torch.no_grad():
+        z = F(z_p.to(DEV), m.to(DEV), g=g.to(DEV), reverse=True)
+        o = G(z * m.to(DEV), g.to(DEV)).cpu()
+    z_ref = flow_forward_torch(fhp, fsd, z_p, m, g, reverse=True)
+    o_ref = generator_forward_torch(ghp, to_torch_state_dict(gsd), z_ref * m, g)
+    check(z_ref, z.cpu(), snr_min=55.0, frac=0.005)
+    check(o_ref, o, snr_min=45.0, frac=0.01)   # two fp16 stages in series (bf16: 30 dB)

@@ -254,3 +254,60 @@ def test_randomised_conv_shapes():
         assert torch.isfinite(y.float()).all() and err < REL_TOL, (case, B, L, ci, co, k, d, use_res, fold, err)
         n_fold += int(fold)
     assert n_fold >= 5
+
+
+# ---- fp16 storage mode (decoder option "fp16"): same kernels, IEEE fp16 operands / residual / output
+FP16_CASES = [
+    (2, 300, 128, 128, 7, 5, True),     # channels-as-M tile, streamed weights, residual
+    (2, 1000, 256, 256, 11, 5, True),   # two M-tiles of channels
+    (3, 777, 32, 32, 11, 3, True),      # 64-byte rows, time-as-M
+    (2, 517, 64, 64, 7, 3, True),
+    (2, 50, 192, 512, 7, 1, False),     # conv_pre shape
+    (1, 1, 64, 64, 11, 5, True),
+    (5, 130, 96, 96, 3, 1, False),      # generic epilogue
+]
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("case", FP16_CASES, ids=lambda c: "B%d_L%d_ci%d_co%d_k%d_d%d_r%d" % c)
+def test_conv1d_fp16_storage_matches_torch(case, impl):
+    B, L, ci, co, k, d, use_res = case
+    torch.manual_seed(B * 1000 + L + 7)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, L, ci, device=dev).half()
+    w = torch.randn(co, ci, k, device=dev) / (ci * k) ** 0.5
+    b = torch.randn(co, device=dev) * 0.1
+    res = torch.randn(B, L, co, device=dev).half() if use_res else None
+    y = ops.conv1d_cl(x, w, b, dilation=d, res=res, res_gain=10.0, out_slope=0.1, impl=impl)
+    torch.cuda.synchronize()
+    assert y.dtype == torch.float16
+    kk = w.shape[2]
+    r = F.conv1d(x.float().transpose(1, 2), w.half().float(), b, dilation=d, padding=(kk - 1) // 2 * d)
+    if res is not None:
+        rr = res.float().transpose(1, 2)
+        r = r + torch.where(rr >= 0, rr, rr * 10.0)
+    r = torch.where(r >= 0, r, r * 0.1).transpose(1, 2)
+    # fp16 output rounding is 2^-12 relative: eight times tighter than the bf16 tolerance
+    assert rel_err(y, r) < REL_TOL / 8
+
+
+def test_fp16_storage_folded_forms_and_saturation():
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    # time-folded (plain and dilated) forms agree with the plain tile to one fp16 ulp
+    for (L, k, d) in ((1024, 7, 1), (3111, 11, 3)):
+        x = torch.randn(2, L, 32, device=dev).half()
+        w = torch.randn(32, 32, k, device=dev) / (32 * k) ** 0.5
+        b = torch.randn(32, device=dev) * 0.1
+        res = torch.randn(2, L, 32, device=dev).half()
+        a = ops.conv1d_cl(x, w, b, dilation=d, res=res, out_slope=0.1, impl=0).float()
+        c = ops.conv1d_cl(x, w, b, dilation=d, res=res, out_slope=0.1, impl=0, desc_mode=16).float()
+        assert float(((a - c).abs() / (a.abs() + 1e-2)).max()) < 2 ** -9
+    # stores saturate at the largest finite fp16 instead of overflowing to inf
+    x = torch.full((1, 256, 64), 200.0, device=dev).half()
+    w = torch.full((64, 64, 3), 4.0, device=dev)
+    y = ops.conv1d_cl(x, w, None, out_slope=0.1, impl=0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all() and float(y.float().max()) == 65504.0
+    y = ops.conv1d_cl(x, -w, None, out_slope=1.0, impl=0)
+    assert torch.isfinite(y.float()).all() and float(y.float().min()) == -65504.0

@@ -24,3 +24,12 @@ for seed, B, T in ((21, 2, 20), (36, 2, 173), (44, 1, 400)):
             y = G(z.cuda(), g.cuda()).cpu()
         out.append("%s %.2f dB" % (opts, snr(ref, y)))
     print((seed, B, T), " | ".join(out))
+    for k_, v in {"fuse_pairs": 1, "fold": 1, "pairf": 1}.items():
+        G.set_option(k_, v)
+    out = []
+    for f16 in (0, 1):   # 16-bit storage format of weights and activations
+        G.set_option("fp16", f16)
+        with torch.no_grad():
+            y = G(z.cuda(), g.cuda()).cpu()
+        out.append("fp16=%d %.2f dB, max-abs %.5f of peak" % (f16, snr(ref, y), float((ref - y).abs().max() / ref.abs().max())))
+    print((seed, B, T), " | ".join(out))
