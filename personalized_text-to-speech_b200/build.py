@@ -22,6 +22,10 @@ if os.environ.get("VITSDEC_TRACE") == "1":   # debug build with per-tile clock64
     NVCC_FLAGS = NVCC_FLAGS + ["-DVITSDEC_TRACE=1"]
 
 
+if os.environ.get("VITSDEC_SPIN_SLEEP"):   # experiment: back-off (ns) between failed mbarrier polls
+    NVCC_FLAGS = NVCC_FLAGS + ["-DVITSDEC_SPIN_SLEEP=" + os.environ["VITSDEC_SPIN_SLEEP"]]
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):

@@ -26,7 +26,8 @@ namespace vd {
 #endif
 constexpr bool kPairTrace = VITSDEC_TRACE != 0;
 constexpr int kPairEpiWarps = 16;
-constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
+constexpr int kPairThreads = 64 + 32 * kPairEpiWarps + 32;  // producer, c1 issuer, 16 epilogue warps, c2 issuer
+constexpr int kPairC2Warp = 2 + kPairEpiWarps;
 constexpr int kPairMaxNA = 4;
 constexpr int kPairHRows = 272;  // 256 + (k-1) rounded up, k <= 15
 
@@ -107,82 +108,92 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       mbar_expect_tx(w_full, 2 * p.k * B_STAGE);
       for (int tap = 0; tap < 2 * p.k; ++tap) tma_load_3d(&tmW, w_full, smemW + tap * B_STAGE, 0, 0, tap);
+      uint32_t sa = 0, pa = 0;   // stage / phase counters: a runtime i % NA is ~150 cycles of dependent integer code
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t tile = blockIdx.x + i * gridDim.x;
         uint32_t b, mt;
         p.div_m.divmod(tile, b, mt);
         const int t0 = mt * p.bmo;
-        const uint32_t sa = i % NA, pa = (i / NA) & 1;
         mbar_wait(&a_empty[sa], pa ^ 1);
+        if (kPairTrace && p.trace && blockIdx.x == 0 && i < 256) p.trace[i * 12 + 10] = clock64();
         mbar_expect_tx(&a_full[sa], p.nboxes * 64 * ROWB);
         for (int bx = 0; bx < p.nboxes; ++bx)
           tma_load_3d(&tmA, &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, 0,
                       t0 - hk - hk * p.dil + bx * 64, (int)b);
+        if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (warp-uniform; elected lane issues)
+  } else if (warp == 1 || warp == kPairC2Warp) {
+    // ------------------------------------------------------------ MMA issuers (warp-uniform; elected lane issues)
+    // Two issuing warps: warp 1 runs c1 of every tile, the last warp c2.  With ONE issuer the fixed cost of its
+    // in-order stream per tile (4 mbarrier waits, 4 commits, index arithmetic: ~2000 cycles, gaps of ~600 cycles
+    // between every c1 and c2 in profiles/r01_trace_pair.txt) overlapped with nothing and bounded every pair; the
+    // tensor pipe executes the two streams in issue order and the hand-offs (acc1 / h / acc2 / activation stages) are
+    // the same mbarriers as before.  tcgen05.commit tracks the MMAs of the committing thread only.
     constexpr uint32_t idesc = umma_idesc_f16(CH, F16);
     constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
     const uint32_t leader = elect_one();
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), w_lo0 = umma_desc_lo(smem_u32(smemW));
     const uint32_t h_lo0 = umma_desc_lo(smem_u32(smemH));
     const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t h_buf16 = (uint32_t)(HROWS * ROWB) >> 4;
+    const int k = p.k;
     mbar_wait(w_full, 0);
     tc_fence_after();
-    auto c1 = [&](int i) {
-      const uint32_t as = i & 1, sa = i % NA;
-      mbar_wait(&acc1_empty[as], ((i >> 1) & 1) ^ 1);
-      mbar_wait(&a_full[sa], (i / NA) & 1);
-      tc_fence_after();
-      const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
-      if (tr) p.trace[i * 12 + 0] = clock64();
-      const uint32_t d_base = tmem_base + as * ACC_COLS;
-      const uint32_t a_lo = a_lo0 + sa * a_stage16;
-      for (int tap = 0; tap < p.k; ++tap) {
-        const uint32_t at = a_lo + ((uint32_t)(tap * p.dil * ROWB) >> 4);
-        const uint32_t wt = w_lo0 + tap * (B_STAGE >> 4);
+    if (warp == 1) {
+      const uint32_t tap_step16 = (uint32_t)(p.dil * ROWB) >> 4;
+      uint32_t sa = 0, pa = 0;   // stage / phase counters instead of i % NA, i / NA
+      for (int i = 0; i < my_tiles; ++i) {
+        const uint32_t as = i & 1;
+        if (kPairTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0) p.trace[i * 12 + 11] = clock64();
+        mbar_wait(&acc1_empty[as], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&a_full[sa], pa);
+        tc_fence_after();
+        const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
+        if (tr) p.trace[i * 12 + 0] = clock64();
+        const uint32_t d_base = tmem_base + as * ACC_COLS;
+        uint32_t at = a_lo0 + sa * a_stage16, wt = w_lo0;
+        for (int tap = 0; tap < k; ++tap, at += tap_step16, wt += B_STAGE >> 4) {
 #pragma unroll
-        for (int acc = 0; acc < NACC; ++acc)
+          for (int acc = 0; acc < NACC; ++acc)
 #pragma unroll
-          for (int kk = 0; kk < KC / 16; ++kk)
-            umma_f16_lohi(d_base + acc * CH, at + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
-                          desc_hi, idesc, (tap > 0 || kk > 0) ? 1u : 0u, leader);
+            for (int kk = 0; kk < KC / 16; ++kk)
+              umma_f16_lohi(d_base + acc * CH, at + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
+                            desc_hi, idesc, (tap > 0 || kk > 0) ? 1u : 0u, leader);
+        }
+        if (leader) {
+          umma_commit(&acc1_full[as]);
+          umma_commit(&a_empty[sa]);
+        }
+        if (tr) p.trace[i * 12 + 1] = clock64();
+        if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1; }
       }
-      if (leader) {
-        umma_commit(&acc1_full[as]);
-        umma_commit(&a_empty[sa]);
-      }
-      if (tr) p.trace[i * 12 + 1] = clock64();
-    };
-    auto c2 = [&](int i) {
-      const uint32_t as = i & 1, hb = i % NH;
-      mbar_wait(&h_full[hb], (i / NH) & 1);
-      mbar_wait(&acc2_empty[as], ((i >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
-      if (tr) p.trace[i * 12 + 2] = clock64();
-      const uint32_t d_base = tmem_base + 2 * ACC_COLS + as * ACC_COLS;
-      for (int tap = 0; tap < p.k; ++tap) {
-        const uint32_t ht = h_lo0 + ((uint32_t)(hb * HROWS * ROWB + tap * ROWB) >> 4);
-        const uint32_t wt = w_lo0 + (p.k + tap) * (B_STAGE >> 4);
+    } else {
+      uint32_t hb = 0, ph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const uint32_t as = i & 1;
+        mbar_wait(&h_full[hb], ph);
+        mbar_wait(&acc2_empty[as], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
+        if (tr) p.trace[i * 12 + 2] = clock64();
+        const uint32_t d_base = tmem_base + 2 * ACC_COLS + as * ACC_COLS;
+        uint32_t ht = h_lo0 + hb * h_buf16, wt = w_lo0 + k * (B_STAGE >> 4);
+        for (int tap = 0; tap < k; ++tap, ht += ROWB >> 4, wt += B_STAGE >> 4) {
 #pragma unroll
-        for (int acc = 0; acc < NACC; ++acc)
+          for (int acc = 0; acc < NACC; ++acc)
 #pragma unroll
-          for (int kk = 0; kk < KC / 16; ++kk)
-            umma_f16_lohi(d_base + acc * CH, ht + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
-                          desc_hi, idesc, (tap > 0 || kk > 0) ? 1u : 0u, leader);
+            for (int kk = 0; kk < KC / 16; ++kk)
+              umma_f16_lohi(d_base + acc * CH, ht + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
+                            desc_hi, idesc, (tap > 0 || kk > 0) ? 1u : 0u, leader);
+        }
+        if (leader) {
+          umma_commit(&acc2_full[as]);
+          umma_commit(&h_empty[hb]);
+        }
+        if (tr) p.trace[i * 12 + 3] = clock64();
+        if (++hb == (uint32_t)NH) { hb = 0; ph ^= 1; }
       }
-      if (leader) {
-        umma_commit(&acc2_full[as]);
-        umma_commit(&h_empty[hb]);
-      }
-      if (tr) p.trace[i * 12 + 3] = clock64();
-    };
-    if (my_tiles > 0) c1(0);
-    for (int i = 0; i < my_tiles; ++i) {
-      if (i + 1 < my_tiles) c1(i + 1);
-      c2(i);
     }
     __syncwarp();
   } else {
@@ -196,13 +207,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __nv_bfloat16* const out = p.out;
 
     // h = lrelu(c1 + b1), zero outside the utterance, written as c2's swizzled K-major A operand
+    uint32_t hb = 0, ph = 0;   // epi1: h buffer / phase counters;  epi2: activation stage counter (no runtime i % N)
+    uint32_t sa = 0;
     auto epi1 = [&](int i) {
       const uint32_t tile = blockIdx.x + i * gridDim.x;
       uint32_t b, mt;
       p.div_m.divmod(tile, b, mt);
       const int t0 = mt * p.bmo;
-      const uint32_t as = i & 1, hb = i % NH;
+      const uint32_t as = i & 1;
       uint8_t* const hbuf = smemH + hb * HROWS * ROWB;
+      if (kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 256) p.trace[i * 12 + 9] = clock64();
       mbar_wait(&acc1_full[as], (i >> 1) & 1);
       tc_fence_after();
       const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 256;
@@ -236,7 +250,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (!h_free) {  // the c2 that last read this h buffer must have retired before it is overwritten
-          mbar_wait(&h_empty[hb], ((i / NH) & 1) ^ 1);
+          mbar_wait(&h_empty[hb], ph ^ 1);
           h_free = true;
         }
         const uint32_t sw = swz_row<ROWB>(r);
@@ -251,6 +265,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_arrive(&h_full[hb]);
         mbar_arrive(&acc1_empty[as]);
       }
+      if (++hb == (uint32_t)NH) { hb = 0; ph ^= 1; }
       if (tr) p.trace[i * 12 + 5] = clock64();
     };
 
@@ -260,11 +275,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t b, mt;
       p.div_m.divmod(tile, b, mt);
       const int t0 = mt * p.bmo;
-      const uint32_t as = i & 1, sa = i % NA;
+      const uint32_t as = i & 1;
       const uint8_t* atile = smemA + sa * p.a_stage_bytes;
+      if (kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 + kPairEpiWarps / 2 && lane == 0 && i < 256)
+        p.trace[i * 12 + 8] = clock64();
       mbar_wait(&acc2_full[as], (i >> 1) & 1);
       tc_fence_after();
-      const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 256;
+      const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 + kPairEpiWarps / 2 && lane == 0 && i < 256;
       if (tr) p.trace[i * 12 + 6] = clock64();
       for (int it = hsel; it < NITEMS; it += NW) {
         const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 16;
@@ -314,6 +331,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_arrive(&acc2_empty[as]);
         mbar_arrive(&a_empty[sa]);
       }
+      if (++sa == (uint32_t)NA) sa = 0;
       if (tr) p.trace[i * 12 + 7] = clock64();
     };
 

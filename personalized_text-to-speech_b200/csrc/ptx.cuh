@@ -44,6 +44,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef VITSDEC_SPIN_SLEEP
+    __nanosleep(VITSDEC_SPIN_SLEEP);
+#endif
     if (++spins > (1u << 26)) {
       printf("vitsdec: mbarrier timeout block %d thread %d bar@%u parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);

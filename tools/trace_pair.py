@@ -29,7 +29,8 @@ for (C, L, k, d) in ((32, 220672, 3, 1), (32, 220672, 7, 3), (32, 220672, 11, 5)
     base = t[0, 0]
     print("C=%d k=%d d=%d tiles %d" % (C, k, d, n))
     for i in range(n // 2, min(n, n // 2 + 4)):
-        print("  tile %3d: c1 %7d-%7d  c2 %7d-%7d | epi1 %7d-%7d epi2 %7d-%7d" % ((i,) + tuple(int(v - base) for v in t[i][:8])))
+        print("  tile %3d: c1 %7d-%7d  c2 %7d-%7d | epi1 %7d-%7d epi2 %7d-%7d | epi2 wait from %7d  epi1 wait from %7d  TMA issued %7d  c1 wait from %7d"
+              % ((i,) + tuple(int(v - base) for v in t[i][:12])))
     s = slice(10, n - 5)
     per = (t[n - 5, 7] - t[10, 7]) / (n - 15)
     print("  cycles/tile %.0f | c1 issue %.0f  c2 issue %.0f | epi1 %.0f  epi2 %.0f | c1 end->epi1 start %.0f  epi1 end->c2 start %.0f  c2 end->epi2 start %.0f"
