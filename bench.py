@@ -140,6 +140,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="utterances per GPU")
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling runs (ncu): warm-up + the device-resident timed loop only, no JSON line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -236,6 +238,11 @@ def main():
         conv_ms, conv_launches = G.profile_read()
         G.set_option("profile", 0)
         launches = G.last_launch_count() * args.steps
+        if args.quick:
+            sys.stderr.write("quick: %.3f ms/step device-resident (%d steps)\n" % (ms_total / args.steps, args.steps))
+            if world > 1:
+                dist.destroy_process_group()
+            return 0
 
         # ---- end to end through the public API with HOST buffers (pinned): H2D + decode + D2H every step, two batches
         # in flight (vitsdec.HostPipeline: the copies of neighbouring steps overlap the decode of the current one)

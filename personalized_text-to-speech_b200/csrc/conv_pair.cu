@@ -209,6 +209,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // h = lrelu(c1 + b1), zero outside the utterance, written as c2's swizzled K-major A operand
     uint32_t hb = 0, ph = 0;   // epi1: h buffer / phase counters;  epi2: activation stage counter (no runtime i % N)
     uint32_t sa = 0;
+    // A warp's items always cover the same NBS 16-column groups (item it = hsel + NW*m -> columns 16*(it % CHUNKS)):
+    // their biases live in registers instead of being re-read from shared memory for every item, where the loads queue
+    // behind the tensor core's operand reads
+    constexpr int NBS = CHUNKS / NW;
+    float4 breg[NBS][4];
+#pragma unroll
+    for (int s2 = 0; s2 < NBS; ++s2)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        breg[s2][j] = *reinterpret_cast<const float4*>(sbias + grp * CH + (hsel + NW * s2) * 16 + 4 * j);
     auto epi1 = [&](int i) {
       const uint32_t tile = blockIdx.x + i * gridDim.x;
       uint32_t b, mt;
@@ -222,16 +232,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 256;
       if (tr) p.trace[i * 12 + 4] = clock64();
       bool h_free = false;
-      for (int it = hsel; it < NITEMS; it += NW) {
+#pragma unroll
+      for (int m = 0; m < NITEMS / NW; ++m) {
+        const int it = hsel + NW * m;
         const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 16;
+        const float4 (&bv)[4] = breg[m % NBS];
         const int r = acc * 128 + q * 32 + lane;
         const int th = t0 - hk + r;
         uint32_t a[16];
         __syncwarp();
         tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + acc * CH + c0, a);
-        float4 bv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
         tmem_ld_wait();
         const bool inside = th >= 0 && th < L;
         uint4 o[2];
@@ -283,26 +293,26 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const bool tr = kPairTrace && p.trace && blockIdx.x == 0 && warp == 2 + kPairEpiWarps / 2 && lane == 0 && i < 256;
       if (tr) p.trace[i * 12 + 6] = clock64();
-      for (int it = hsel; it < NITEMS; it += NW) {
+#pragma unroll
+      for (int m = 0; m < NITEMS / NW; ++m) {
+        const int it = hsel + NW * m;
         const int acc = it / CHUNKS, c0 = (it % CHUNKS) * 16;
+        const float4 (&bv)[4] = breg[m % NBS];
         const int i0 = acc * 128 + q * 32;            // first output row of this warp's 32
         const int ra = i0 + lane + hk + hk * p.dil;   // row of x(t0 + i0 + lane) in the activation tile
         uint32_t a[16];
         __syncwarp();
         tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + as * ACC_COLS + acc * CH + c0, a);
-        float4 bv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sbias + CH + c0 + 4 * j);
         const uint32_t sw = swz_row<ROWB>(ra);
         uint4 rx[2];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) rx[h2] = ld_shared_u4(atile + ra * ROWB + ((((c0 >> 3) + h2) ^ sw) << 4));
         tmem_ld_wait();
+        uint4 ov[2];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const uint32_t* r2 = reinterpret_cast<const uint32_t*>(&rx[h2]);
-          uint4 ov;
-          uint32_t* o2 = reinterpret_cast<uint32_t*>(&ov);
+          uint32_t* o2 = reinterpret_cast<uint32_t*>(&ov[h2]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = h2 * 8 + e * 2;
@@ -312,18 +322,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v1 = __uint_as_float(a[j + 1]) + ((j & 3) == 0 ? bq.y : bq.w) + (xr.y >= 0.f ? xr.y : xr.y * res_gain);
             o2[e] = pack_act2<F16>(fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope));
           }
-          *reinterpret_cast<uint4*>(scratch + lane * 32 + ((h2 ^ ((lane >> 2) & 1)) << 4)) = ov;
         }
-        __syncwarp();
+        // this thread's row segment is one aligned 32-byte sector: a single 256-bit store, no shared-memory transposition
+        // (the scratch round trip queued behind the tensor core's operand reads, profiles/r01_trace_pair.txt)
         const int rows_valid = min(32, max(0, min(p.bmo - i0, L - (t0 + i0))));
-        const long row0 = (long)b * L + t0 + i0;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int row = 16 * j + (lane >> 1);
-          const uint4 ov = *reinterpret_cast<const uint4*>(scratch + row * 32 + (((lane & 1) ^ ((row >> 2) & 1)) << 4));
-          if (row < rows_valid) *(reinterpret_cast<uint4*>(out + (row0 + row) * C + c0) + (lane & 1)) = ov;
-        }
-        __syncwarp();
+        if (lane < rows_valid) st_global_v8(out + ((long)b * L + t0 + i0 + lane) * C + c0, ov[0], ov[1]);
       }
       tc_fence_before();
       __syncwarp();

@@ -434,12 +434,15 @@ static PfGeom pf_geom(int channels, int k, int dil) {
 
 int pairf_taps(int channels, int k) { return pf_geom(channels, k, 1).nt; }
 bool pairf_supported(int channels, int k, int dil) { return pf_geom(channels, k, dil).ok; }
-// Where the folded kernel beats conv_pair.cu inside the 16 x 10 s decode (ncu launch lists, profiles/): C=32 k=11 d=1
-// 271 vs 300 us.  Ties elsewhere (C=32 k=7: 229 vs 226; C=64 k=11 vs the two unfused folded convs: 358 vs 347), losses
-// for k=3: the exposed h epilogue and the output epilogue's shared-memory traffic (it slows the overlapping c1 MMAs
-// from 160 to 260 cycles) eat what the wider MMAs gain (profiles/r01_trace_pairf.txt).
+// Where the folded kernel beats conv_pair.cu inside the 16 x 10 s decode (ncu launch lists, profiles/): nowhere any
+// more.  It won C=32 k=11 d=1 (271 vs 300 us) until conv_pair.cu got its second MMA-issuing warp (now 224 us at d=5,
+// profiles/r01_launches_final.txt); it ties for C=32 k=7 and for C=64 k=11 against the two unfused folded convs (358 vs
+// 347 us) and loses for k=3: the exposed h epilogue and the output epilogue's shared-memory traffic (it slows the
+// overlapping c1 MMAs from 160 to 260 cycles) eat what the wider MMAs gain (profiles/r01_trace_pairf.txt).  The kernel
+// stays reachable through option pairf=2 (tests, experiments).
 bool pairf_preferred(int channels, int k, int dil) {
-  return pairf_supported(channels, k, dil) && dil == 1 && channels == 32 && k >= 11;
+  (void)channels; (void)k; (void)dil;
+  return false;
 }
 
 int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
