@@ -335,7 +335,7 @@ def main():
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor",
-                     "kernel": "conv_tc_kernel + conv_pair_kernel + conv_pairf_kernel (tcgen05 implicit-GEMM convs: %d launches/step, "
+                     "kernel": "conv_tc_kernel + conv_pair_kernel (tcgen05 implicit-GEMM convs: %d launches/step, "
                                ">98%% of step time; figures are per launch, averaged over them)" % launches_conv,
                      "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                      "frac_of_sustained": achieved / sustained, "peak_source": peak_src + ", bf16 dense burst",
