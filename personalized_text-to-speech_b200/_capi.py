@@ -93,7 +93,7 @@ def lib():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
+        path = os.environ.get("VITSDEC_LIB") or _build.LIB   # VITSDEC_LIB: A/B two builds on one box (tools/ab.sh)
         if not os.path.exists(path):
             try:
                 _build.build()

@@ -98,7 +98,9 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t ita = 0, itb = 0;
+      // ring positions are (stage, phase) counters: a runtime `it % NA` is ~150 cycles of dependent integer code per
+      // K-chunk / tap in a single-thread stream
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       if (p.stationary) {
         // all taps x K-chunks of this layer's weights stay resident: one bulk load per CTA, no per-tap handshake
         // non-zero K-chunks only, packed in (tap, chunk) order: slot = w_slot[tap] + rank of the chunk in the mask
@@ -131,7 +133,6 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
           const int tap1 = p.g.seg_tap_end[sg];
           const int nbx = p.seg_nboxes[sg];
           for (int kc = 0; kc < nkc; ++kc) {
-            const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
             mbar_wait(&a_empty[sa], pa ^ 1);
             if (kTrace && p.trace && blockIdx.x == 0 && sg == 0 && kc == 0 && tile / gridDim.x < 256)
               p.trace[(tile / gridDim.x) * 12 + 0] = clock64();
@@ -142,15 +143,14 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
             for (int bx = 0; bx < nbx; ++bx)
               tma_load_5d(&tm.a[sg], &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, 0, c1, c2,
                           t0 + p.seg_halo_lo[sg] + bx * 64, b);
-            ++ita;
+            if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1; }
             if (p.stationary) continue;
             for (int tap = tap0; tap < tap1; ++tap) {
               if (p.g.tap_nlo[tap] >= n0 + BN || p.g.tap_nhi[tap] <= n0 || !((p.g.tap_kmask[tap] >> kc) & 1u)) continue;
-              const uint32_t sb = itb % NB, pb = (itb / NB) & 1;
               mbar_wait(&b_empty[sb], pb ^ 1);
               mbar_expect_tx(&b_full[sb], B_STAGE);
               tma_load_3d(&tmW, &b_full[sb], smemB + sb * B_STAGE, kc * KC, n0, tap);
-              ++itb;
+              if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1; }
             }
           }
           tap0 = tap1;
@@ -170,7 +170,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     const uint32_t leader = elect_one();
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), b_lo0 = umma_desc_lo(smem_u32(smemB));
     const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
-    uint32_t ita = 0, itb = 0, itt = 0;
+    uint32_t itt = 0;
+    uint32_t sa = 0, pa = 0, sb_next = 0, pb = 0;   // ring (stage, phase) counters, see the producer
     if (p.stationary) {
       mbar_wait(w_full, 0);
       tc_fence_after();
@@ -195,7 +196,6 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       for (int sg = 0; sg < p.g.nseg; ++sg) {
       const int tap1 = p.g.seg_tap_end[sg];
       for (int kc = 0; kc < nkc; ++kc) {
-        const uint32_t sa = ita % NA, pa = (ita / NA) & 1;
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
         if (tr && sg == 0 && kc == 0) p.trace[itt * 12 + 2] = clock64();
@@ -222,8 +222,8 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
             const uint32_t slot = p.w_slot[tap] + __popc(p.g.tap_kmask[tap] & ((1u << kc) - 1u));
             b_lo = b_lo0 + slot * (B_STAGE >> 4);
           } else {
-            sb = itb % NB;
-            mbar_wait(&b_full[sb], (itb / NB) & 1);
+            sb = sb_next;
+            mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             b_lo = b_lo0 + sb * (B_STAGE >> 4);
           }
@@ -246,11 +246,11 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
           accum = 1;
           if (!p.stationary) {
             if (leader) umma_commit(&b_empty[sb]);  // weights stage free once these MMAs retire
-            ++itb;
+            if (++sb_next == (uint32_t)NB) { sb_next = 0; pb ^= 1; }
           }
         }
         if (leader) umma_commit(&a_empty[sa]);
-        ++ita;
+        if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1; }
       }
       tap0 = tap1;
       }
