@@ -176,15 +176,20 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       mbar_wait(w_full, 0);
       tc_fence_after();
     }
+    int tapmask_n0 = -1;     // the taps that reach an N-tile depend on the tile's column range only: recompute on change
+    uint32_t tapmask = 0;    // (2 constant-bank loads per tap; one N-tile per layer is the common case)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++itt) {
       const uint32_t mb_ = p.div_n.quot(tile);
       const int n0 = (tile - mb_ * p.n_tiles) * BN;
       uint32_t bq_, mt_, bu_, rho_;
       p.div_m.divmod(mb_, bq_, mt_);
       p.div_rho.divmod(bq_, bu_, rho_);
-      uint32_t tapmask = 0;
-      for (int tap = 0; tap < p.g.ntaps; ++tap)
-        if (p.g.tap_nlo[tap] < n0 + BN && p.g.tap_nhi[tap] > n0) tapmask |= 1u << tap;
+      if (n0 != tapmask_n0) {
+        tapmask = 0;
+        for (int tap = 0; tap < p.g.ntaps; ++tap)
+          if (p.g.tap_nlo[tap] < n0 + BN && p.g.tap_nhi[tap] > n0) tapmask |= 1u << tap;
+        tapmask_n0 = n0;
+      }
       const uint32_t as = itt % C::NBUF, pacc = (itt / C::NBUF) & 1;
       mbar_wait(&acc_empty[as], pacc ^ 1);
       tc_fence_after();
@@ -336,6 +341,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       float4 bv[kIW / 4];  // bias for this item's columns: read from smem while the TMEM load is in flight
       float bias4[4] = {0.f, 0.f, 0.f, 0.f};  // channels-as-M: this thread's channels are 8m + lane/4 (fragment layout)
       if constexpr (SWAP) {
+        // (keeping these four values in registers across the items of an N-tile measured 0.8 % SLOWER, tools/ab.sh)
 #pragma unroll
         for (int m = 0; m < 4; ++m) bias4[m] = sbias[cur.n + 8 * m + (lane >> 2)];
       } else {
