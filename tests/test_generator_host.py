@@ -187,3 +187,23 @@ def test_time_folded_conv_derivation():
                     if t < L:
                         y[t] = acc[phi * C:(phi + 1) * C]
         assert np.abs(ref - y).max() < 1e-12, (C, k, r, d, L)
+
+
+def test_options_are_remembered_until_a_native_handle_exists():
+    """set_option before the first forward (no handle, no GPU) is recorded and replayed at vitsdec_create; changing
+    the 16-bit storage format ("fp16") invalidates the folded weights so that the next forward re-folds them."""
+    G = make(oracle.TINY)
+    assert G._handle is None
+    G._loaded_fingerprint = ("stale",)
+    G.set_option("fp16", 1)
+    assert G._options == {"fp16": 1} and G._loaded_fingerprint is None and G._handle is None
+    G._loaded_fingerprint = ("kept",)
+    G.set_option("fp16", 1)          # unchanged value: nothing to re-fold
+    G.set_option("graph", 0)         # other options never touch the weights
+    assert G._loaded_fingerprint == ("kept",) and G._options == {"fp16": 1, "graph": 0}
+    G.set_option("fp16", 0)
+    assert G._loaded_fingerprint is None
+    F = vitsdec.ResidualCouplingBlock(8, 8, 5, 1, 2, n_flows=2, gin_channels=4)
+    F._loaded_fingerprint = ("stale",)
+    F.set_option("fp16", 1)
+    assert F._options == {"fp16": 1} and F._loaded_fingerprint is None and F._handle is None
