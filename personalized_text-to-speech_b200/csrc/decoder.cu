@@ -231,6 +231,7 @@ struct vitsdec_decoder {
   int hop = 1;
   float* scale_scratch = nullptr;
   int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1, par = 1;
+  int c_z = 0;   // initial_channel rounded up to a multiple of 32: the packed latent and conv_pre's K are zero-padded
   int fp16 = 0;  // option "fp16": weights and stored activations are IEEE fp16 instead of bf16 (ConvEpilogue::f16)
   cudaStream_t cstream = nullptr;  // capture-only stream (the caller's may be the legacy default stream)
   cudaStream_t bstream[VITSDEC_MAX_KERNELS] = {};  // capture-only streams of MRF branches 1.. (Plan::par)
@@ -330,7 +331,7 @@ static WsLayout ws_layout(const vitsdec_decoder* d, int B, int T) {
   slot = align_up(slot, 1024);
   size_t o = 0;
   w.slot = slot;
-  w.off_a0 = o; o += align_up((size_t)B * T * d->hp.initial_channel * 2, 1024);
+  w.off_a0 = o; o += align_up((size_t)B * T * d->c_z * 2, 1024);
   w.off_cb = o; o += align_up((size_t)B * d->hp.upsample_initial_channel * 4, 1024);
   w.nslots = all_fused(d) ? 4 + 2 * d->hp.num_kernels + 2 * (d->hp.num_kernels - 1)
                           : std::max(7, 4 + 2 * d->hp.num_kernels);
@@ -575,7 +576,7 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
   VD_CHECK(hp->resblock == 1 || hp->resblock == 2, "resblock must be 1 or 2");
   VD_CHECK(hp->num_upsamples >= 1 && hp->num_upsamples <= VITSDEC_MAX_UPSAMPLES, "bad num_upsamples");
   VD_CHECK(hp->num_kernels >= 1 && hp->num_kernels <= VITSDEC_MAX_KERNELS, "bad num_kernels");
-  VD_CHECK(hp->initial_channel % 32 == 0, "initial_channel must be a multiple of 32");
+  VD_CHECK(hp->initial_channel > 0 && hp->initial_channel <= 4096, "initial_channel out of range");
   VD_CHECK(hp->upsample_initial_channel % 32 == 0, "upsample_initial_channel must be a multiple of 32");
   int ndev = 0;
   VD_CUDA(cudaGetDeviceCount(&ndev));
@@ -591,7 +592,9 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
   d->device = device;
   d->num_sms = prop.multiProcessorCount;
   const int c0 = hp->upsample_initial_channel;
-  d->l_pre = add_layer(d.get(), "conv_pre", kConv, hp->initial_channel, c0, 7, 1, 1);
+  // any latent width (HiFi-GAN mel inputs have 80 channels): K is padded with zero channels to the 32-channel K-chunk
+  d->c_z = (hp->initial_channel + 31) / 32 * 32;
+  d->l_pre = add_layer(d.get(), "conv_pre", kConv, d->c_z, c0, 7, 1, 1);
   for (int i = 0; i < hp->num_upsamples; ++i) {
     const int ci = c0 >> i, co = c0 >> (i + 1);
     const int k = hp->upsample_kernel_sizes[i], s = hp->upsample_rates[i];
@@ -790,8 +793,10 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
   Layer& l = d->layers[it->second];
   if (l.kind == kConv) {
     VD_CHECK(l.c_out <= 4096, "too many channels");
-    if (launch_wn_scale(w, wg, d->scale_scratch, l.c_out, l.c_in * l.k, st)) return 1;
-    if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st, 0, d->fp16)) return 1;
+    // conv_pre: the caller's weight has initial_channel input channels, the packed operand d->c_z (zero-padded)
+    const int cin_src = it->second == d->l_pre ? d->hp.initial_channel : l.c_in;
+    if (launch_wn_scale(w, wg, d->scale_scratch, l.c_out, cin_src * l.k, st)) return 1;
+    if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st, 0, d->fp16, cin_src)) return 1;
     if (launch_replicate_bias(bias, l.bias, l.c_out, 1, st)) return 1;
     if (l.fold_r) {
       if (launch_pack_conv_fold(w, d->scale_scratch, l.wfold, l.c_in, l.c_out, l.k, l.fold_r, st, 0, d->fp16)) return 1;
@@ -892,7 +897,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   }
 
   int launches = 0;
-  if (launch_pack_z(z, zsb, zsc, plan->a0, B, d->hp.initial_channel, T, st, d->fp16)) return 1;
+  if (launch_pack_z(z, zsb, zsc, plan->a0, B, d->hp.initial_channel, T, st, d->fp16, d->c_z)) return 1;
   ++launches;
   if (g) {
     const Layer& lc = d->layers[d->l_cond];

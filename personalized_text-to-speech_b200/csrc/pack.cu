@@ -30,14 +30,16 @@ __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __rest
 // Conv1d weight [co][ci][k] -> packed [tap][co][ci] bf16 (B operand rows = co, K = ci contiguous).
 // interleave != 0: packed row 2j holds weight row j, packed row 2j+1 weight row c_out/2 + j (gate pairs, ConvEpilogue::gate)
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                 __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int k, int interleave, int f16) {
+                                 __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int k, int interleave, int f16,
+                                 int c_in_src) {
+  // c_in_src < c_in: the packed K dimension is zero-padded (conv_pre of a latent whose width is not a multiple of 32)
   const long total = (long)k * c_out * c_in;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int ci = i % c_in;
     int co = (i / c_in) % c_out;
     if (interleave) co = (co & 1) ? c_out / 2 + (co >> 1) : (co >> 1);
     const int j = i / ((long)c_in * c_out);
-    wp[i] = pack_act_rt(w[((long)co * c_in + ci) * k + j] * scale[co], f16);
+    wp[i] = pack_act_rt(ci < c_in_src ? w[((long)co * c_in_src + ci) * k + j] * scale[co] : 0.f, f16);
   }
 }
 
@@ -107,9 +109,9 @@ __global__ void sum_bias_kernel(const float* __restrict__ b0, const float* __res
   out[i] = s;
 }
 
-// z fp32 [B][C][T] (strided) -> bf16 [B][T][C]
+// z fp32 [B][C][T] (strided) -> bf16 [B][T][Cp], channels [C, Cp) zero
 __global__ void pack_z_kernel(const float* __restrict__ z, long sb, long sc, __nv_bfloat16* __restrict__ out, int C,
-                              int T, int f16) {
+                              int T, int f16, int Cp) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -120,7 +122,7 @@ __global__ void pack_z_kernel(const float* __restrict__ z, long sb, long sc, __n
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int t = t0 + i, c = c0 + threadIdx.x;
-    if (t < T && c < C) out[((long)b * T + t) * C + c] = pack_act_rt(tile[threadIdx.x][i], f16);
+    if (t < T && c < Cp) out[((long)b * T + t) * Cp + c] = pack_act_rt(tile[threadIdx.x][i], f16);
   }
 }
 
@@ -219,10 +221,11 @@ int launch_interleave_bias(const float* b, float* out, int c_out, cudaStream_t s
   return 0;
 }
 int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int c_out, int c_in, int k,
-                     cudaStream_t st, int interleave, int f16) {
+                     cudaStream_t st, int interleave, int f16, int c_in_src) {
   const long total = (long)k * c_out * c_in;
   pack_conv_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_out, c_in, k,
-                                                                                   interleave, f16);
+                                                                                   interleave, f16,
+                                                                                   c_in_src > 0 ? c_in_src : c_in);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -257,9 +260,10 @@ int launch_sum_bias(const float* b0, const float* b1, const float* b2, const flo
   return 0;
 }
 int launch_pack_z(const float* z, long sb, long sc, __nv_bfloat16* out, int B, int C, int T, cudaStream_t st,
-                  int f16) {
-  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  pack_z_kernel<<<grid, block, 0, st>>>(z, sb, sc, out, C, T, f16);
+                  int f16, int c_pad) {
+  const int Cp = c_pad > C ? c_pad : C;
+  dim3 grid((T + 31) / 32, (Cp + 31) / 32, B), block(32, 8);
+  pack_z_kernel<<<grid, block, 0, st>>>(z, sb, sc, out, C, T, f16, Cp);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

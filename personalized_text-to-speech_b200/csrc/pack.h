@@ -8,7 +8,7 @@
 namespace vd {
 int launch_wn_scale(const float* v, const float* g, float* scale, int rows, int inner, cudaStream_t st);
 int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int c_out, int c_in, int k,
-                     cudaStream_t st, int interleave = 0, int f16 = 0);
+                     cudaStream_t st, int interleave = 0, int f16 = 0, int c_in_src = 0);
 int launch_interleave_bias(const float* b, float* out, int c_out, cudaStream_t st);
 int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp, int C, int c_out, int k, int r,
                           cudaStream_t st, int lo_part = 0, int f16 = 0);
@@ -18,7 +18,7 @@ int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaS
 int launch_sum_bias(const float* b0, const float* b1, const float* b2, const float* b3, float* out, int n,
                     cudaStream_t st);
 int launch_pack_z(const float* z, long sb, long sc, __nv_bfloat16* out, int B, int C, int T, cudaStream_t st,
-                  int f16 = 0);
+                  int f16 = 0, int c_pad = 0);
 int launch_cond(const float* wc, const float* bc, const float* g, float* cb, int B, int c_out, int gin,
                 cudaStream_t st);
 int launch_conv_post(const __nv_bfloat16* x, const float* w, float* out, int B, int L, int C, cudaStream_t st,

@@ -422,3 +422,37 @@ def test_fp16_mode_full_size_determinism():
     assert torch.equal(y0[5:6], y_one)       # batch independence, bit-exact
     ref = generator_forward_torch(hp, to_torch_state_dict(sd), z[5:6].cpu(), g[5:6].cpu())
     check_fp16(ref, y_one.cpu())
+
+
+# ---- other HiFi-GAN configurations through the same constructor
+HIFIGAN_V3_LIKE = oracle.hparams.DecoderHParams(80, "2", (3, 5, 7), ((1, 2), (2, 6), (3, 12)), (8, 8, 4), 256, (16, 16, 8), 0)
+WIDE_K13 = oracle.hparams.DecoderHParams(96, "1", (3, 13), ((1, 3, 5), (1, 2, 4)), (5, 4, 2), 256, (11, 8, 4), 64)
+
+
+@pytest.mark.parametrize("hp,B,T,fp16", [(HIFIGAN_V3_LIKE, 2, 50, 0), (HIFIGAN_V3_LIKE, 1, 211, 1), (WIDE_K13, 3, 33, 0),
+                                         (WIDE_K13, 1, 90, 1)],
+                         ids=["v3like_bf16", "v3like_fp16", "k13_stride5_bf16", "k13_stride5_fp16"])
+def test_other_hifigan_configs_vs_fp32_restatement(hp, B, T, fp16):
+    """ResBlock2 with the published HiFi-GAN V3 shape (3 stages, rates 8/8/4, dilations up to 12, no speaker input) and a
+    ResBlock1 variant with an odd stride (5, kernel 11), k = 13 and 2 kernels per stage: nothing in the kernels is
+    specific to configs/finetune_speaker.json."""
+    G, sd = build(hp, 91)
+    G.set_option("fp16", fp16)
+    rs = np.random.RandomState(B * 10 + T)
+    z = torch.from_numpy(rs.standard_normal((B, hp.initial_channel, T)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((B, hp.gin_channels, 1)).astype(np.float32)) if hp.gin_channels else None
+    ref = generator_forward_torch(hp, to_torch_state_dict(sd), z, g)
+    with torch.no_grad():
+        y = G(z.to(DEV), None if g is None else g.to(DEV))
+    assert y.shape == (B, 1, T * hp.hop)
+    (check_fp16 if fp16 else check)(ref, y.cpu())
+
+
+def test_unsupported_channel_widths_fail_loudly():
+    """HiFi-GAN V2 narrows to 16 and 8 channels; the tcgen05 tiles need multiples of 32: a clear error, no fallback."""
+    hp = oracle.hparams.DecoderHParams(80, "1", (3, 7, 11), ((1, 3, 5),) * 3, (8, 8, 2, 2), 128, (16, 16, 4, 4), 0)
+    args, kw = hp.ctor_args()
+    G = vitsdec.Generator(*args, **kw).to(DEV).eval()
+    with pytest.raises(Exception, match="multiple of 32"):
+        with torch.no_grad():
+            G(torch.randn(1, 80, 8, device=DEV))
