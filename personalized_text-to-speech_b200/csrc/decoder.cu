@@ -54,6 +54,7 @@ struct Layer {
   std::string name;
   LayerKind kind;
   int c_in = 0, c_out = 0, k = 0, dil = 1, stride = 1;
+  int cin_src = 0, cout_src = 0;   // the caller's weight dimensions when the packed operand is zero-padded (0 = same)
   ConvGeom geom{};        // B, L filled per decode
   bf16* w = nullptr;      // packed operand [ntaps][n_total][c_in]
   float* bias = nullptr;  // [n_total] (zero when the layer has no bias)
@@ -595,14 +596,24 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
   // any latent width (HiFi-GAN mel inputs have 80 channels): K is padded with zero channels to the 32-channel K-chunk
   d->c_z = (hp->initial_channel + 31) / 32 * 32;
   d->l_pre = add_layer(d.get(), "conv_pre", kConv, d->c_z, c0, 7, 1, 1);
+  d->layers[d->l_pre].cin_src = hp->initial_channel;
+  // Stage widths are the reference's c0 // 2^(i+1) (models.py:254,260); tensors narrower than 32 channels (HiFi-GAN V2:
+  // 16 and 8) are carried with zero channels up to 32 -- zero weights and zero biases keep them zero through every
+  // leaky-relu, so the padded decoder computes exactly the narrow one.
+  auto pad32 = [](int c) { return (c + 31) / 32 * 32; };
+  std::vector<int> real_ch;
   for (int i = 0; i < hp->num_upsamples; ++i) {
-    const int ci = c0 >> i, co = c0 >> (i + 1);
+    const int ci_real = c0 >> i, co_real = c0 >> (i + 1);
+    const int ci = pad32(ci_real), co = pad32(co_real);
     const int k = hp->upsample_kernel_sizes[i], s = hp->upsample_rates[i];
-    VD_CHECK(co % 32 == 0 && co > 0, "every stage needs a multiple of 32 channels");
+    VD_CHECK(co_real > 0, "upsample_initial_channel is too small for this many stages");
     VD_CHECK(k >= s && (k - s) % 2 == 0, "upsample kernel must satisfy k >= stride and (k - stride) even");
     d->stage_ch.push_back(co);
+    real_ch.push_back(co_real);
     d->hop *= s;
     d->l_ups.push_back(add_layer(d.get(), "ups." + std::to_string(i), kConvT, ci, co, k, 1, s));
+    d->layers.back().cin_src = ci_real;
+    d->layers.back().cout_src = co_real;
     VD_CHECK(d->layers.back().geom.ntaps <= kMaxTaps, "upsample kernel too large");
   }
   int n = 0;
@@ -629,10 +640,12 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
           ids.push_back(add_layer(d.get(), base + "convs." + std::to_string(m), kConv, ch, ch, k,
                                   hp->resblock_dilation_sizes[j][m], 1));
       }
+      for (int id : ids) d->layers[id].cin_src = d->layers[id].cout_src = real_ch[i];
       d->l_rb.push_back(ids);
     }
   }
   d->l_post = add_layer(d.get(), "conv_post", kPost, d->stage_ch.back(), 1, 7, 1, 1);
+  d->layers[d->l_post].cin_src = real_ch.back();
   {
     // conv_post on the tensor cores: time-folded like the narrow ResBlock convs, the single output channel padded to C
     // (zero weight rows), tanh + fp32 store in the epilogue (conv_tc.cu EPI 4)
@@ -791,51 +804,56 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   std::lock_guard<std::mutex> lock(d->mu);
   Layer& l = d->layers[it->second];
+  // the caller's tensors have the reference's (source) dimensions; packed operands are zero-padded to the 32-channel
+  // granularity of the tiles (conv_pre's latent width, stages narrower than 32 channels)
+  const int ci_s = l.cin_src ? l.cin_src : l.c_in, co_s = l.cout_src ? l.cout_src : l.c_out;
   if (l.kind == kConv) {
     VD_CHECK(l.c_out <= 4096, "too many channels");
-    // conv_pre: the caller's weight has initial_channel input channels, the packed operand d->c_z (zero-padded)
-    const int cin_src = it->second == d->l_pre ? d->hp.initial_channel : l.c_in;
-    if (launch_wn_scale(w, wg, d->scale_scratch, l.c_out, cin_src * l.k, st)) return 1;
-    if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st, 0, d->fp16, cin_src)) return 1;
-    if (launch_replicate_bias(bias, l.bias, l.c_out, 1, st)) return 1;
+    if (launch_wn_scale(w, wg, d->scale_scratch, co_s, ci_s * l.k, st)) return 1;
+    if (launch_pack_conv(w, d->scale_scratch, l.w, l.c_out, l.c_in, l.k, st, 0, d->fp16, ci_s, co_s)) return 1;
+    if (launch_replicate_bias(bias, l.bias, l.c_out, 1, st, co_s)) return 1;
     if (l.fold_r) {
-      if (launch_pack_conv_fold(w, d->scale_scratch, l.wfold, l.c_in, l.c_out, l.k, l.fold_r, st, 0, d->fp16)) return 1;
-      if (launch_replicate_bias(bias, l.bias_fold, l.c_out, l.fold_r, st)) return 1;
+      if (launch_pack_conv_fold(w, d->scale_scratch, l.wfold, l.c_in, co_s, l.k, l.fold_r, st, 0, d->fp16, ci_s)) return 1;
+      if (launch_replicate_bias(bias, l.bias_fold, l.c_out, l.fold_r, st, co_s)) return 1;
     }
     if (l.mrf_group >= 0) {
       Layer& v = d->layers[l.mrf_group];
       if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.mrf_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
-                           st, 0, d->fp16))
+                           st, 0, d->fp16, ci_s, co_s))
         return 1;
       if (v.fold_r &&
           launch_pack_conv_fold(w, d->scale_scratch,
-                                v.wfold + (size_t)l.mrf_ftap_base * v.fgeom.n_total * v.fgeom.c_in, l.c_in, l.c_out,
-                                l.k, v.fold_r, st, 0, d->fp16))
+                                v.wfold + (size_t)l.mrf_ftap_base * v.fgeom.n_total * v.fgeom.c_in, l.c_in, co_s,
+                                l.k, v.fold_r, st, 0, d->fp16, ci_s))
         return 1;
       v.bias_dirty = true;
     }
     if (l.pair_group >= 0) {
       Layer& v = d->layers[l.pair_group];
       if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.pair_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
-                           st, 0, d->fp16))
+                           st, 0, d->fp16, ci_s, co_s))
         return 1;
       if (v.fold_r && launch_pack_conv_fold(w, d->scale_scratch, v.wfold + (size_t)l.pair_ftap_base * 128 * 128, l.c_in,
-                                            l.c_out, l.k, v.fold_r, st, 0, d->fp16))
+                                            co_s, l.k, v.fold_r, st, 0, d->fp16, ci_s))
         return 1;
     }
   } else if (l.kind == kConvT) {
     VD_CHECK(l.c_in <= 4096, "too many channels");
-    if (launch_wn_scale(w, wg, d->scale_scratch, l.c_in, l.c_out * l.k, st)) return 1;  // dim 0 of [C_in,C_out,k]
+    if (launch_wn_scale(w, wg, d->scale_scratch, ci_s, co_s * l.k, st)) return 1;  // dim 0 of [C_in,C_out,k]
     if (launch_pack_convT(w, d->scale_scratch, l.w, l.c_in, l.c_out, l.k, l.stride, (l.k - l.stride) / 2,
-                          l.geom.ntaps, l.geom.tap_off[0], st, d->fp16))
+                          l.geom.ntaps, l.geom.tap_off[0], st, d->fp16, ci_s, co_s))
       return 1;
-    if (launch_replicate_bias(bias, l.bias, l.c_out, l.stride, st)) return 1;
+    if (launch_replicate_bias(bias, l.bias, l.c_out, l.stride, st, co_s)) return 1;
   } else {
     VD_CHECK(wg == nullptr, "conv_post / cond are not weight-normed in the reference (models.py:264,268)");
-    VD_CUDA(cudaMemcpyAsync(l.wf32, w, (size_t)l.c_out * l.c_in * l.k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // [c_out][ci_s][k] -> the first ci_s rows of the (zero-initialised) padded copy; c_out = 1 for conv_post and cond
+    // has no padding, so one contiguous copy serves both
+    VD_CUDA(cudaMemsetAsync(l.wf32, 0, (size_t)l.c_out * l.c_in * l.k * sizeof(float), st));
+    VD_CHECK(l.kind == kCond || l.c_out == 1, "conv_post has one output channel");
+    VD_CUDA(cudaMemcpyAsync(l.wf32, w, (size_t)l.c_out * ci_s * l.k * sizeof(float), cudaMemcpyDeviceToDevice, st));
     // two-term weights: virtual channel 0 = bf16(w), channel 1 = bf16(w - bf16(w))
     if (l.kind == kPost && l.fold_r && launch_pack_conv_fold(w, nullptr, l.wfold, l.c_in, 1, l.k, l.fold_r, st, 1,
-                                                                     d->fp16))
+                                                                     d->fp16, ci_s))
       return 1;
     if (l.kind == kCond) {
       VD_CHECK(bias != nullptr, "cond needs a bias");

@@ -31,15 +31,16 @@ __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __rest
 // interleave != 0: packed row 2j holds weight row j, packed row 2j+1 weight row c_out/2 + j (gate pairs, ConvEpilogue::gate)
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                  __nv_bfloat16* __restrict__ wp, int c_out, int c_in, int k, int interleave, int f16,
-                                 int c_in_src) {
-  // c_in_src < c_in: the packed K dimension is zero-padded (conv_pre of a latent whose width is not a multiple of 32)
+                                 int c_in_src, int c_out_src) {
+  // c_in_src < c_in / c_out_src < c_out: the source weight is narrower than the packed operand, which is zero-padded
+  // (conv_pre of a latent whose width is not a multiple of 32; stages narrower than 32 channels)
   const long total = (long)k * c_out * c_in;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int ci = i % c_in;
     int co = (i / c_in) % c_out;
     if (interleave) co = (co & 1) ? c_out / 2 + (co >> 1) : (co >> 1);
     const int j = i / ((long)c_in * c_out);
-    wp[i] = pack_act_rt(ci < c_in_src ? w[((long)co * c_in_src + ci) * k + j] * scale[co] : 0.f, f16);
+    wp[i] = pack_act_rt(ci < c_in_src && co < c_out_src ? w[((long)co * c_in_src + ci) * k + j] * scale[co] : 0.f, f16);
   }
 }
 
@@ -48,7 +49,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
 // j - (k-1)/2 = r*(s_min+s) + psi - phi.
 __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                       __nv_bfloat16* __restrict__ wp, int C, int c_out, int k, int r, int s_min,
-                                      int ntaps, int lo_part, int f16) {
+                                      int ntaps, int lo_part, int f16, int c_in_src) {
   const int rc = r * C;
   const long total = (long)ntaps * rc * rc;
   const int hk = (k - 1) / 2;
@@ -62,7 +63,8 @@ __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* 
     // lo_part (two-term weights of a single-output layer): output row 0 holds bf16(w), row 1 the bf16 remainder
     // w - bf16(w) of the SAME source row; the epilogue adds the two accumulator rows
     const int src = lo_part ? 0 : co;
-    if (j >= 0 && j < k && co < (lo_part ? 2 : c_out)) val = w[((long)src * C + ci) * k + j] * (scale ? scale[src] : 1.f);
+    if (j >= 0 && j < k && co < (lo_part ? 2 : c_out) && ci < c_in_src)
+      val = w[((long)src * c_in_src + ci) * k + j] * (scale ? scale[src] : 1.f);
     if (lo_part && co == 1) val -= unpack_act_rt(pack_act_rt(val, f16), f16);
     wp[i] = pack_act_rt(val, f16);
   }
@@ -72,7 +74,7 @@ __global__ void pack_conv_fold_kernel(const float* __restrict__ w, const float* 
 // output sample s*i + r takes input rows i + off; the contributing kernel index is j = r + p - s*off.
 __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                   __nv_bfloat16* __restrict__ wp, int c_in, int c_out, int k, int s, int p,
-                                  int ntaps, int off0, int f16) {
+                                  int ntaps, int off0, int f16, int c_in_src, int c_out_src) {
   const long total = (long)ntaps * s * c_out * c_in;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int ci = i % c_in;
@@ -82,14 +84,15 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __re
     const int r = n / c_out, co = n % c_out;
     const int j = r + p - s * (off0 + tap);
     float val = 0.f;
-    if (j >= 0 && j < k) val = w[((long)ci * c_out + co) * k + j] * scale[ci];
+    if (j >= 0 && j < k && ci < c_in_src && co < c_out_src) val = w[((long)ci * c_out_src + co) * k + j] * scale[ci];
     wp[i] = pack_act_rt(val, f16);
   }
 }
 
-__global__ void replicate_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int c_out, int reps) {
+__global__ void replicate_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int c_out, int reps,
+                                      int c_out_src) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < c_out * reps) out[i] = b ? b[i % c_out] : 0.f;
+  if (i < c_out * reps) out[i] = (b && i % c_out < c_out_src) ? b[i % c_out] : 0.f;   // padded channels: zero bias
 }
 __global__ void interleave_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int c_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,35 +224,40 @@ int launch_interleave_bias(const float* b, float* out, int c_out, cudaStream_t s
   return 0;
 }
 int launch_pack_conv(const float* w, const float* scale, __nv_bfloat16* wp, int c_out, int c_in, int k,
-                     cudaStream_t st, int interleave, int f16, int c_in_src) {
+                     cudaStream_t st, int interleave, int f16, int c_in_src, int c_out_src) {
   const long total = (long)k * c_out * c_in;
   pack_conv_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_out, c_in, k,
                                                                                    interleave, f16,
-                                                                                   c_in_src > 0 ? c_in_src : c_in);
+                                                                                   c_in_src > 0 ? c_in_src : c_in,
+                                                                                   c_out_src > 0 ? c_out_src : c_out);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
 int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp, int C, int c_out, int k, int r,
-                          cudaStream_t st, int lo_part, int f16) {
+                          cudaStream_t st, int lo_part, int f16, int c_in_src) {
   const int hk = (k - 1) / 2;
   const int s_min = -((hk + r - 1) / r), s_max = (r - 1 + hk) / r;  // floor(-hk/r), floor((r-1+hk)/r)
   const int ntaps = s_max - s_min + 1;
   const long total = (long)ntaps * r * C * r * C;
   pack_conv_fold_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, C, c_out, k, r,
-                                                                                        s_min, ntaps, lo_part, f16);
+                                                                                        s_min, ntaps, lo_part, f16,
+                                                                                        c_in_src > 0 ? c_in_src : C);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
 int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int c_in, int c_out, int k, int s, int p,
-                      int ntaps, int off0, cudaStream_t st, int f16) {
+                      int ntaps, int off0, cudaStream_t st, int f16, int c_in_src, int c_out_src) {
   const long total = (long)ntaps * s * c_out * c_in;
   pack_convT_kernel<<<(int)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(w, scale, wp, c_in, c_out, k, s, p,
-                                                                                   ntaps, off0, f16);
+                                                                                   ntaps, off0, f16,
+                                                                                   c_in_src > 0 ? c_in_src : c_in,
+                                                                                   c_out_src > 0 ? c_out_src : c_out);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
-int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaStream_t st) {
-  replicate_bias_kernel<<<(c_out * reps + 255) / 256, 256, 0, st>>>(b, out, c_out, reps);
+int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaStream_t st, int c_out_src) {
+  replicate_bias_kernel<<<(c_out * reps + 255) / 256, 256, 0, st>>>(b, out, c_out, reps,
+                                                                    c_out_src > 0 ? c_out_src : c_out);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

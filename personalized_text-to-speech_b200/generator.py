@@ -269,6 +269,7 @@ class Generator(nn.Module):
             C, L = c0 // (2 ** (i + 1)), frames
             for u in rates[: i + 1]:
                 L *= u
+        C = -(-C // 32) * 32   # stages narrower than 32 channels are carried zero-padded
         dev = self._handle_device
         buf = torch.empty((batch, C, L), dtype=torch.float32, device=dev)
         c, l = ctypes.c_int(0), ctypes.c_int(0)

@@ -448,9 +448,31 @@ def test_other_hifigan_configs_vs_fp32_restatement(hp, B, T, fp16):
     (check_fp16 if fp16 else check)(ref, y.cpu())
 
 
-def test_unsupported_channel_widths_fail_loudly():
-    """HiFi-GAN V2 narrows to 16 and 8 channels; the tcgen05 tiles need multiples of 32: a clear error, no fallback."""
-    hp = oracle.hparams.DecoderHParams(80, "1", (3, 7, 11), ((1, 3, 5),) * 3, (8, 8, 2, 2), 128, (16, 16, 4, 4), 0)
+HIFIGAN_V2_LIKE = oracle.hparams.DecoderHParams(80, "1", (3, 7, 11), ((1, 3, 5),) * 3, (8, 8, 2, 2), 128, (16, 16, 4, 4), 0)
+
+
+@pytest.mark.parametrize("fp16", [0, 1], ids=["bf16", "fp16"])
+def test_hifigan_v2_narrow_stages(fp16):
+    """HiFi-GAN V2 narrows to 16 and 8 channels: those stages are carried zero-padded to the 32-channel granularity of
+    the tiles (zero weights and biases keep the padding at zero), so the result is the narrow decoder's."""
+    hp = HIFIGAN_V2_LIKE
+    G, sd = build(hp, 92)
+    G.set_option("fp16", fp16)
+    rs = np.random.RandomState(17)
+    z = torch.from_numpy(rs.standard_normal((2, hp.initial_channel, 37)).astype(np.float32))
+    ref = generator_forward_torch(hp, to_torch_state_dict(sd), z, None)
+    with torch.no_grad():
+        y = G(z.to(DEV))
+        G.set_option("fold", 0)
+        G.set_option("fuse_pairs", 0)
+        y_plain = G(z.to(DEV))
+    (check_fp16 if fp16 else check)(ref, y.cpu())
+    (check_fp16 if fp16 else check)(ref, y_plain.cpu())
+
+
+def test_unsupported_widths_fail_loudly():
+    """upsample_initial_channel itself must be a multiple of 32: a clear error, no fallback."""
+    hp = oracle.hparams.DecoderHParams(80, "1", (3,), ((1, 3, 5),), (2,), 48, (4,), 0)
     args, kw = hp.ctor_args()
     G = vitsdec.Generator(*args, **kw).to(DEV).eval()
     with pytest.raises(Exception, match="multiple of 32"):
