@@ -102,6 +102,8 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
  *          "pairf" = 0 keeps fused pairs on conv_pair.cu (default 1: time-folded conv_pairf.cu where it is faster);
  *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph);
+ *          "pdl" = 0 no programmatic dependent launch (default 1: launches whose grid leaves SMs idle let the next launch
+ *          of the stream start its prologue early; 2: every launch);
  *          "fp16" = 1 packs weights and stores activations as IEEE fp16 instead of bf16 (default 0).  Same tensor-core
  *          rate (tcgen05 kind::f16), fp32 accumulation, 10 instead of 7 stored mantissa bits; stored activations saturate
  *          at +-65504.  Changing it invalidates the loaded weights: every vitsdec_load_layer must be repeated before the

@@ -75,6 +75,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();   // see conv_tc_kernel: the next launch may start its prologue; activations are touched after pdl_wait()
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
@@ -108,6 +109,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       mbar_expect_tx(w_full, 2 * p.k * B_STAGE);
       for (int tap = 0; tap < 2 * p.k; ++tap) tma_load_3d(&tmW, w_full, smemW + tap * B_STAGE, 0, 0, tap);
+      pdl_wait();   // the weights (static) load while the previous launch drains; activations only from here on
       uint32_t sa = 0, pa = 0;   // stage / phase counters: a runtime i % NA is ~150 cycles of dependent integer code
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t tile = blockIdx.x + i * gridDim.x;
@@ -205,6 +207,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int L = p.L, C = CH;
     const float slope = p.slope, res_gain = p.res_gain;
     __nv_bfloat16* const out = p.out;
+    pdl_wait();   // output stores may overwrite a buffer the previous launch still reads
 
     // h = lrelu(c1 + b1), zero outside the utterance, written as c2's swizzled K-major A operand
     uint32_t hb = 0, ph = 0;   // epi1: h buffer / phase counters;  epi2: activation stage counter (no runtime i % N)
@@ -401,6 +404,7 @@ int plan_conv_pair(PairPlan* pl, int B, int L, int channels, int k, int dil, con
   p.div_m.init(p.m_tiles);
   p.trace = nullptr;
   pl->channels = channels;
+  pl->pdl = false;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + fixed + 256 + 1024 + 16384;
   if (encode_tmap_3d(&pl->tmA, x, channels, L, B, channels, 64, true)) return 1;
@@ -415,6 +419,20 @@ static int launch_pair_typed(const PairPlan& pl, cudaStream_t stream) {
     VD_CUDA(cudaFuncSetAttribute(conv_pair_kernel<CH, CH, NACC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024));
     attr_set = true;
+  }
+  if (pl.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(kPairThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    VD_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<CH, CH, NACC, F16>, pl.tmA, pl.tmW, pl.p));
+    return 0;
   }
   conv_pair_kernel<CH, CH, NACC, F16><<<pl.grid, kPairThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());

@@ -33,6 +33,7 @@ struct PairPlan {
   int nacc;         // 128-row accumulators per conv per tile (2, or 1 when shared memory is tight)
   int grid;
   size_t smem;
+  bool pdl;         // see ConvTcPlan::pdl
 };
 
 // true when both convs' weights, three activation stages and the h tile fit in shared memory

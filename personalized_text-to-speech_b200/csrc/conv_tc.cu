@@ -74,6 +74,11 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Programmatic dependent launch (small decodes, ConvTcPlan::pdl): the next launch of the stream may begin its prologue
+  // (barrier init, TMEM allocation, descriptor prefetch, bias staging -- nothing the previous kernel writes) on SMs this
+  // grid leaves idle; every access to activations comes after pdl_wait() below.
+  pdl_launch_dependents();
+
   if (warp == 0 && lane == 0) {
     for (int sg = 0; sg < p.g.nseg; ++sg) tma_prefetch_desc(&tm.a[sg]);
     tma_prefetch_desc(&tmW);
@@ -113,6 +118,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
             if ((p.g.tap_kmask[tap] >> kc) & 1u)
               tma_load_3d(&tmW, w_full, smemB + (slot++) * B_STAGE, kc * KC, 0, tap);
       }
+      pdl_wait();   // resident weights (static data) are already on their way; activations only from here on
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         uint32_t mb, nt, bq, mt, bu, rho;
         p.div_n.divmod(tile, mb, nt);
@@ -172,6 +178,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
     uint32_t itt = 0;
     uint32_t sa = 0, pa = 0, sb_next = 0, pb = 0;   // ring (stage, phase) counters, see the producer
+    pdl_wait();   // (this warp writes one row of a staged activation tile in the dilated folded view)
     if (p.stationary) {
       mbar_wait(w_full, 0);
       tc_fence_after();
@@ -281,6 +288,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     const int L = p.g.L, n_total = p.g.n_total, total_tiles = p.total_tiles, tile_step = gridDim.x;
     const float out_slope = p.ep.out_slope, mrf_scale = p.ep.mrf_scale, res_gain = p.ep.res_gain;
     ConvEpilogue ep = p.ep;
+    pdl_wait();   // residual reads and output stores depend on the previous launch
     auto coords = [&](int tile, int it, EpiItem& e) {
       uint32_t mb, nt, bq, mt;
       div_n.divmod(tile, mb, nt);
@@ -493,6 +501,20 @@ static int launch_typed(const ConvTcPlan& pl, cudaStream_t stream) {
                                  227 * 1024));
     attr_set = true;
   }
+  if (pl.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    VD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, EPI, SWAP, F16>, pl.tm, pl.tmW, pl.p));
+    return 0;
+  }
   conv_tc_kernel<BN, KC, EPI, SWAP, F16><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
@@ -547,6 +569,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   // of the shared-memory transposition.  It removes ~15 % of the SM's shared-memory traffic but its partial-sector
   // loads/stores cost far more: 11.97 vs 10.52 ms per 16 x 10 s step.
   pl->epi_smem = (desc_mode & 128) == 0;
+  pl->pdl = false;
   const int na_stream = (desc_mode & 32) ? 3 : ((desc_mode & 64) ? 4 : 2);  // experiment knob: activation stages when streaming
   desc_mode &= 1;
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");

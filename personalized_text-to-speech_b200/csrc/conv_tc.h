@@ -71,6 +71,8 @@ struct ConvTcPlan {
   bool no_res_prefetch;
   bool epi_smem;    // channels-as-M epilogue transposes through shared memory instead of registers (experiment knob)
   bool swap;        // channels-as-M variant (128 channels x 256 time rows per tile)
+  bool pdl;         // launch with the programmatic-serialization attribute (set by the decoder for launches that leave
+                    // SMs idle: the kernel's prologue then overlaps the previous launch of the stream)
   size_t smem;
 };
 

@@ -233,6 +233,7 @@ struct vitsdec_decoder {
   float* scale_scratch = nullptr;
   int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1, par = 1;
   int c_z = 0;   // initial_channel rounded up to a multiple of 32: the packed latent and conv_pre's K are zero-padded
+  int pdl = 1;   // option "pdl": programmatic dependent launch for launches that leave SMs idle (0 off, 2 every launch)
   int fp16 = 0;  // option "fp16": weights and stored activations are IEEE fp16 instead of bf16 (ConvEpilogue::f16)
   cudaStream_t cstream = nullptr;  // capture-only stream (the caller's may be the legacy default stream)
   cudaStream_t bstream[VITSDEC_MAX_KERNELS] = {};  // capture-only streams of MRF branches 1.. (Plan::par)
@@ -529,6 +530,15 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   pl.L_final = L;
   pl.C_final = d->stage_ch.back();
   pl.par = all_fused(d) && nk > 1 && d->par != 0;
+  // Programmatic dependent launch: a short launch (at most two tile rounds) lets the next launch of its stream run its
+  // prologue early (barrier init, TMEM allocation, descriptor prefetch, resident-weight loads: a few of the ~15 us a small
+  // launch takes).  Long launches gain nothing (one CTA per SM, no room for the dependent's CTAs) and measured slower.
+  for (Step& s : pl.steps) {
+    const int tiles = s.is_pair ? s.pair.p.total_tiles : s.tc.p.total_tiles;   // at most two tile rounds: a short launch
+    const bool on = d->impl == 0 && !s.is_pairf && (d->pdl == 2 || (d->pdl == 1 && tiles <= 2 * d->num_sms));
+    s.tc.pdl = on && !s.is_pair;
+    s.pair.pdl = on && s.is_pair;
+  }
   pl.post_tc = false;
   Layer& lp = d->layers[d->l_post];
   if (d->impl == 0 && d->fold && lp.fold_r && L % lp.fold_r == 0) {
@@ -897,7 +907,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, d->desc_mode * 128 + d->par * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
+    const PlanKey key{B, T, d->impl, d->desc_mode * 256 + d->pdl * 64 + d->par * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -1064,6 +1074,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "par")) d->par = value ? 1 : 0;
+  else if (!strcmp(key, "pdl")) d->pdl = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "fp16")) {
     // the 16-bit storage format of weights AND activations: packed weights of the other format are useless, so every
     // layer must be loaded again (the Python Generator re-folds by itself) and cached plans are dropped
@@ -1110,6 +1121,7 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   else if (!strcmp(key, "fold")) *value = d->fold;
   else if (!strcmp(key, "pairf")) *value = d->pairf;
   else if (!strcmp(key, "par")) *value = d->par;
+  else if (!strcmp(key, "pdl")) *value = d->pdl;
   else if (!strcmp(key, "fp16")) *value = d->fp16;
   else if (!strcmp(key, "hop")) *value = d->hop;
   else if (!strcmp(key, "num_sms")) *value = d->num_sms;

@@ -55,6 +55,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel of the stream (if it was launched with the programmatic-serialization attribute)
+// may start its prologue now; wait: block until the previous grid has completed and its memory is visible.  Both are
+// no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- 256-bit global accesses (sm_100: LDG/STG.E.256)
 // A thread that owns one row of a 32-row x 16-column bf16 item moves its whole 32-byte sector in one instruction, so the
 // row-owner register layout of a time-as-M epilogue needs no shared-memory transposition to reach full-sector accesses.

@@ -478,3 +478,23 @@ def test_unsupported_widths_fail_loudly():
     with pytest.raises(Exception, match="multiple of 32"):
         with torch.no_grad():
             G(torch.randn(1, 80, 8, device=DEV))
+
+
+def test_programmatic_dependent_launch_modes_agree():
+    """Option "pdl": short launches start their prologue under the previous launch of the stream (griddepcontrol); the
+    result must not depend on it -- plain launches (first uses of a plan) and the captured graph (third use on)."""
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 38)
+    outs = {}
+    for B, T in ((1, 40), (2, 173), (3, 300)):
+        z = torch.randn(B, hp.initial_channel, T, device=DEV)
+        g = torch.randn(B, hp.gin_channels, 1, device=DEV)
+        for pdl in (0, 1, 2):
+            G.set_option("pdl", pdl)
+            with torch.no_grad():
+                ys = [G(z, g).clone() for _ in range(5)]
+            assert all(torch.equal(ys[0], y) for y in ys[1:])
+            outs[pdl] = ys[0]
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = generator_forward_torch(hp, to_torch_state_dict(sd), z.cpu(), g.cpu())
+    check(ref, outs[1].cpu())
