@@ -184,7 +184,8 @@ VITSDEC_API const char* vitsdec_flow_layer_name(const vitsdec_flow* flow, int in
 VITSDEC_API int vitsdec_flow_load_layer(vitsdec_flow* flow, const char* name, const float* w_dev, const float* wg_dev,
                                         const float* bias_dev, void* stream);
 /* Options: "fp16" = 1 conv operands and stored activations are fp16 instead of bf16 (as the decoder's option; the latent
- * itself stays fp32 either way).  Changing it invalidates the loaded weights: load every layer again. */
+ * itself stays fp32 either way).  Changing it invalidates the loaded weights: load every layer again.
+ * "pdl" = 0 switches programmatic dependent launch off (default 1, as for the decoder). */
 VITSDEC_API int vitsdec_flow_set_option(vitsdec_flow* flow, const char* key, int value);
 VITSDEC_API size_t vitsdec_flow_workspace_bytes(const vitsdec_flow* flow, int batch, int frames);
 /* x_dev: fp32 [batch, channels, frames] with element strides (x_stride_b, x_stride_c, 1); x_mask_dev: fp32

@@ -209,6 +209,7 @@ struct vitsdec_flow {
   std::list<std::pair<std::tuple<int, int, const void*>, std::shared_ptr<FlowPlan>>> plans;
   cudaStream_t cstream = nullptr;   // capture-only stream
   int fp16 = 0;                     // vitsdec_flow_set_option("fp16"): conv operands / stored activations are fp16
+  int pdl = 1;                      // vitsdec_flow_set_option("pdl"): 0 = no programmatic dependent launch
 };
 
 namespace vd {
@@ -273,6 +274,9 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
       const bf16* xs[kMaxSeg] = {x, nullptr, nullptr, nullptr};
       if (plan_conv_tc(&s.tc, g, xs, cv.w, f->num_sms, 0, /*allow_swap=*/false)) return 1;
       s.ep = e;
+      // programmatic dependent launch (see decoder.cu): the flow's launches are all short; the small kernels between
+      // them (flip / cond / couple) neither trigger nor wait, which degrades to ordinary stream order around them
+      s.tc.pdl = f->pdl && s.tc.p.total_tiles <= 2 * f->num_sms;
       if (bind_residual_tc(s.tc, e)) return 1;
       pl.steps[ci].push_back(s);
       return 0;
@@ -464,6 +468,11 @@ int vitsdec_flow_set_option(vitsdec_flow* f, const char* key, int value) {
       for (FlowCoupling& c : f->cpl) c.loaded.clear();
       f->plans.clear();
     }
+    return 0;
+  }
+  if (!strcmp(key, "pdl")) {
+    if ((value != 0) != (f->pdl != 0)) f->plans.clear();
+    f->pdl = value ? 1 : 0;
     return 0;
   }
   set_error(std::string("unknown option ") + key);

@@ -87,7 +87,7 @@ class ResidualCouplingBlock(nn.Module):
         self._options[key] = int(value)
         if self._handle is not None:
             _capi.check(_capi.lib().vitsdec_flow_set_option(self._handle, key.encode(), int(value)), "flow set_option")
-        if changed:
+        if changed and key == "fp16":
             self._loaded_fingerprint = None
 
     def _fingerprint(self):

@@ -10,14 +10,16 @@ with torch.no_grad():
             p.uniform_(-0.07, 0.07)
 F = F.to("cuda:0").eval()
 F.assume_frozen = True
-for B, T in (((16, 862),) if once else ((1, 173), (1, 862), (16, 862))):
-    x = torch.randn(B, 192, T, device="cuda:0"); g = torch.randn(B, 256, 1, device="cuda:0"); m = torch.ones(B, 1, T, device="cuda:0")
-    with torch.no_grad():
-        for _ in range(1 if once else 5): F(x, m, g=g, reverse=True)
-        if once:
-            torch.cuda.synchronize(); break
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record()
-        for _ in range(30): F(x, m, g=g, reverse=True)
-        e1.record(); torch.cuda.synchronize()
-    print("flow reverse B=%d T=%d: %.3f ms" % (B, T, e0.elapsed_time(e1) / 30))
+for pdl in ((1,) if once else (0, 1)):
+  F.set_option("pdl", pdl)
+  for B, T in (((16, 862),) if once else ((1, 173), (1, 862), (16, 862))):
+      x = torch.randn(B, 192, T, device="cuda:0"); g = torch.randn(B, 256, 1, device="cuda:0"); m = torch.ones(B, 1, T, device="cuda:0")
+      with torch.no_grad():
+          for _ in range(1 if once else 5): F(x, m, g=g, reverse=True)
+          if once:
+              torch.cuda.synchronize(); break
+          e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          torch.cuda.synchronize(); e0.record()
+          for _ in range(30): F(x, m, g=g, reverse=True)
+          e1.record(); torch.cuda.synchronize()
+      print("flow reverse pdl=%d B=%d T=%d: %.3f ms" % (pdl, B, T, e0.elapsed_time(e1) / 30))
