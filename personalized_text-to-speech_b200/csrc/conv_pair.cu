@@ -420,11 +420,12 @@ static int launch_pair_typed(const PairPlan& pl, cudaStream_t stream) {
                                  227 * 1024));
     attr_set = true;
   }
+  const size_t smem = pl.smem > (size_t)120 * 1024 ? pl.smem : (size_t)120 * 1024;   // one CTA per SM, see conv_tc.cu
   if (pl.pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.grid);
     cfg.blockDim = dim3(kPairThreads);
-    cfg.dynamicSmemBytes = pl.smem;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -434,7 +435,7 @@ static int launch_pair_typed(const PairPlan& pl, cudaStream_t stream) {
     VD_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<CH, CH, NACC, F16>, pl.tmA, pl.tmW, pl.p));
     return 0;
   }
-  conv_pair_kernel<CH, CH, NACC, F16><<<pl.grid, kPairThreads, pl.smem, stream>>>(pl.tmA, pl.tmW, pl.p);
+  conv_pair_kernel<CH, CH, NACC, F16><<<pl.grid, kPairThreads, smem, stream>>>(pl.tmA, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -501,11 +501,16 @@ static int launch_typed(const ConvTcPlan& pl, cudaStream_t stream) {
                                  227 * 1024));
     attr_set = true;
   }
+  // More than half an SM's shared memory for EVERY launch of this kernel: CTAs of two overlapping launches (programmatic
+  // dependent launch, concurrent MRF branches) can then never share an SM, so a dependent's CTA can never take the TMEM
+  // columns that a CTA of the launch it waits for is about to allocate (deadlock).  Today the register file already
+  // forbids such co-residency; this makes it independent of the compiler's register count.
+  const size_t smem = pl.smem > (size_t)120 * 1024 ? pl.smem : (size_t)120 * 1024;
   if (pl.pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.grid);
     cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = pl.smem;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -515,7 +520,7 @@ static int launch_typed(const ConvTcPlan& pl, cudaStream_t stream) {
     VD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, EPI, SWAP, F16>, pl.tm, pl.tmW, pl.p));
     return 0;
   }
-  conv_tc_kernel<BN, KC, EPI, SWAP, F16><<<pl.grid, kTcThreads, pl.smem, stream>>>(pl.tm, pl.tmW, pl.p);
+  conv_tc_kernel<BN, KC, EPI, SWAP, F16><<<pl.grid, kTcThreads, smem, stream>>>(pl.tm, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
