@@ -632,7 +632,7 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
     for (int j = 0; j < hp->num_kernels; ++j, ++n) {
       const int k = hp->resblock_kernel_sizes[j];
       const int nd = hp->num_dilations[j];
-      VD_CHECK(k % 2 == 1 && k <= kMaxTaps, "resblock kernel sizes must be odd and <= 16");
+      VD_CHECK(k % 2 == 1 && k <= kMaxTaps, "resblock kernel sizes must be odd and <= 31");
       VD_CHECK(nd >= 1 && nd <= VITSDEC_MAX_DILATIONS, "bad dilation count");
       std::vector<int> ids;
       const std::string base = "resblocks." + std::to_string(n) + ".";
@@ -1229,7 +1229,7 @@ int vitsdec_op_conv1d(int device, const void* x, const float* w, const float* bi
                       float out_slope, void* y, int B, int L, int c_in, int c_out, int k, int dilation, int impl,
                       int desc_mode, void* stream) {
   VD_CHECK(x && w && y, "vitsdec_op_conv1d: null argument");
-  VD_CHECK(k % 2 == 1 && k <= kMaxTaps && k >= 1, "k must be odd and <= 16");
+  VD_CHECK(k % 2 == 1 && k <= kMaxTaps && k >= 1, "k must be odd and <= 31");
   Layer l;
   l.kind = kConv; l.c_in = c_in; l.c_out = c_out; l.k = k; l.dil = dilation;
   conv_geom(l);
