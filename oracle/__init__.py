@@ -24,6 +24,7 @@ container*: ``tests/golden/make_golden.py`` imports the unmodified
 the outputs under ``tests/golden/``; ``tests/test_oracle.py`` checks both oracle
 implementations against those fixtures.
 """
-from .hparams import DecoderHParams, FINETUNE_SPEAKER, UMA_TRILINGUAL, TINY, TINY_RB2  # noqa: F401
+from .hparams import (DecoderHParams, FINETUNE_SPEAKER, UMA_TRILINGUAL, TINY, TINY_RB2, HIFIGAN_V2,  # noqa: F401
+                      HIFIGAN_V3)
 from .weights import synth_state_dict, state_dict_keys, fold_weight_norm  # noqa: F401
 from .generator_np import generator_forward_np  # noqa: F401

@@ -49,3 +49,8 @@ UMA_TRILINGUAL = FINETUNE_SPEAKER
 # small shapes for fast CPU tests / committed golden vectors (not reference configs)
 TINY = DecoderHParams(64, "1", (3, 5), ((1, 3, 5), (1, 2, 3)), (4, 2), 128, (8, 4), 32)
 TINY_RB2 = DecoderHParams(64, "2", (3, 7), ((1, 3), (1, 2)), (4, 2), 128, (8, 4), 0)
+
+# Other HiFi-GAN shapes through the same constructor: the published V2 / V3 generator configurations
+# (jik876/hifi-gan config_v2.json / config_v3.json: mel input of 80 channels, no speaker conditioning)
+HIFIGAN_V2 = DecoderHParams(80, "1", (3, 7, 11), ((1, 3, 5), (1, 3, 5), (1, 3, 5)), (8, 8, 2, 2), 128, (16, 16, 4, 4), 0)
+HIFIGAN_V3 = DecoderHParams(80, "2", (3, 5, 7), ((1, 2), (2, 6), (3, 12)), (8, 8, 4), 256, (16, 16, 8), 0)

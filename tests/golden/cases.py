@@ -11,6 +11,9 @@ CASES = [
     ("tiny_rb2_b2_t13", oracle.TINY_RB2, 13, 2, 13, False),
     ("full_b2_t32", oracle.FINETUNE_SPEAKER, 21, 2, 32, True),
     ("full_b1_t7_nog", oracle.FINETUNE_SPEAKER, 22, 1, 7, False),
+    # other HiFi-GAN shapes through the reference's constructor (V2: stages down to 8 channels; V3: ResBlock2, 3 stages)
+    ("v2like_b1_t6", oracle.HIFIGAN_V2, 23, 1, 6, False),
+    ("v3like_b2_t5", oracle.HIFIGAN_V3, 24, 2, 5, False),
 ]
 
 

@@ -39,7 +39,10 @@ from tests.golden.cases import CASES, weight_checksum  # noqa: E402
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    only = sys.argv[1:]   # optional name filters: regenerate just the matching cases (the .npz bytes carry timestamps)
     for name, hp, seed, B, T, use_g in CASES:
+        if only and not any(o in name for o in only):
+            continue
         sd = oracle.synth_state_dict(hp, seed, gain=2.0)
         args, kw = hp.ctor_args()
         G = models_infer.Generator(*args, **kw).eval()
@@ -67,6 +70,8 @@ def main():
             out["g"] = g
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
+    if only:
+        return
     # per-op vectors straight from torch (the third-party arithmetic the reference composes)
     rs = np.random.RandomState(7)
     x = rs.standard_normal((2, 6, 17)).astype(np.float32)
