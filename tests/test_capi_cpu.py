@@ -80,3 +80,21 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_library_sass_is_tcgen05_and_tma():
+    """The built library's SASS (no GPU needed) carries the Blackwell mnemonics the design claims: tcgen05.mma (UTCHMMA)
+    with mbarrier commits (UTCBAR), TMEM loads (LDTM), TMEM allocation (UTCATOMSWS), TMA tensor loads (UTMALDG) and the
+    256-bit global stores of the pair kernel -- and no legacy mma.sync (HMMA) or wgmma path."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    _capi.lib()   # builds the library when this test runs first
+    sass = subprocess.run([exe, "-sass", _capi.library_path()], stdout=subprocess.PIPE, text=True, check=True).stdout
+    for mnemonic in ("UTCHMMA", "UTCBAR", "LDTM", "UTCATOMSWS", "UTMALDG", "STG.E.ENL2.256"):
+        assert mnemonic in sass, mnemonic
+    assert " HMMA." not in sass and "WGMMA" not in sass and "HGMMA" not in sass
+    kernels = [l for l in sass.splitlines() if "Function :" in l]
+    assert sum("conv_tc_kernel" in k for k in kernels) >= 40 and any("conv_pair_kernel" in k for k in kernels)
