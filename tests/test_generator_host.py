@@ -207,3 +207,37 @@ def test_options_are_remembered_until_a_native_handle_exists():
     F._loaded_fingerprint = ("stale",)
     F.set_option("fp16", 1)
     assert F._options == {"fp16": 1} and F._loaded_fingerprint is None and F._handle is None
+
+
+def test_zero_padded_channels_compute_the_narrow_decoder():
+    """The device carries stages narrower than 32 channels (HiFi-GAN V2) and latents whose width is not a multiple of 32
+    zero-padded to 32 (csrc/decoder.cu, Layer::cin_src / cout_src).  The claim behind it, checked on the CPU oracle: with
+    zero weights and zero biases on the padding, the padded decoder's output IS the narrow decoder's."""
+    hp = oracle.hparams.DecoderHParams(20, "1", (3, 5), ((1, 3, 5), (1, 2, 3)), (4, 2), 32, (8, 4), 0)   # stages 16, 8
+    sd = oracle.weights.fold_state_dict(oracle.synth_state_dict(hp, 77, gain=2.0))
+    rs = np.random.RandomState(3)
+    z = rs.standard_normal((2, hp.initial_channel, 9)).astype(np.float32)
+    ref = oracle.generator_forward_np(hp, sd, z, None, dtype=np.float64)
+
+    def pad(a, axes, to=32):
+        w = [(0, 0)] * a.ndim
+        for ax in axes:
+            w[ax] = (0, to - a.shape[ax])
+        return np.pad(a, w)
+
+    padded = {}
+    for k, v in sd.items():
+        if k == "conv_pre.weight":
+            padded[k] = pad(v, [1])                 # [c0, initial_channel -> 32, 7]
+        elif k == "conv_pre.bias":
+            padded[k] = v
+        elif k.startswith("ups.0.weight"):
+            padded[k] = pad(v, [1])                 # [c_in = c0 = 32, c_out 16 -> 32, k]
+        elif k.endswith(".weight"):
+            padded[k] = pad(v, [0, 1]) if k != "conv_post.weight" else pad(v, [1])
+        else:
+            padded[k] = pad(v, [0])                 # biases
+    zp = pad(z, [1])
+    got = oracle.generator_forward_np(hp, padded, zp, None, dtype=np.float64)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)                 # exact: the padding contributes exact zeros to every sum
