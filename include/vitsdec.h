@@ -107,7 +107,9 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
  *          "fp16" = 1 packs weights and stores activations as IEEE fp16 instead of bf16 (default 0).  Same tensor-core
  *          rate (tcgen05 kind::f16), fp32 accumulation, 10 instead of 7 stored mantissa bits; stored activations saturate
  *          at +-65504.  Changing it invalidates the loaded weights: every vitsdec_load_layer must be repeated before the
- *          next decode (vitsdec_decode fails with "no weights loaded" otherwise). */
+ *          next decode (vitsdec_decode fails with "no weights loaded" otherwise).
+ * Options are configuration, not per-call arguments: set them while no decode of this decoder is in flight (a schedule
+ * option drops the cached plans; "fp16" rewrites the packed weights a running decode would still be reading). */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
 
