@@ -2,12 +2,19 @@
 """Headline benchmark: decoded audio-seconds per second of the VITS waveform decoder (HiFi-GAN Generator).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a decoder
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (torch eager port)
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference Generator on the host cores
 
 One "step" = one decode of a batch of synthetic latents (BASELINE.json config 3: 16 utterances x 10 s,
 T = 862 frames, hop 256, 22.05 kHz, random-init weights of configs/finetune_speaker.json).  N > 1: one
 process per GPU (torchrun), every rank decodes its own 16 utterances (utterance sharding, no collective
 on the data path; "weak" scaling), time = max over ranks.  Prints ONE JSON line on rank 0.
+
+Extra keys of the same line (outside the headline metric): BASELINE config 4 as stated (256 x 10 s sharded 256/N per
+GPU, strong scaling, final waveform gather inside the timed region: "config4_strong"), config 5 (60 s utterance decoded
+in 512-frame chunks with recompute halos: "chunked_60s_audio_s_per_s"), config 2 latency with the module's DEFAULT
+settings, config 1 (the reference's SynthesizerTrn.infer on the host cores with the decoder's share) and the survey's
+"kernel to beat": the unmodified reference Generator through torch-eager cuDNN on the same B200 ("cudnn_eager_*").
+The reference itself is the byte-for-byte install under baseline/_ref (baseline/install_ref.py).
 """
 import argparse
 import json
@@ -98,28 +105,142 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference(batch, frames, steps, warmup, threads=None):
-    """The reference's CPU implementation of the path: torch eager conv1d/conv_transpose1d/leaky_relu/tanh with the
-    weight-norm recompute per forward (oracle/generator_torch.py restates models.py:270-289 op for op)."""
+def reference_dir():
+    d = os.path.join(ROOT, "baseline", "_ref")
+    return d if os.path.exists(os.path.join(d, "models.py")) else None
+
+
+def import_reference(name):
+    d = reference_dir()
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    import importlib
+    import warnings
+    warnings.filterwarnings("ignore", category=FutureWarning)   # old-style weight_norm deprecation notice
+    return importlib.import_module(name)
+
+
+def reference_generator(device="cpu"):
+    """The reference's own decoder, unmodified (baseline/_ref/models.py:244-296), built like models.py:447 builds it,
+    with the SAME weights bench.py gives the B200 decoder (seed 1234, weight_g perturbed)."""
+    import torch
+    import vitsdec
+    models = import_reference("models")
+    cargs, ckw = vitsdec.generator_args()
+    torch.manual_seed(1234)
+    G = models.Generator(*cargs, **ckw)
+    with torch.no_grad():
+        for name, p in G.named_parameters():
+            if name.endswith("weight_g"):
+                p.mul_(torch.empty_like(p).uniform_(0.5, 1.5))
+    return G.to(device).eval()
+
+
+def cpu_reference(batch, frames, steps, warmup, threads=None, budget_s=None):
+    """The reference's CPU implementation of the path on the host cores.  kind "reference": the unmodified
+    models.Generator from baseline/_ref; kind "port" (only when that install is missing): oracle/generator_torch.py,
+    the op-for-op torch restatement that tests/test_oracle.py pins bit-identical to it.
+    Returns (audio-s/s, seconds per pass, threads, kind, passes timed)."""
     import numpy as np
     import torch
-    import oracle
-    from oracle.generator_torch import generator_forward_torch, to_torch_state_dict
     # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the
     # reference to one thread)
     torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
-    hp = oracle.FINETUNE_SPEAKER
-    sd = to_torch_state_dict(oracle.synth_state_dict(hp, 0, gain=2.0))
     rs = np.random.RandomState(1)
-    z = torch.from_numpy(rs.standard_normal((batch, hp.initial_channel, frames)).astype(np.float32))
-    g = torch.from_numpy(rs.standard_normal((batch, hp.gin_channels, 1)).astype(np.float32))
+    z = torch.from_numpy(rs.standard_normal((batch, 192, frames)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((batch, 256, 1)).astype(np.float32))
+    if reference_dir() is not None:
+        G = reference_generator("cpu")
+        kind = "reference"
+
+        def run():
+            with torch.no_grad():
+                return G(z, g=g)
+    else:
+        import oracle
+        from oracle.generator_torch import generator_forward_torch, to_torch_state_dict
+        hp = oracle.FINETUNE_SPEAKER
+        sd = to_torch_state_dict(oracle.synth_state_dict(hp, 0, gain=2.0))
+        kind = "port"
+
+        def run():
+            return generator_forward_torch(hp, sd, z, g)
+    t0 = time.perf_counter()
     for _ in range(warmup):
-        generator_forward_torch(hp, sd, z, g)
+        run()
+    t_warm = (time.perf_counter() - t0) / max(1, warmup)
+    if budget_s is not None and warmup > 0:   # bounded: as many of the requested passes as fit the time budget
+        steps = max(1, min(steps, int(budget_s / max(t_warm, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
-        generator_forward_torch(hp, sd, z, g)
+        run()
     dt = (time.perf_counter() - t0) / steps
-    return batch * frames * HOP / SR / dt, dt, torch.get_num_threads()
+    return batch * frames * HOP / SR / dt, dt, torch.get_num_threads(), kind, steps
+
+
+def cudnn_eager(z, g, reps=3):
+    """The survey's "kernel to beat" (SURVEY.md 2.1 / 8d): the unmodified reference Generator through torch-eager cuDNN
+    on this B200, same weights and batch.  ms per step for strict fp32, torch's default fp32 (TF32 convs allowed) and
+    bf16 autocast; cudnn.benchmark on so that the library path gets its best algorithms."""
+    import torch
+    G = reference_generator(z.device)
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        for key, tf32, autocast in (("cudnn_eager_fp32_ms_per_step", False, False),
+                                    ("cudnn_eager_tf32_ms_per_step", True, False),
+                                    ("cudnn_eager_bf16_autocast_ms_per_step", True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                for _ in range(2):
+                    y = G(z, g=g)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    y = G(z, g=g)
+                e1.record()
+                torch.cuda.synchronize()
+            out[key] = e0.elapsed_time(e1) / reps
+            out[key.replace("_ms_per_step", "_out_dtype")] = str(y.dtype).replace("torch.", "")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = saved
+    del G
+    torch.cuda.empty_cache()
+    return out
+
+
+def infer_cpu(reps=2):
+    """BASELINE config 1: the reference's SynthesizerTrn.infer on the host cores (fp32, finetune_speaker.json
+    hyper-parameters, random init, batch 1, 50 synthetic symbols, sid 0) and the share of it spent in ``dec``."""
+    import torch
+    models = import_reference("models")
+    cfg = json.load(open(os.path.join(reference_dir(), "configs", "finetune_speaker.json")))
+    torch.manual_seed(1234)
+    net = models.SynthesizerTrn(68, cfg["data"]["filter_length"] // 2 + 1,
+                                cfg["train"]["segment_size"] // cfg["data"]["hop_length"],
+                                n_speakers=cfg["data"]["n_speakers"], **cfg["model"]).eval()
+    x = torch.randint(1, 68, (1, 50))
+    xl = torch.tensor([50])
+    sid = torch.tensor([0])
+    t_dec = [0.0]
+    t_in = [0.0]
+    h0 = net.dec.register_forward_pre_hook(lambda m, a: t_in.__setitem__(0, time.perf_counter()))
+    h1 = net.dec.register_forward_hook(lambda m, a, o: t_dec.__setitem__(0, t_dec[0] + time.perf_counter() - t_in[0]))
+    best = None
+    with torch.no_grad():
+        net.infer(x, xl, sid=sid, noise_scale=.667, noise_scale_w=0.8, length_scale=1)   # warm-up
+        for _ in range(reps):
+            t_dec[0] = 0.0
+            t0 = time.perf_counter()
+            o = net.infer(x, xl, sid=sid, noise_scale=.667, noise_scale_w=0.8, length_scale=1)[0]
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, t_dec[0], o.shape[-1] / SR)
+    h0.remove()
+    h1.remove()
+    return {"infer_cpu_s": best[0], "dec_share": best[1] / best[0], "infer_cpu_audio_s": best[2]}
 
 
 def main():
@@ -139,7 +260,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="utterances per GPU")
     ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--total-batch", type=int, default=256,
+                    help="BASELINE config 4: utterances sharded over all GPUs for the strong-scaling extra key (0 = skip)")
+    ap.add_argument("--micro-batch", type=int, default=64, help="utterances per decode call of the config-4 leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e only (A/B runs)")
     ap.add_argument("--quick", action="store_true",
                     help="profiling runs (ncu): warm-up + the device-resident timed loop only, no JSON line")
     args = ap.parse_args()
@@ -158,16 +283,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # bounded sample: ONE utterance of the same workload per step (the CPU needs seconds per utterance)
-        steps = max(1, min(args.steps, 3))
-        val, dt, cores = cpu_reference(1, frames, steps, 1)
+        # the WHOLE batch of the workload per step (16 x 10 s), every host thread; as many of the K requested passes as
+        # fit ~150 s of CPU time (a pass takes ~6 s on 16 cores)
+        val, dt, cores, kind, steps = cpu_reference(B, frames, max(1, args.steps), 1, budget_s=150.0)
         line = {"impl": "reference", "metric": "decoded audio-sec/sec, VITS Generator", "value": val,
                 "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                 "sample": "1 of the %d utterances (B=1, T=%d) per step, torch CPU eager fp32, "
-                                           "weight-norm recomputed per forward like the reference" % (B, frames)},
+                "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                                 "ref_install": "baseline/_ref (unmodified models.Generator)" if kind == "reference"
+                                 else "missing: oracle/generator_torch.py port",
+                                 "sample": "the whole batch (B=%d, T=%d) per step, %d timed passes after 1 warm-up (as "
+                                           "many of the requested %d as fit 150 s), torch CPU eager fp32"
+                                           % (B, frames, steps, args.steps)},
                 "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -248,73 +376,136 @@ def main():
         # in flight (vitsdec.HostPipeline: the copies of neighbouring steps overlap the decode of the current one)
         pipe = vitsdec.HostPipeline(G, depth=2)
         outs_host = [out_host, torch.empty_like(out_host).pin_memory()]
+        # N > 1: the final waveform gather (north_star: the one collective of the path) is part of every e2e step: an
+        # all_gather_into_tensor of the rank's fp32 waveforms, started from the decode's stream as soon as the decode is
+        # enqueued (NCCL runs it on its own stream), overlapping the D2H copy and the next batch's H2D + decode.
+        gathers = []
+        fulls = [torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev) for _ in range(2)] \
+            if world > 1 else None
+        step_no = [0]
+
+        def gather_hook(y, stream):
+            w = dist.all_gather_into_tensor(fulls[step_no[0] % 2], y, async_op=True)
+            gathers.append(w)
+            if len(gathers) > 2:
+                gathers.pop(0)
+            step_no[0] += 1
+
+        hook = gather_hook if world > 1 else None
         for i in range(8):   # each slot's plan reaches its graph (captured at the third use) before the timed region
-            pipe.submit(z_host, g_host, outs_host[i % 2])
+            pipe.submit(z_host, g_host, outs_host[i % 2], on_device=hook)
         pipe.wait_all()
+        for w in gathers:
+            w.wait()
         barrier()
         e0.record()
         for i in range(args.steps):
-            pipe.submit(z_host, g_host, outs_host[i % 2])
+            pipe.submit(z_host, g_host, outs_host[i % 2], on_device=hook)
         pipe.join()
+        for w in gathers:
+            w.wait()          # the current stream waits for the last gathers: they are inside the timed region
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-
-        # the stage before the decoder: flow(z_p, reverse) on the same batch, timed separately -- it is
-        # not part of the metric, which is the Generator decode alone
-        Fl = vitsdec.ResidualCouplingBlock(cargs[0], 192, 5, 1, 4, gin_channels=ckw["gin_channels"])
-        for name, p in Fl.named_parameters():
-            if name.endswith("post.weight"):
-                p.uniform_(-0.07, 0.07)  # the reference zero-initialises post: give the couplings something to do
-        Fl = Fl.to(dev).eval()
-        Fl.assume_frozen = True
-        ymask = torch.ones((B, 1, frames), device=dev)
-        for _ in range(3):
-            zf = Fl(z, ymask, g=g, reverse=True)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            zf = Fl(z, ymask, g=g, reverse=True)
-        e1.record()
-        barrier()
-        flow_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-
-        # BASELINE config 2 (batch 1, 2 s latent): latency of one decode, launch- and prologue-bound (extra key)
-        z1, g1 = z[:1, :, :173].contiguous(), g[:1]
-        for _ in range(5):
-            G(z1, g1)
-        barrier()
-        e0.record()
-        for _ in range(50):
-            G(z1, g1)
-        e1.record()
-        barrier()
-        lat_ms = max_over_ranks(e0.elapsed_time(e1)) / 50
-
-        # option "fp16" (fp16 instead of bf16 operands / stored activations; same kernels, same FLOPs): a short timed
-        # loop as an extra key.  The headline above is the bf16 mode BASELINE.json names.
-        G.set_option("fp16", 1)
-        for _ in range(4):
-            G(z, g)
-        barrier()
-        e0.record()
-        for _ in range(5):
-            G(z, g)
-        e1.record()
-        barrier()
-        fp16_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
-        G.set_option("fp16", 0)
-
+        extras = {}
         gather_ms = None
-        if world > 1:  # the optional final waveform gather (north_star): timed separately, not on the data path
-            full = torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(full, y)
+
+        def timed(fn, reps, warm):
+            for _ in range(warm):
+                fn()
             barrier()
             e0.record()
-            dist.all_gather_into_tensor(full, y)
+            for _ in range(reps):
+                fn()
             e1.record()
             barrier()
-            gather_ms = max_over_ranks(e0.elapsed_time(e1))
+            return max_over_ranks(e0.elapsed_time(e1)) / reps
+
+        if not args.no_extras:
+            # the stage before the decoder: flow(z_p, reverse) on the same batch, timed separately -- it
+            # is not part of the metric, which is the Generator decode alone
+            Fl = vitsdec.ResidualCouplingBlock(cargs[0], 192, 5, 1, 4, gin_channels=ckw["gin_channels"])
+            for name, p in Fl.named_parameters():
+                if name.endswith("post.weight"):
+                    p.uniform_(-0.07, 0.07)  # the reference zero-initialises post: give the couplings something to do
+            Fl = Fl.to(dev).eval()
+            Fl.assume_frozen = True
+            ymask = torch.ones((B, 1, frames), device=dev)
+            extras["flow_reverse_ms_per_step"] = timed(lambda: Fl(z, ymask, g=g, reverse=True), args.steps, 3)
+            del Fl
+
+            # BASELINE config 2 (batch 1, 2 s latent): latency of one decode, launch- and prologue-bound.  With the
+            # module's DEFAULT settings (per-call parameter-version check on) and with assume_frozen.
+            z1, g1 = z[:1, :, :173].contiguous(), g[:1]
+            G.assume_frozen = False
+            extras["latency_b1_2s_ms"] = timed(lambda: G(z1, g1), 50, 5)
+            G.assume_frozen = True
+            extras["latency_b1_2s_frozen_ms"] = timed(lambda: G(z1, g1), 50, 5)
+
+            # BASELINE config 5: one 60 s utterance (T = 5168) decoded in 512-frame chunks with recompute halos
+            # (vitsdec.decode_chunked; the exact receptive field, 13 frames; interior chunks run as one batch)
+            T60 = -(-int(round(60.0 * SR)) // HOP)
+            z60 = torch.from_numpy(np.random.RandomState(60 + rank).standard_normal((1, cargs[0], T60)).astype(np.float32)).to(dev)
+            ms60 = timed(lambda: vitsdec.decode_chunked(G, z60, g1, chunk_frames=512, hop=HOP), 10, 4)
+            extras["chunked_60s_audio_s_per_s"] = world * T60 * HOP / SR / (ms60 / 1e3)
+            extras["chunked_60s_ms"] = ms60
+            ms60u = timed(lambda: G(z60, g1), 10, 4)
+            extras["unchunked_60s_ms"] = ms60u
+            extras["chunked_60s_config"] = "T=%d, 512-frame chunks, halo %d frames each side (halo recompute %.1f %%), " \
+                                           "1 utterance per GPU" % (T60, G.receptive_halo(), 100.0 * 2 * G.receptive_halo() / 512)
+            del z60
+
+            # option "fp16" (fp16 instead of bf16 operands / stored activations; same kernels, same FLOPs): a short timed
+            # loop as an extra key.  The headline above is the bf16 mode BASELINE.json names.
+            G.set_option("fp16", 1)
+            extras["fp16_mode_ms_per_step"] = timed(lambda: G(z, g), 5, 4)
+            G.set_option("fp16", 0)
+            G(z, g)
+
+            # BASELINE config 4 as stated: 256 x 10 s sharded by utterance, 256/N per GPU (strong scaling), decoded in
+            # micro-batches, with the final fp32 waveform gather INSIDE the timed region (started after the last
+            # micro-batch; all ranks receive all 256 waveforms).  Device-resident inputs; max over ranks.
+            if args.total_batch > 0 and args.total_batch % world == 0:
+                n = args.total_batch // world
+                mb = min(n, max(1, args.micro_batch))
+                rs4 = np.random.RandomState(100 + rank)
+                z4 = torch.from_numpy(rs4.standard_normal((n, cargs[0], frames)).astype(np.float32)).to(dev)
+                g4 = torch.from_numpy(rs4.standard_normal((n, ckw["gin_channels"], 1)).astype(np.float32)).to(dev)
+                y4 = torch.empty((n, 1, frames * HOP), dtype=torch.float32, device=dev)
+                full4 = torch.empty((args.total_batch, 1, frames * HOP), dtype=torch.float32, device=dev) if world > 1 else None
+
+                def step4():
+                    for lo in range(0, n, mb):
+                        y4[lo:lo + mb] = G(z4[lo:lo + mb], g4[lo:lo + mb])
+                    if world > 1:
+                        dist.all_gather_into_tensor(full4, y4)
+
+                ms4 = timed(step4, max(2, min(args.steps, 5)), 3)
+                extras["config4_strong"] = {
+                    "workload": "Generator decode, %d x %.0f s latents sharded by utterance, %d per GPU in micro-batches "
+                                "of %d, final waveform all-gather inside the timed region" % (args.total_batch, args.seconds, n, mb),
+                    "scaling": "strong", "total_batch": args.total_batch, "per_gpu": n, "micro_batch": mb,
+                    "ms_per_step": ms4, "value": args.total_batch * frames * HOP / SR / (ms4 / 1e3), "unit": "audio-s/s",
+                    "tflops": args.total_batch * (frames * FLOP_PER_FRAME + FLOP_PER_UTT) / (ms4 / 1e3) / 1e12,
+                    "gather_bytes_per_rank": int(y4.numel() * 4) if world > 1 else 0}
+                del z4, g4, y4, full4
+                torch.cuda.empty_cache()
+
+            if world > 1:  # the gather alone, for reference
+                full = torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev)
+                gather_ms = timed(lambda: dist.all_gather_into_tensor(full, y), 3, 1)
+                del full
+            extras["graph_failed_plans"] = G.get_option("graph_failed")
+
+            # the survey's "kernel to beat" and BASELINE config 1, rank 0 of a 1-GPU run only (they are baselines)
+            if world == 1 and reference_dir() is not None:
+                try:
+                    extras.update(cudnn_eager(z, g))
+                    ms_ref = extras["cudnn_eager_bf16_autocast_ms_per_step"]
+                    extras["speedup_vs_cudnn_eager_bf16_autocast"] = ms_ref / (ms_total / args.steps)
+                    extras["speedup_vs_cudnn_eager_fp32"] = extras["cudnn_eager_fp32_ms_per_step"] / (ms_total / args.steps)
+                except Exception as e:   # a baseline leg must never take the headline down with it
+                    extras["cudnn_eager_error"] = repr(e)[:200]
 
     audio_s = world * B * frames * HOP / SR
     ms_step = ms_total / args.steps
@@ -346,17 +537,24 @@ def main():
                      "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"},
         "clocks": clocks,
     }
-    line["flow_reverse_ms_per_step"] = flow_ms
-    line["latency_b1_2s_ms"] = lat_ms
-    line["fp16_mode_ms_per_step"] = fp16_ms
+    line.update(extras)
     if gather_ms is not None:
         line["waveform_gather_ms"] = gather_ms
+    if world > 1:
+        line["e2e"]["includes_waveform_gather"] = True
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            val, dt, cores = cpu_reference(1, frames, 2, 1)
-            line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                    "sample": "1 of the %d utterances (B=1, T=%d), 2 timed passes after 1 warm-up, "
-                                              "torch CPU eager fp32 (oracle/generator_torch.py)" % (B, frames)}
+            val, dt, cores, kind, n = cpu_reference(1, frames, 2, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                                    "sample": "1 of the %d utterances (B=1, T=%d), %d timed passes after 1 warm-up, "
+                                              "torch CPU eager fp32, %s" % (B, frames, n,
+                                              "the unmodified reference Generator (baseline/_ref)" if kind == "reference"
+                                              else "oracle/generator_torch.py port")}
+            if not args.no_extras and reference_dir() is not None:
+                try:
+                    line.update(infer_cpu())
+                except Exception as e:
+                    line["infer_cpu_error"] = repr(e)[:200]
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -93,14 +93,22 @@ VITSDEC_API int vitsdec_decode(vitsdec_decoder* dec, const float* z_dev, int64_t
 VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, const float* g_host, float* out_host, int batch,
                         int frames);
 
-/* Options: "impl" = 0 tcgen05 tensor-core kernels (default), 1 CUDA-core cross-check kernels (tests only);
+/* Output side of cmd_inference.py:114-117 / VC_inference.py:49-51 (`.cpu().float().numpy()` -> wavfile.write): convert a
+ * decoded waveform (fp32, [-1, 1], `samples` contiguous values) to 16-bit PCM on the device --
+ * round-to-nearest(clip(x, -1, 1) * 32767) -- so that the D2H copy moves half the bytes and can land directly behind the
+ * WAV header of a pinned host buffer (personalized_text-to-speech_b200/wavout.py).  Asynchronous on `stream`. */
+VITSDEC_API int vitsdec_wav_pcm16(int device, const float* wav_dev, int16_t* pcm_dev, int64_t samples, void* stream);
+
+/* Options: "impl" = 0 tcgen05 tensor-core kernels (the only backend of libvitsdec.so); 1 = CUDA-core cross-check kernels,
+ *          accepted by the test build libvitsdec_test.so only (build.py: -DVITSDEC_TESTING);
  *          "desc_mode" = debug knob of the UMMA descriptor (0 is the correct setting);
  *          "debug_keep" = 1 keep named intermediates for vitsdec_debug_read; "profile" = 1 see below;
  *          "fuse_pairs" = 0 run every ResBlock conv as its own launch (default 1: fused pairs where they fit);
  *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph from the
  *          plan's third use on; 2: capture at the first use);
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
- *          "pairf" = 0 keeps fused pairs on conv_pair.cu (default 1: time-folded conv_pairf.cu where it is faster);
+ *          "pairf" = 2 runs fused pairs through the time-folded conv_pairf.cu wherever it exists (tests / experiments);
+ *          0 / 1 (default): conv_pair.cu -- the folded pair kernel is not preferred anywhere in the default schedule;
  *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph);
  *          "pdl" = 0 no programmatic dependent launch (default 1: launches whose grid leaves SMs idle let the next launch
  *          of the stream start its prologue early; 2: every launch);
@@ -111,6 +119,8 @@ VITSDEC_API int vitsdec_decode_host(vitsdec_decoder* dec, const float* z_host, c
  * Options are configuration, not per-call arguments: set them while no decode of this decoder is in flight (a schedule
  * option drops the cached plans; "fp16" rewrites the packed weights a running decode would still be reading). */
 VITSDEC_API int vitsdec_set_option(vitsdec_decoder* dec, const char* key, int value);
+/* get_option also reads: "hop", "num_sms", "testing_build", and "graph_failed" = number of launch plans whose CUDA-graph
+ * capture or instantiation failed (those plans run as plain launches; results are identical, batch-1 latency is not). */
 VITSDEC_API int vitsdec_get_option(const vitsdec_decoder* dec, const char* key, int* value);
 
 /* Option "profile"=1 brackets the convolution launches (the tcgen05 kernel) of every decode with CUDA

@@ -43,6 +43,7 @@ class VitsdecError(RuntimeError):
 
 
 _lib = None
+_lib_test = None
 _lock = threading.Lock()
 
 _vp, _i, _f, _sz, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_int64
@@ -60,6 +61,7 @@ SIGNATURES = {
     "vitsdec_workspace_bytes": (_sz, [_vp, _i, _i]),
     "vitsdec_decode": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "vitsdec_decode_host": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
+    "vitsdec_wav_pcm16": (_i, [_i, _vp, _vp, _i64, _vp]),
     "vitsdec_set_option": (_i, [_vp, _cp, _i]),
     "vitsdec_get_option": (_i, [_vp, _cp, ctypes.POINTER(_i)]),
     "vitsdec_last_launch_count": (_i, [_vp]),
@@ -85,36 +87,60 @@ def library_path():
     return _build.LIB
 
 
-def lib():
-    """Load (building first if needed) libvitsdec.so and declare the prototypes."""
-    global _lib
+def lib(testing=False):
+    """Load (building first if needed) libvitsdec.so and declare the prototypes.
+
+    testing=True loads libvitsdec_test.so instead: the same code plus the CUDA-core cross-check backend (option
+    impl=1).  Only the GPU tests ask for it (Generator.set_option("impl", 1), ops.*(impl=1)); the product library has
+    no second backend."""
+    global _lib, _lib_test
+    if testing:
+        if _lib_test is not None:
+            return _lib_test
+        lib()  # builds / freshness check
+        with _lock:
+            if _lib_test is None:
+                L = ctypes.CDLL(_build.LIB_TEST)
+                _declare(L)
+                _lib_test = L
+        return _lib_test
     if _lib is not None:
         return _lib
     with _lock:
         if _lib is not None:
             return _lib
         path = os.environ.get("VITSDEC_LIB") or _build.LIB   # VITSDEC_LIB: A/B two builds on one box (tools/ab.sh)
-        if not os.path.exists(path):
+        if not os.environ.get("VITSDEC_LIB") and not _build.is_fresh():
+            # missing, or older than csrc/ + include/ (source digest in csrc/.build_stamp): rebuild rather than load a
+            # stale binary silently (*.so is git-ignored but ships in-tree)
             try:
                 _build.build()
-            except Exception as e:  # no nvcc and no prebuilt library: nothing to run the decoder with
-                raise ImportError(
-                    "vitsdec: %s is missing and could not be built (%s). There is no CPU/PyTorch "
-                    "fallback for the decoder." % (path, e))
+            except Exception as e:
+                if not os.path.exists(path):  # no nvcc and no prebuilt library: nothing to run the decoder with
+                    raise ImportError(
+                        "vitsdec: %s is missing and could not be built (%s). There is no CPU/PyTorch "
+                        "fallback for the decoder." % (path, e))
+                import warnings
+                warnings.warn("vitsdec: %s is older than its sources and could not be rebuilt (%s); loading it anyway"
+                              % (path, e))
         L = ctypes.CDLL(path)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)  # AttributeError here = ABI drift between header and library
-            fn.restype = res
-            fn.argtypes = args
-        if L.vitsdec_abi_version() != 1:
-            raise ImportError("vitsdec: ABI version mismatch")
+        _declare(L)
         _lib = L
     return _lib
 
 
-def check(rc, what=""):
+def _declare(L):
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError here = ABI drift between header and library
+        fn.restype = res
+        fn.argtypes = args
+    if L.vitsdec_abi_version() != 1:
+        raise ImportError("vitsdec: ABI version mismatch")
+
+
+def check(rc, what="", L=None):
     if rc != 0:
-        msg = lib().vitsdec_last_error()
+        msg = (L or lib()).vitsdec_last_error()
         raise VitsdecError("%s: %s" % (what or "vitsdec", msg.decode() if msg else "unknown error"))
 
 

@@ -11,9 +11,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libvitsdec.so")
+LIB = os.path.join(HERE, "libvitsdec.so")            # the product: tcgen05 / TMA kernels only
+LIB_TEST = os.path.join(HERE, "libvitsdec_test.so")  # + the CUDA-core cross-check backend (option impl=1), tests only
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["decoder.cu", "conv_tc.cu", "conv_pair.cu", "conv_pairf.cu", "conv_simt.cu", "pack.cu", "flow.cu"]
+SOURCES = ["decoder.cu", "conv_tc.cu", "conv_pair.cu", "conv_pairf.cu", "pack.cu", "flow.cu"]
+# Test build: the same objects, except that decoder.cu is compiled with -DVITSDEC_TESTING (which is what makes impl=1
+# reachable) and conv_simt.cu, the CUDA-core restatement of the conv primitive, is linked in.  The product library has
+# no second backend (north_star: "no multi-backend dispatch").
+TEST_ONLY_SOURCES = ["conv_simt.cu"]
+TEST_RECOMPILED = ["decoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
@@ -46,7 +52,8 @@ def _digest():
 
 
 def is_fresh():
-    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == _digest()
+    return (os.path.exists(LIB) and os.path.exists(LIB_TEST) and os.path.exists(STAMP)
+            and open(STAMP).read().strip() == _digest())
 
 
 def build(force=False, verbose=False):
@@ -54,26 +61,38 @@ def build(force=False, verbose=False):
     if not force and is_fresh():
         return LIB
     nvcc = _nvcc()
-    objs = []
+    objs, objs_test = [], []
     log = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+
+    def compile_(src, suffix, extra):
+        obj = os.path.join(HERE, "build", src.replace(".cu", suffix + ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        return obj
+
+    for src in SOURCES:
+        obj = compile_(src, "", [])
         objs.append(obj)
+        if src in TEST_RECOMPILED:
+            objs_test.append(compile_(src, "_test", ["-DVITSDEC_TESTING=1"]))
+        else:
+            objs_test.append(obj)
+    for src in TEST_ONLY_SOURCES:
+        objs_test.append(compile_(src, "_test", ["-DVITSDEC_TESTING=1"]))
     for src, cmd, p in procs:
         out, _ = p.communicate()
         log.append(out)
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on %s: %s" % (src, " ".join(cmd)))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
-    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if out.returncode != 0:
-        sys.stderr.write(out.stdout)
-        raise RuntimeError("link failed: " + " ".join(cmd))
+    for lib, obj_list in ((LIB, objs), (LIB_TEST, objs_test)):
+        cmd = [nvcc, "-shared", "-o", lib] + obj_list + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if out.returncode != 0:
+            sys.stderr.write(out.stdout)
+            raise RuntimeError("link failed: " + " ".join(cmd))
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     with open(STAMP, "w") as f:

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <list>
 #include <map>
@@ -38,7 +39,7 @@
 namespace vd {
 
 static thread_local std::string g_err;
-static unsigned long long* g_trace_buffer = nullptr;  // vitsdec_debug_set_trace: device buffer [256][8] of clock64 stamps
+static std::atomic<unsigned long long*> g_trace_buffer{nullptr};  // vitsdec_debug_set_trace: device buffer of clock64 stamps
 void set_error(const std::string& msg) { g_err = msg; }
 
 typedef __nv_bfloat16 bf16;
@@ -62,7 +63,6 @@ struct Layer {
   bool loaded = false;
   // kMrf (virtual layer): the last convs of one stage's MRF branches, accumulated in one launch
   std::vector<int> members;      // real layer ids, one per branch
-  bool bias_dirty = false;       // combined bias = sum of member biases, rebuilt lazily
   int mrf_group = -1;            // real layers: id of the virtual layer they also feed, and their tap base in it
   int mrf_tap_base = 0;
   int pair_group = -1;           // real layers: id of the fused-pair virtual layer (kPair) and their tap base in it
@@ -197,7 +197,7 @@ struct Plan {
   // Capturing + instantiating the graph costs ~12 ms (a batch-1 decode takes 0.5 ms): a plan is replayed as a graph
   // only from its third use on, so a serving loop whose shape changes every call (tools/shape_churn.py: 12.1 ms per
   // new shape with eager capture, 1.3 ms with plain launches) never pays for graphs it will not reuse.
-  int uses = 0;
+  std::atomic<int> uses{0};
   // Concurrent MRF branches: small decodes (a 2 s utterance has 12-170 tiles per launch for 148 SMs) are bound by
   // launch latency and under-filled kernels; the three branches of a stage are independent, so under the CUDA graph
   // they run on forked streams: 0.84 -> 0.53 ms at 173 frames, 1.19 -> 0.96 ms at 862, neutral to -1.5 % at 16 x 862
@@ -239,12 +239,15 @@ struct vitsdec_decoder {
   cudaStream_t bstream[VITSDEC_MAX_KERNELS] = {};  // capture-only streams of MRF branches 1.. (Plan::par)
   cudaEvent_t ev_fork = nullptr, ev_join[VITSDEC_MAX_KERNELS] = {};
   std::map<std::pair<int, int>, int> l_pair;  // (resblock index, pair index) -> kPair virtual layer id
-  int last_launches = 0;
+  std::atomic<int> last_launches{0};
+  std::atomic<int> graph_failures{0};   // plans whose CUDA-graph capture / instantiation failed (they run as plain launches)
+  int max_dil = 1;                      // largest ResBlock dilation: sizes the slack behind the last workspace slot
   // profile=1: CUDA events around the convolution launches of every decode, accumulated on read
   cudaEvent_t ev_conv0 = nullptr, ev_conv1 = nullptr;
   bool ev_pending = false;
   double prof_conv_ms = 0.0;
   long prof_conv_launches = 0;
+  std::mutex prof_mu;                   // guards the four profile fields above (option "profile" is a single-stream bench hook)
   std::mutex mu;
   std::list<std::pair<PlanKey, std::shared_ptr<Plan>>> plans;  // small LRU
   std::shared_ptr<Plan> last_plan;
@@ -340,7 +343,8 @@ static WsLayout ws_layout(const vitsdec_decoder* d, int B, int T) {
   w.off_slots = o; o += (size_t)w.nslots * slot;
   w.off_dbg = o;
   if (d->debug_keep) o += align_up(dbg, 1024);
-  o += 4096;  // dilated folded views read (and mask) up to rho_d*r rows past the last utterance of a slot
+  // dilated folded views read (and mask) up to rho_d*r rows (= 256 * dilation bytes) past the last utterance of a slot
+  o += align_up((size_t)256 * d->max_dil + 1024, 4096);
   w.total = o;
   return w;
 }
@@ -571,7 +575,12 @@ static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
     return launch_conv_pair(s.pair, d->layers[ly.members[0]].bias, d->layers[ly.members[1]].bias, kSlope, s.ep.out, st,
                             d->fp16);
   if (d->impl == 0) return launch_conv_tc(s.tc, s.ep, st);
-  return launch_conv_simt(s.tc.p.g, s.ep, s.xs, ly.w, st);
+#ifdef VITSDEC_TESTING
+  return launch_conv_simt(s.tc.p.g, s.ep, s.xs, ly.w, st);   // CUDA-core cross-check: test build only (build.py)
+#else
+  set_error("impl=1 (CUDA-core cross-check kernels) exists only in the test build libvitsdec_test.so");
+  return 1;
+#endif
 }
 
 }  // namespace vd
@@ -598,7 +607,8 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
   DeviceGuard guard(device);
   VD_CHECK(guard.ok, "cudaSetDevice failed");
 
-  std::unique_ptr<vitsdec_decoder> d(new vitsdec_decoder());
+  // every error return below frees what was allocated so far (vitsdec_destroy tolerates a half-built decoder)
+  std::unique_ptr<vitsdec_decoder, void (*)(vitsdec_decoder*)> d(new vitsdec_decoder(), vitsdec_destroy);
   d->hp = *hp;
   d->device = device;
   d->num_sms = prop.multiProcessorCount;
@@ -634,10 +644,15 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
       const int nd = hp->num_dilations[j];
       VD_CHECK(k % 2 == 1 && k <= kMaxTaps, "resblock kernel sizes must be odd and <= 31");
       VD_CHECK(nd >= 1 && nd <= VITSDEC_MAX_DILATIONS, "bad dilation count");
+      for (int m = 0; m < nd; ++m) {
+        VD_CHECK(hp->resblock_dilation_sizes[j][m] >= 1 && hp->resblock_dilation_sizes[j][m] <= 64,
+                 "resblock dilations must be in 1..64");
+        d->max_dil = std::max(d->max_dil, hp->resblock_dilation_sizes[j][m]);
+      }
       std::vector<int> ids;
       const std::string base = "resblocks." + std::to_string(n) + ".";
       if (hp->resblock == 1) {
-        VD_CHECK(nd == 3, "ResBlock1 takes exactly 3 dilations (modules.py:188)");
+        VD_CHECK(nd >= 3, "ResBlock1 needs 3 dilations (modules.py:188-196 indexes dilation[0..2])");   // extras are ignored, like the reference
         std::vector<int> c1, c2;
         for (int m = 0; m < 3; ++m)
           c1.push_back(add_layer(d.get(), base + "convs1." + std::to_string(m), kConv, ch, ch, k,
@@ -836,7 +851,13 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
                                 v.wfold + (size_t)l.mrf_ftap_base * v.fgeom.n_total * v.fgeom.c_in, l.c_in, co_s,
                                 l.k, v.fold_r, st, 0, d->fp16, ci_s))
         return 1;
-      v.bias_dirty = true;
+      // combined bias of the fused launch = sum of the member biases (unloaded members still hold zeros), rebuilt HERE
+      // on the load stream -- which the caller synchronises -- so that no load-time work is ever deferred into a decode
+      // (a concurrent first decode on another stream could have read it before the deferred kernel ran)
+      const float* bs[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
+      for (size_t j = 0; j < v.members.size(); ++j) bs[j] = d->layers[v.members[j]].bias;
+      if (launch_sum_bias(bs[0], bs[1], bs[2], bs[3], v.bias, v.c_out, st)) return 1;
+      if (v.fold_r && launch_replicate_bias(v.bias, v.bias_fold, v.c_out, v.fold_r, st)) return 1;
     }
     if (l.pair_group >= 0) {
       Layer& v = d->layers[l.pair_group];
@@ -890,19 +911,6 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     VD_CHECK(d->layers[i].loaded, "vitsdec_decode: layer " + d->layers[i].name + " has no weights loaded");
   DeviceGuard guard(d->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  {
-    std::lock_guard<std::mutex> lock(d->mu);
-    for (size_t i = d->num_real_layers; i < d->layers.size(); ++i) {
-      Layer& v = d->layers[i];
-      if (v.kind != kMrf || !v.bias_dirty) continue;
-      const float* bs[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
-      for (size_t j = 0; j < v.members.size(); ++j) bs[j] = d->layers[v.members[j]].bias;
-      if (launch_sum_bias(bs[0], bs[1], bs[2], bs[3], v.bias, v.c_out, st)) return 1;
-      if (v.fold_r && launch_replicate_bias(v.bias, v.bias_fold, v.c_out, v.fold_r, st)) return 1;
-      v.bias_dirty = false;
-    }
-  }
-
   std::shared_ptr<Plan> plan;
   {
     std::lock_guard<std::mutex> lock(d->mu);
@@ -924,6 +932,9 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
     d->last_plan = plan;
   }
 
+  // option "profile": one pair of events per decoder, so profiled decodes are serialised (a bench hook, not a serving mode)
+  std::unique_lock<std::mutex> prof_lock(d->prof_mu, std::defer_lock);
+  if (d->profile) prof_lock.lock();
   int launches = 0;
   if (launch_pack_z(z, zsb, zsc, plan->a0, B, d->hp.initial_channel, T, st, d->fp16, d->c_z)) return 1;
   ++launches;
@@ -1001,7 +1012,8 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
       if (!ok) {
         cudaGetLastError();
         exec = nullptr;
-        plan->graph_failed = true;  // fall back to plain launches for this plan
+        plan->graph_failed = true;  // this plan runs as plain launches from now on; visible as option "graph_failed"
+        d->graph_failures.fetch_add(1);
       }
     }
     if (exec) {
@@ -1063,10 +1075,24 @@ int vitsdec_decode_host(vitsdec_decoder* d, const float* z, const float* g, floa
   return 0;
 }
 
+int vitsdec_wav_pcm16(int device, const float* wav_dev, int16_t* pcm_dev, int64_t samples, void* stream) {
+  VD_CHECK(samples >= 0 && (samples == 0 || (wav_dev && pcm_dev)), "vitsdec_wav_pcm16: null argument");
+  DeviceGuard guard(device);
+  VD_CHECK(guard.ok, "cudaSetDevice failed");
+  return launch_pcm16(wav_dev, pcm_dev, (long)samples, static_cast<cudaStream_t>(stream));
+}
+
 int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   VD_CHECK(d && key, "vitsdec_set_option: null argument");
   std::lock_guard<std::mutex> lock(d->mu);
-  if (!strcmp(key, "impl")) { VD_CHECK(value == 0 || value == 1, "impl: 0 (tcgen05) or 1 (simt)"); d->impl = value; }
+  if (!strcmp(key, "impl")) {
+#ifdef VITSDEC_TESTING
+    VD_CHECK(value == 0 || value == 1, "impl: 0 (tcgen05) or 1 (simt)");
+#else
+    VD_CHECK(value == 0, "impl=1 (CUDA-core cross-check kernels) exists only in the test build libvitsdec_test.so");
+#endif
+    d->impl = value;
+  }
   else if (!strcmp(key, "desc_mode")) d->desc_mode = value;
   else if (!strcmp(key, "debug_keep")) d->debug_keep = value ? 1 : 0;
   else if (!strcmp(key, "fuse_pairs")) d->fuse_pairs = value ? 1 : 0;
@@ -1087,6 +1113,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
     }
   }
   else if (!strcmp(key, "profile")) {
+    std::lock_guard<std::mutex> pl(d->prof_mu);
     d->profile = value ? 1 : 0;
     d->prof_conv_ms = 0.0;
     d->prof_conv_launches = 0;
@@ -1099,6 +1126,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
 int vitsdec_profile_read(vitsdec_decoder* d, double* conv_ms, int64_t* conv_launches) {
   VD_CHECK(d && conv_ms && conv_launches, "vitsdec_profile_read: null argument");
   DeviceGuard guard(d->device);
+  std::lock_guard<std::mutex> pl(d->prof_mu);
   if (d->ev_pending) {
     float ms = 0.f;
     VD_CUDA(cudaEventSynchronize(d->ev_conv1));
@@ -1123,13 +1151,21 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   else if (!strcmp(key, "par")) *value = d->par;
   else if (!strcmp(key, "pdl")) *value = d->pdl;
   else if (!strcmp(key, "fp16")) *value = d->fp16;
+  else if (!strcmp(key, "graph_failed")) *value = d->graph_failures.load();
+  else if (!strcmp(key, "testing_build")) {
+#ifdef VITSDEC_TESTING
+    *value = 1;
+#else
+    *value = 0;
+#endif
+  }
   else if (!strcmp(key, "hop")) *value = d->hop;
   else if (!strcmp(key, "num_sms")) *value = d->num_sms;
   else { set_error(std::string("unknown option ") + key); return 1; }
   return 0;
 }
 
-int vitsdec_last_launch_count(const vitsdec_decoder* d) { return d ? d->last_launches : 0; }
+int vitsdec_last_launch_count(const vitsdec_decoder* d) { return d ? d->last_launches.load() : 0; }
 
 int vitsdec_debug_read(vitsdec_decoder* d, const char* name, float* out, size_t out_elems, int* channels, int* length,
                        void* stream) {
@@ -1207,11 +1243,16 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
       ConvTcPlan pl{};
       const bf16* xs[kMaxSeg] = {static_cast<const bf16*>(x), nullptr, nullptr, nullptr};
       rc = plan_conv_tc(&pl, g, xs, fold ? l.wfold : l.w, prop.multiProcessorCount, desc_mode);
-      pl.p.trace = g_trace_buffer;
+      pl.p.trace = g_trace_buffer.load();
       rc = rc || launch_conv_tc(pl, e, st);
     } else {
+#ifdef VITSDEC_TESTING
       const bf16* xs[kMaxSeg] = {static_cast<const bf16*>(x), nullptr, nullptr, nullptr};
       rc = launch_conv_simt(g, e, xs, l.w, st);
+#else
+      set_error("impl=1 (CUDA-core cross-check kernels) exists only in the test build libvitsdec_test.so");
+      rc = 1;
+#endif
     }
   }
   cudaError_t se = cudaStreamSynchronize(st);
@@ -1221,7 +1262,7 @@ static int op_conv_common(int device, Layer& l, const void* x, const float* w, c
 }
 
 int vitsdec_debug_set_trace(void* trace_dev) {
-  g_trace_buffer = static_cast<unsigned long long*>(trace_dev);
+  g_trace_buffer.store(static_cast<unsigned long long*>(trace_dev));
   return 0;
 }
 
@@ -1261,7 +1302,7 @@ int vitsdec_op_resblock_pair(int device, const void* x, const float* w1, const f
   if (!rc) {
     PairPlan pl{};
     rc = plan_conv_pair(&pl, B, L, channels, k, dilation, static_cast<const bf16*>(x), w, prop.multiProcessorCount);
-    pl.p.trace = g_trace_buffer;
+    pl.p.trace = g_trace_buffer.load();
     rc = rc || launch_conv_pair(pl, bias, bias + channels, slope, static_cast<bf16*>(y), st);
   }
   cudaError_t se = cudaStreamSynchronize(st);
@@ -1295,7 +1336,7 @@ int vitsdec_op_resblock_pair_folded(int device, const void* x, const float* w1, 
   if (!rc) {
     PairFPlan pl{};
     rc = plan_conv_pairf(&pl, B, L, channels, k, dilation, static_cast<const bf16*>(x), w, prop.multiProcessorCount);
-    pl.p.trace = g_trace_buffer;
+    pl.p.trace = g_trace_buffer.load();
     rc = rc || launch_conv_pairf(pl, bias, bias + channels, slope, static_cast<bf16*>(y), st);
   }
   cudaError_t se = cudaStreamSynchronize(st);

@@ -23,7 +23,9 @@ __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __rest
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
-    scale[r] = g != nullptr ? g[r] / sqrtf(t) : 1.f;
+    // an all-zero row (pruned / dead channel of a remove_weight_norm checkpoint re-expressed as v = w, g = ||w|| = 0):
+    // 0 * v = 0 like the reference's folded weight, not 0/0 = NaN
+    scale[r] = g != nullptr ? (t > 0.f ? g[r] / sqrtf(t) : 0.f) : 1.f;
   }
 }
 
@@ -213,6 +215,28 @@ __global__ void unpack_debug_kernel(const __nv_bfloat16* __restrict__ a, float g
 }
 
 // ------------------------------------------------------------------------------------------ launchers
+// Output side (cmd_inference.py:114-117): waveform fp32 [-1, 1] -> 16-bit PCM on the device, so that the D2H copy moves
+// half the bytes and lands directly behind the WAV header in a pinned host buffer.  round-to-nearest-even of
+// clip(x, -1, 1) * 32767, the usual float -> int16 export; 8 samples per thread, 16-byte stores.
+__global__ void pcm16_kernel(const float* __restrict__ wav, int16_t* __restrict__ out, long n) {
+  const long i8 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i8 + 8 <= n && (reinterpret_cast<uintptr_t>(out + i8) & 15) == 0 && (reinterpret_cast<uintptr_t>(wav + i8) & 15) == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(wav + i8), b = *reinterpret_cast<const float4*>(wav + i8 + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int lo = __float2int_rn(fminf(fmaxf(v[2 * j], -1.f), 1.f) * 32767.f);
+      const int hi = __float2int_rn(fminf(fmaxf(v[2 * j + 1], -1.f), 1.f) * 32767.f);
+      pk[j] = ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu);
+    }
+    *reinterpret_cast<uint4*>(out + i8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  } else {
+    for (long i = i8; i < n && i < i8 + 8; ++i)
+      out[i] = (int16_t)__float2int_rn(fminf(fmaxf(wav[i], -1.f), 1.f) * 32767.f);
+  }
+}
+
 int launch_wn_scale(const float* v, const float* g, float* scale, int rows, int inner, cudaStream_t st) {
   wn_scale_kernel<<<rows, 256, 0, st>>>(v, g, scale, inner);
   VD_CUDA(cudaGetLastError());
@@ -258,6 +282,13 @@ int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int
 int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaStream_t st, int c_out_src) {
   replicate_bias_kernel<<<(c_out * reps + 255) / 256, 256, 0, st>>>(b, out, c_out, reps,
                                                                     c_out_src > 0 ? c_out_src : c_out);
+  VD_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_pcm16(const float* wav, int16_t* out, long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long threads = (n + 7) / 8;
+  pcm16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(wav, out, n);
   VD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,7 @@ int launch_pack_conv_fold(const float* w, const float* scale, __nv_bfloat16* wp,
 int launch_pack_convT(const float* w, const float* scale, __nv_bfloat16* wp, int c_in, int c_out, int k, int s, int p,
                       int ntaps, int off0, cudaStream_t st, int f16 = 0, int c_in_src = 0, int c_out_src = 0);
 int launch_replicate_bias(const float* b, float* out, int c_out, int reps, cudaStream_t st, int c_out_src = 0);
+int launch_pcm16(const float* wav, int16_t* out, long n, cudaStream_t st);
 int launch_sum_bias(const float* b0, const float* b1, const float* b2, const float* b3, float* out, int n,
                     cudaStream_t st);
 int launch_pack_z(const float* z, long sb, long sc, __nv_bfloat16* out, int B, int C, int T, cudaStream_t st,

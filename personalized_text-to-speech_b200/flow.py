@@ -76,9 +76,13 @@ class ResidualCouplingBlock(nn.Module):
         self._handle = None
         self._handle_device = None
         self._loaded_fingerprint = None
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()   # held across weight sync AND the decode enqueue, see generator.py
         self.assume_frozen = False
         self._options = {}
+        self._plist = None
+        self._dirty = True
+        self._ws = {}
+        self._register_load_state_dict_pre_hook(self._mark_dirty)
 
     def set_option(self, key, value):
         """fp16: 1 = fp16 instead of bf16 conv operands / stored activations (the latent stays fp32 either way);
@@ -90,8 +94,32 @@ class ResidualCouplingBlock(nn.Module):
         if changed and key == "fp16":
             self._loaded_fingerprint = None
 
+    def _mark_dirty(self, *args):
+        self._dirty = True
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._plist = None
+        self._dirty = True
+        self._ws = {}
+        return out
+
     def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Sum of the parameters' version counters over a cached list (see Generator._fingerprint)."""
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        pl = self._plist
+        return (len(pl), sum(p._version for p in pl), pl[0].data_ptr(), pl[-1].data_ptr())
+
+    def _workspace(self, device, nbytes):
+        key = torch.cuda.current_stream(device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            if ws is None and len(self._ws) >= 4:
+                self._ws.pop(next(iter(self._ws)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
 
     def _sync_native(self, device):
         lib = _capi.lib()
@@ -108,9 +136,10 @@ class ResidualCouplingBlock(nn.Module):
             for k, v in self._options.items():
                 _capi.check(lib.vitsdec_flow_set_option(self._handle, k.encode(), v), "flow set_option")
         fp = None
-        if self._loaded_fingerprint is None or not self.assume_frozen:
+        if self._loaded_fingerprint is None or self._dirty or not self.assume_frozen:
             fp = self._fingerprint()
         if self._loaded_fingerprint is None or (fp is not None and fp != self._loaded_fingerprint):
+            torch.cuda.synchronize(device)   # no decode in flight may still read the packed weights
             mods = dict(self.named_modules())
             stream = torch.cuda.current_stream(device).cuda_stream
             keep = []
@@ -133,6 +162,7 @@ class ResidualCouplingBlock(nn.Module):
                             "vitsdec_flow_load_layer(%s)" % name)
             torch.cuda.current_stream(device).synchronize()
             self._loaded_fingerprint = fp if fp is not None else self._fingerprint()
+        self._dirty = False
 
     def __del__(self):
         try:
@@ -173,11 +203,10 @@ class ResidualCouplingBlock(nn.Module):
         if g is not None:
             gf = g.to(device=device, dtype=torch.float32).reshape(B, self.gin_channels).contiguous()
         lib = _capi.lib()
-        with torch.cuda.device(device):
-            with self._lock:
-                self._sync_native(device)
+        with torch.cuda.device(device), self._lock:
+            self._sync_native(device)
             nbytes = lib.vitsdec_flow_workspace_bytes(self._handle, B, T)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            ws = self._workspace(device, nbytes)
             out = torch.empty((B, self.channels, T), dtype=torch.float32, device=device)
             stream = torch.cuda.current_stream(device).cuda_stream
             _capi.check(lib.vitsdec_flow_apply(self._handle, xf.data_ptr(), xf.stride(0), xf.stride(1),

@@ -8,6 +8,7 @@ contract.  The torch sub-modules below only HOLD parameters so that ``load_state
 reference's tensors; they are never called.  ``forward`` hands raw device pointers to the C ABI
 (``vitsdec_decode``), which runs the hand-written sm_100a kernels.  There is no PyTorch fallback.
 """
+import operator
 import threading
 
 import torch
@@ -17,6 +18,7 @@ from torch.nn.utils import remove_weight_norm, weight_norm
 from . import _capi
 
 LRELU_SLOPE = 0.1  # modules.py:17
+_VERSION = operator.attrgetter("_version")
 
 
 def get_padding(kernel_size, dilation=1):  # commons.py:14-15
@@ -95,12 +97,21 @@ class Generator(nn.Module):
         self._handle = None          # vitsdec_decoder*
         self._handle_device = None
         self._loaded_fingerprint = None
-        self._lock = threading.Lock()  # Gradio calls forward from worker threads (VC_inference.py:38-53)
+        # Gradio calls forward from worker threads (VC_inference.py:38-53).  The lock is held across the weight sync AND
+        # the (asynchronous, ~0.1 ms) enqueue of the decode: a re-fold or a handle swap can then never run while another
+        # thread is inside vitsdec_decode, and a re-fold first drains the device so that no decode still in flight on
+        # another stream reads packed weights that are being rewritten.
+        self._lock = threading.RLock()
         self.assume_frozen = False   # True: skip the per-call parameter-version check
         self._options = {}
+        self._testing_lib = False    # option impl=1 (CUDA-core cross-check) switches this instance to libvitsdec_test.so
+        self._plist = None           # cached parameter list (the module-tree walk of parameters() costs ~0.25 ms per call)
+        self._dirty = True           # set by load_state_dict / .to() / remove_weight_norm: forces a re-fold check
+        self._ws = {}                # CUDA stream -> workspace tensor kept across calls (stable pointer = plan / graph hits)
 
     # ------------------------------------------------------------------ state_dict compatibility
     def _accept_folded_keys(self, state_dict, prefix, *args):
+        self._dirty = True
         own = dict(self.named_parameters())
         for name in list(own):
             if not name.endswith("weight_v"):
@@ -118,6 +129,15 @@ class Generator(nn.Module):
         for l in self.resblocks:
             l.remove_weight_norm()
         self._loaded_fingerprint = None
+        self._plist = None
+        self._dirty = True
+
+    def _apply(self, fn, *args, **kwargs):   # .to() / .cuda() / .float(): parameters move or are replaced
+        out = super()._apply(fn, *args, **kwargs)
+        self._plist = None
+        self._dirty = True
+        self._ws = {}
+        return out
 
     # ------------------------------------------------------------------ native handle management
     def set_option(self, key, value):
@@ -126,19 +146,39 @@ class Generator(nn.Module):
         saturate at +-65504; the weights are re-folded on the next forward).  Full list: include/vitsdec.h."""
         changed = self._options.get(key) != int(value)
         self._options[key] = int(value)
+        if key == "impl" and int(value) != 0 and not self._testing_lib:
+            # the product library has no second backend: rebuild the handle on the test build (tests only)
+            with self._lock:
+                self._drop_handle()
+                self._testing_lib = True
         if self._handle is not None:
-            _capi.check(_capi.lib().vitsdec_set_option(self._handle, key.encode(), int(value)), "set_option")
+            _capi.check(self._lib().vitsdec_set_option(self._handle, key.encode(), int(value)), "set_option", self._lib())
         if key == "fp16" and changed:
             self._loaded_fingerprint = None   # packed weights of the other 16-bit format are invalid
 
+    def _lib(self):
+        return _capi.lib(testing=self._testing_lib)
+
+    def _drop_handle(self):
+        if self._handle is not None:
+            self._lib().vitsdec_destroy(self._handle)   # synchronises the device first
+            self._handle = None
+            self._loaded_fingerprint = None
+
     def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Cheap change detector (~20 us for 233 tensors): every in-place update of a parameter bumps its version
+        counter, so the sum over a fixed parameter list is strictly monotone; moves / replacements (which change
+        pointers without touching versions) set ``_dirty`` through ``_apply`` / the state_dict hook instead."""
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        pl = self._plist
+        return (len(pl), sum(map(_VERSION, pl)), pl[0].data_ptr(), pl[-1].data_ptr())
 
     def _layer_tensors(self):
         """state_dict prefix -> (weight or weight_v, weight_g or None, bias or None)."""
         out = {}
         mods = dict(self.named_modules())
-        lib = _capi.lib()
+        lib = self._lib()
         for i in range(lib.vitsdec_num_layers(self._handle)):
             name = lib.vitsdec_layer_name(self._handle, i).decode()
             m = mods[name]
@@ -150,25 +190,26 @@ class Generator(nn.Module):
 
     def _sync_native(self, device):
         """(Re)build the native decoder and (re)fold weights when parameters moved or changed."""
-        lib = _capi.lib()
+        lib = self._lib()
         if self._handle is None or self._handle_device != device:
-            if self._handle is not None:
-                lib.vitsdec_destroy(self._handle)
-                self._handle = None
+            self._drop_handle()
             hp = _capi.make_hparams(*self._hp_args[:7], gin_channels=self._hp_args[7])
             h = _capi._vp()
             import ctypes
             index = device.index if device.index is not None else torch.cuda.current_device()
-            _capi.check(lib.vitsdec_create(ctypes.byref(hp), index, ctypes.byref(h)), "vitsdec_create")
+            _capi.check(lib.vitsdec_create(ctypes.byref(hp), index, ctypes.byref(h)), "vitsdec_create", lib)
             self._handle = h
             self._handle_device = device
             self._loaded_fingerprint = None
             for k, v in self._options.items():
-                _capi.check(lib.vitsdec_set_option(self._handle, k.encode(), v), "set_option")
+                _capi.check(lib.vitsdec_set_option(self._handle, k.encode(), v), "set_option", lib)
         fp = None
-        if self._loaded_fingerprint is None or not self.assume_frozen:
+        if self._loaded_fingerprint is None or self._dirty or not self.assume_frozen:
             fp = self._fingerprint()
         if self._loaded_fingerprint is None or (fp is not None and fp != self._loaded_fingerprint):
+            # decodes of other threads / streams may still be reading the packed weights: drain the device first (rare:
+            # once per load_state_dict / .to() / in-place update)
+            torch.cuda.synchronize(device)
             stream = torch.cuda.current_stream(device).cuda_stream
             keep = []
             for name, (w, g, b) in self._layer_tensors().items():
@@ -183,15 +224,31 @@ class Generator(nn.Module):
                     keep.append(t)
                     ts.append(t.data_ptr())
                 _capi.check(lib.vitsdec_load_layer(self._handle, name.encode(), ts[0], ts[1], ts[2], stream),
-                            "vitsdec_load_layer(%s)" % name)
+                            "vitsdec_load_layer(%s)" % name, lib)
             torch.cuda.current_stream(device).synchronize()  # temporaries in `keep` die here
             self._loaded_fingerprint = fp if fp is not None else self._fingerprint()
+        self._dirty = False
+
+    def _workspace(self, device, nbytes):
+        """Per-stream scratch kept across calls.  The C side caches its launch plans (tensor maps, CUDA graphs) per
+        workspace pointer: a fresh torch.empty per call keeps the pointer only as long as the caching allocator happens
+        to return the same block.  Grow-only, at most 4 streams are remembered; release_workspace() frees them."""
+        key = torch.cuda.current_stream(device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            if ws is None and len(self._ws) >= 4:
+                self._ws.pop(next(iter(self._ws)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
+
+    def release_workspace(self):
+        with self._lock:
+            self._ws = {}
 
     def __del__(self):
         try:
-            if self._handle is not None:
-                _capi.lib().vitsdec_destroy(self._handle)
-                self._handle = None
+            self._drop_handle()
         except Exception:
             pass
 
@@ -224,18 +281,23 @@ class Generator(nn.Module):
                 raise RuntimeError("Generator.forward: expected g of shape [%d, %d, 1], got %s"
                                    % (B, self.gin_channels, tuple(g.shape)))
             gf = g.to(device=device, dtype=torch.float32).reshape(B, self.gin_channels).contiguous()
-        lib = _capi.lib()
-        with torch.cuda.device(device):
-            with self._lock:
-                self._sync_native(device)
+        lib = self._lib()
+        with torch.cuda.device(device), self._lock:
+            self._sync_native(device)
             nbytes = lib.vitsdec_workspace_bytes(self._handle, B, T)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            ws = self._workspace(device, nbytes)
             out = torch.empty((B, 1, T * self.hop), dtype=torch.float32, device=device)
             stream = torch.cuda.current_stream(device).cuda_stream
             _capi.check(lib.vitsdec_decode(self._handle, xf.data_ptr(), xf.stride(0), xf.stride(1),
                                            None if gf is None else gf.data_ptr(), out.data_ptr(), B, T,
-                                           ws.data_ptr(), nbytes, stream), "vitsdec_decode")
+                                           ws.data_ptr(), nbytes, stream), "vitsdec_decode", lib)
         return out if out_dtype == torch.float32 else out.to(out_dtype)
+
+    def receptive_halo(self):
+        """Latent frames each side that an output sample depends on (chunked.receptive_halo; 13 for the shipped config)."""
+        from .chunked import receptive_halo
+        a = self._hp_args
+        return receptive_halo(a[1], a[2], a[3], a[4], a[6])
 
     # ------------------------------------------------------------------ helpers for tests / bench
     @classmethod
@@ -250,17 +312,27 @@ class Generator(nn.Module):
         """(accumulated conv-kernel device ms, conv launches) since set_option('profile', 1)."""
         import ctypes
         ms, n = ctypes.c_double(0), ctypes.c_int64(0)
-        _capi.check(_capi.lib().vitsdec_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(n)), "profile_read")
+        _capi.check(self._lib().vitsdec_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(n)), "profile_read")
         return ms.value, n.value
 
     def last_launch_count(self):
-        return 0 if self._handle is None else _capi.lib().vitsdec_last_launch_count(self._handle)
+        return 0 if self._handle is None else self._lib().vitsdec_last_launch_count(self._handle)
+
+    def get_option(self, key):
+        """Read an option / counter of the native decoder (include/vitsdec.h), e.g. "graph_failed": number of launch
+        plans whose CUDA-graph capture failed and that therefore run as plain launches."""
+        import ctypes
+        if self._handle is None:
+            return self._options.get(key, 0)
+        v = ctypes.c_int(0)
+        _capi.check(self._lib().vitsdec_get_option(self._handle, key.encode(), ctypes.byref(v)), "get_option", self._lib())
+        return v.value
 
     def debug_read(self, name, batch, frames):
         """fp32 [B, C, L] copy of a kept intermediate of the last forward (set_option('debug_keep', 1)).
         Names: conv_pre, ups.<i>, mrf.<i>."""
         import ctypes
-        lib = _capi.lib()
+        lib = self._lib()
         c0, rates = self._hp_args[5], self._hp_args[4]
         if name == "conv_pre":
             C, L = c0, frames

@@ -29,9 +29,10 @@ def conv1d_cl(x, w, bias=None, dilation=1, res=None, res_gain=10.0, out_slope=1.
         buf[:x.numel()].copy_(x.reshape(-1))
         x = buf[:x.numel()].view(B, L, c_in)
     st = torch.cuda.current_stream(x.device).cuda_stream
-    _capi.check(_capi.lib().vitsdec_op_conv1d(x.device.index or 0, _ptr(x), _ptr(w), _ptr(bias), _ptr(res),
-                                              float(res_gain), float(out_slope), _ptr(y), B, L, c_in, c_out, k,
-                                              int(dilation), int(impl), int(desc_mode), st), "vitsdec_op_conv1d")
+    L_ = _capi.lib(testing=bool(impl))   # impl=1 (CUDA-core cross-check) lives in the test build only
+    _capi.check(L_.vitsdec_op_conv1d(x.device.index or 0, _ptr(x), _ptr(w), _ptr(bias), _ptr(res),
+                                     float(res_gain), float(out_slope), _ptr(y), B, L, c_in, c_out, k,
+                                     int(dilation), int(impl), int(desc_mode), st), "vitsdec_op_conv1d", L_)
     return y
 
 
@@ -46,9 +47,10 @@ def conv_transpose1d_cl(x, w, bias=None, stride=2, out_slope=1.0, impl=0):
     bias = None if bias is None else bias.float().contiguous()
     y = torch.empty((B, L * stride, c_out), dtype=torch.bfloat16, device=x.device)
     st = torch.cuda.current_stream(x.device).cuda_stream
-    _capi.check(_capi.lib().vitsdec_op_conv_transpose1d(x.device.index or 0, _ptr(x), _ptr(w), _ptr(bias),
-                                                        float(out_slope), _ptr(y), B, L, c_in, c_out, k, int(stride),
-                                                        int(impl), st), "vitsdec_op_conv_transpose1d")
+    L_ = _capi.lib(testing=bool(impl))
+    _capi.check(L_.vitsdec_op_conv_transpose1d(x.device.index or 0, _ptr(x), _ptr(w), _ptr(bias),
+                                               float(out_slope), _ptr(y), B, L, c_in, c_out, k, int(stride),
+                                               int(impl), st), "vitsdec_op_conv_transpose1d", L_)
     return y
 
 

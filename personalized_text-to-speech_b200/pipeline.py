@@ -20,10 +20,14 @@ class HostPipeline:
         self.done = [None] * len(self.streams)
         self._n = 0
 
-    def submit(self, z_host, g_host, out_host):
+    def submit(self, z_host, g_host, out_host, on_device=None):
         """Enqueue H2D(z, g) -> decode -> D2H(out) on the next stream.  z_host [B, C, T], g_host [B, gin, 1] or None and
-        out_host [B, 1, T*hop] are pinned CPU tensors; out_host is valid after wait(ticket).  Returns a ticket."""
-        for t in (z_host, g_host, out_host):
+        out_host [B, 1, T*hop] are pinned CPU tensors; out_host is valid after wait(ticket).  Returns a ticket.
+
+        on_device(y, stream): optional hook called with the decoded waveform still on the device, inside the slot's
+        stream context right after the decode was enqueued -- e.g. to start the multi-GPU waveform gather on a side
+        stream (bench.py) or a WavBatchWriter.enqueue -- so that it overlaps the D2H copy and the next batch."""
+        for t in (z_host, g_host, out_host):   # out_host may be None when on_device consumes the result
             if t is not None and not (t.device.type == "cpu" and t.is_pinned()):
                 raise RuntimeError("HostPipeline.submit: host tensors must be pinned CPU tensors")
         slot = self._n % len(self.streams)
@@ -35,7 +39,10 @@ class HostPipeline:
             z = z_host.to(self.device, non_blocking=True)
             g = None if g_host is None else g_host.to(self.device, non_blocking=True)
             y = self.G(z, g)
-            out_host.copy_(y, non_blocking=True)
+            if on_device is not None:
+                on_device(y, s)
+            if out_host is not None:
+                out_host.copy_(y, non_blocking=True)
             # the caching allocator may hand these blocks to another stream as soon as they are dropped
             for t in (z, g, y):
                 if t is not None:

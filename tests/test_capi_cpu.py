@@ -30,6 +30,16 @@ def test_library_exports_every_declared_symbol():
     # and the ctypes prototypes cover the whole header (no silently unbound entry point)
     assert sorted(_capi.SIGNATURES) == names
     assert lib.vitsdec_abi_version() == 1
+    # the test build (CUDA-core cross-check backend linked in) exports the same ABI; the product library carries no
+    # second backend: its SASS holds no conv_simt kernel
+    tlib = _capi.lib(testing=True)
+    for n in names:
+        assert hasattr(tlib, n)
+    from importlib import import_module
+    b = import_module("personalized_text-to-speech_b200.build")
+    syms = subprocess.run(["nm", "-C", b.LIB], stdout=subprocess.PIPE, text=True).stdout
+    syms_t = subprocess.run(["nm", "-C", b.LIB_TEST], stdout=subprocess.PIPE, text=True).stdout
+    assert "conv_simt" not in syms and "conv_simt" in syms_t
 
 
 def test_hparams_struct_layout_matches_header():

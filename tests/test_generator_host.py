@@ -114,6 +114,44 @@ def test_decode_chunked_with_oracle_decode_fn():
     assert got.shape == full.shape and float((got - full).abs().max()) < 1e-6
 
 
+def test_receptive_halo_is_exact_for_the_shipped_configuration():
+    """the receptive field of the shipped decoder is 13 latent frames on either side (not "11.5, use 12"):
+    with halo >= 13 the chunked decode equals the unchunked one up to fp64 summation order, 12 leaves ~2e-10; the
+    computed value is the default of decode_chunked."""
+    hp = oracle.FINETUNE_SPEAKER
+    args, _ = hp.ctor_args()
+    assert chunked.receptive_halo(args[1], args[2], args[3], args[4], args[6]) == 13
+    assert chunked.receptive_halo("2", (3, 5, 7), ((1, 2), (2, 6), (3, 12)), (8, 8, 4), (16, 16, 8)) > 0
+    G = vitsdec.Generator(*args, gin_channels=hp.gin_channels)
+    assert G.receptive_halo() == 13
+    from oracle.generator_torch import generator_forward_torch, to_torch_state_dict
+    sd = to_torch_state_dict(oracle.synth_state_dict(hp, 3, gain=2.0), dtype=torch.float64)
+    rs = np.random.RandomState(4)
+    T = 48
+    z = torch.from_numpy(rs.standard_normal((1, hp.initial_channel, T)))
+    g = torch.from_numpy(rs.standard_normal((1, hp.gin_channels, 1)))
+
+    def fn(zz, gg):
+        return generator_forward_torch(hp, sd, zz, gg)
+
+    full = fn(z, g)
+    err = {}
+    for halo in (12, 13, 14):
+        got = vitsdec.decode_chunked(fn, z, g, chunk_frames=8, halo=halo, hop=hp.hop)
+        err[halo] = float((got - full).abs().max())
+    peak = float(full.abs().max())
+    assert err[13] <= 1e-13 * peak and err[14] <= 1e-13 * peak, err     # summation-order noise only
+    assert err[12] > 1e4 * err[13], err            # 12 frames do NOT cover the field (~2e-10: invisible in fp32)
+    # the dependency itself, bit for bit: frame f0's samples see latent frames f0 - 13 .. f0 + 13 and nothing beyond
+    assert chunked.receptive_field(args[1], args[2], args[3], args[4], args[6]) == (13, 13)
+    f0 = 20
+    for dist, depends in ((14, False), (13, True), (-14, False), (-13, True)):
+        z2 = z.clone()
+        z2[0, :, f0 + dist] += 1e3
+        same = torch.equal(fn(z2, g)[0, 0, f0 * hp.hop:(f0 + 1) * hp.hop], full[0, 0, f0 * hp.hop:(f0 + 1) * hp.hop])
+        assert same != depends, (dist, same)
+
+
 def test_polyphase_transposed_conv_derivation():
     """The packing rule used by pack_convT_kernel (csrc/pack.cu): output sample s*i + r reads input rows i + off with
     kernel index j = r + p - s*off.  Restated in numpy and checked against the oracle's conv_transpose1d."""
@@ -241,3 +279,22 @@ def test_zero_padded_channels_compute_the_narrow_decoder():
     got = oracle.generator_forward_np(hp, padded, zp, None, dtype=np.float64)
     assert got.shape == ref.shape
     assert np.array_equal(got, ref)                 # exact: the padding contributes exact zeros to every sum
+
+
+def test_wav_header_is_byte_identical_to_scipy():
+    """Output side (cmd_inference.py:117 writes float32 with scipy.io.wavfile.write): the header WavBatchWriter places in
+    front of the samples, for the reference's float format and for 16-bit PCM."""
+    import io
+    import scipy.io.wavfile as wavf
+    from importlib import import_module
+    wavout = import_module("personalized_text-to-speech_b200.wavout")
+    rs = np.random.RandomState(0)
+    for n in (0, 1, 7, 22050, 220672):
+        x = (rs.standard_normal(n) * 0.3).astype(np.float32)
+        for fmt, data in (("float32", x), ("pcm16", wavout.pcm16_reference(x))):
+            f = io.BytesIO()
+            wavf.write(f, 22050, data)
+            want = f.getvalue()
+            got = wavout.wav_header(n, 22050, fmt) + data.tobytes()
+            assert got == want, (n, fmt)
+    assert wavout.pcm16_reference([2.0, -2.0, 0.5, -0.5, 1.0 / 65534])[:4].tolist() == [32767, -32767, 16384, -16384]

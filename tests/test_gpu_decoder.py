@@ -498,3 +498,75 @@ def test_programmatic_dependent_launch_modes_agree():
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     ref = generator_forward_torch(hp, to_torch_state_dict(sd), z.cpu(), g.cpu())
     check(ref, outs[1].cpu())
+
+
+def test_wav_output_bytes_equal_scipy_write(tmp_path):
+    """SURVEY.md 8f-2, the output side of cmd_inference.py:114-117: WavBatchWriter (device-side PCM16 conversion, async
+    D2H straight behind the header in pinned memory) writes files whose bytes equal scipy.io.wavfile.write of the same
+    samples -- float32 (the format the reference writes) and pcm16 -- and whose content matches the fp32 reference
+    decode within the decoder's tolerance."""
+    import io
+    import scipy.io.wavfile as wavf
+    from importlib import import_module
+    wavout = import_module("personalized_text-to-speech_b200.wavout")
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 77)
+    rs = np.random.RandomState(12)
+    B, T = 3, 40
+    z = torch.from_numpy(rs.standard_normal((B, hp.initial_channel, T)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((B, hp.gin_channels, 1)).astype(np.float32))
+    ref = generator_forward_torch(hp, to_torch_state_dict(sd), z, g)
+    with torch.no_grad():
+        y = G(z.to(DEV), g.to(DEV)) * 30.0        # random-init waveforms peak at ~0.03: bring them to PCM scale
+    ref = ref * 30.0
+    lengths = [T * 256, 31 * 256 + 5, 1]
+    for fmt in ("float32", "pcm16"):
+        w = vitsdec.WavBatchWriter(22050, fmt)
+        images, ev = w.enqueue(y, lengths)
+        paths = [str(tmp_path / ("u%d_%s.wav" % (i, fmt))) for i in range(B)]
+        w.save(images, paths, ev)
+        for i, path in enumerate(paths):
+            mine = y[i, 0, :lengths[i]].cpu().numpy()
+            data = mine if fmt == "float32" else wavout.pcm16_reference(mine)
+            f = io.BytesIO()
+            wavf.write(f, 22050, data)
+            assert open(path, "rb").read() == f.getvalue(), (fmt, i)
+            sr, back = wavf.read(path)
+            assert sr == 22050 and back.shape == (lengths[i],)
+            want = ref[i, 0, :lengths[i]].numpy()
+            if fmt == "pcm16":   # vs the REFERENCE output: within the decoder's 3 %-of-peak bound, in PCM steps
+                want16 = wavout.pcm16_reference(want).astype(np.int64)
+                peak = max(1, int(np.abs(wavout.pcm16_reference(ref.numpy())).max()))
+                assert np.abs(back.astype(np.int64) - want16).max() <= 0.03 * peak + 1
+            elif lengths[i] > 256:
+                check(torch.from_numpy(want), torch.from_numpy(back))
+
+
+def test_default_path_keeps_plans_and_reports_graph_failures():
+    """the default forward must not rebuild launch plans when the allocator moves the workspace -- the module
+    keeps its workspace per stream -- and a plan that fell back from its CUDA graph must be visible."""
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 78)
+    rs = np.random.RandomState(3)
+    z = torch.from_numpy(rs.standard_normal((1, hp.initial_channel, 50)).astype(np.float32)).to(DEV)
+    g = torch.from_numpy(rs.standard_normal((1, hp.gin_channels, 1)).astype(np.float32)).to(DEV)
+    with torch.no_grad():
+        y0 = G(z, g)
+        ptr = next(iter(G._ws.values())).data_ptr()
+        junk = [torch.empty(1 << 20, device=DEV) for _ in range(8)]   # allocator churn between calls
+        for _ in range(6):
+            y = G(z, g)
+            assert next(iter(G._ws.values())).data_ptr() == ptr
+            assert torch.equal(y, y0)
+        del junk
+        # mixed shapes share the workspace; an in-place parameter update is still noticed without assume_frozen
+        y_small = G(z[:, :, :20].contiguous(), g)
+        assert y_small.shape == (1, 1, 20 * 256)
+        G.ups[0].weight_g.mul_(1.25)
+        y2 = G(z, g)
+        assert not torch.equal(y2, y0)
+        G.ups[0].weight_g.div_(1.25)
+    assert G.get_option("graph_failed") == 0
+    assert G.get_option("testing_build") == 0    # the product library has no second backend
+    with pytest.raises(Exception):
+        vitsdec._capi.check(vitsdec._capi.lib().vitsdec_set_option(G._handle, b"impl", 1), "set_option")

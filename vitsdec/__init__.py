@@ -16,6 +16,9 @@ shard_range = _pkg.shard_range
 decode_sharded = _pkg.decode_sharded
 decode_chunked = _pkg.decode_chunked
 HostPipeline = _pkg.HostPipeline
+WavBatchWriter = _pkg.WavBatchWriter
+wav_header = _pkg.wav_header
+synthesize_to_wav = _pkg.synthesize_to_wav
 build = _pkg.build
 generator_args = _pkg.generator_args
 generator_args_from_config = _pkg.generator_args_from_config
