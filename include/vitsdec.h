@@ -109,6 +109,9 @@ VITSDEC_API int vitsdec_wav_pcm16(int device, const float* wav_dev, int16_t* pcm
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
  *          "pairf" = 2 runs fused pairs through the time-folded conv_pairf.cu wherever it exists (tests / experiments);
  *          0 / 1 (default): conv_pair.cu -- the folded pair kernel is not preferred anywhere in the default schedule;
+ *          "mrfp" = 0 runs the last ResBlock pair of every MRF branch as separate launches + one fused-MRF launch (default 1:
+ *          where the stage is narrow enough (C = 32) one launch computes the three last pairs, the branch sum and the
+ *          average, conv_mrfp.cu);
  *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph);
  *          "pdl" = 0 no programmatic dependent launch (default 1: launches whose grid leaves SMs idle let the next launch
  *          of the stream start its prologue early; 2: every launch);

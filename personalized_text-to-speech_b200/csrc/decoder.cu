@@ -31,6 +31,7 @@
 
 #include "../../include/vitsdec.h"
 #include "common.cuh"
+#include "conv_mrfp.h"
 #include "conv_pair.h"
 #include "conv_pairf.h"
 #include "conv_tc.h"
@@ -49,7 +50,7 @@ constexpr float kPostSlope = 0.01f;  // F.leaky_relu default, models.py:285
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int ceildiv(int a, int b) { return -floordiv(-a, b); }
 
-enum LayerKind { kConv = 0, kConvT = 1, kPost = 2, kCond = 3, kMrf = 4, kPair = 5 };
+enum LayerKind { kConv = 0, kConvT = 1, kPost = 2, kCond = 3, kMrf = 4, kPair = 5, kMrfPair = 6 };
 
 struct Layer {
   std::string name;
@@ -65,6 +66,8 @@ struct Layer {
   std::vector<int> members;      // real layer ids, one per branch
   int mrf_group = -1;            // real layers: id of the virtual layer they also feed, and their tap base in it
   int mrf_tap_base = 0;
+  int mrfp_group = -1;           // real layers: id of the stage's fused last-pairs layer (kMrfPair, conv_mrfp.cu) and
+  int mrfp_tap_base = 0;         // their first tap inside its packed weights
   int pair_group = -1;           // real layers: id of the fused-pair virtual layer (kPair) and their tap base in it
   int pair_tap_base = 0;
   // time-folded form (fold_geom): r time samples per row, r*C virtual channels; 0 = layer has no folded form
@@ -180,6 +183,9 @@ struct Step {           // one launch of the conv primitive
   PairPlan pair;
   bool is_pairf = false;    // time-folded fused pair (conv_pairf.cu)
   PairFPlan pairf;
+  bool is_mrfp = false;     // last pairs of all MRF branches + branch average in one launch (conv_mrfp.cu): layer = kMrfPair
+  MrfpPlan mrfp;
+  float mrfp_out_slope = 0.f;
   int branch = -1;          // MRF branch this launch belongs to (-1: trunk), for concurrent branches under the graph
   bf16* dbg_dst = nullptr;  // debug_keep: copy ep.out here after the launch
   size_t dbg_bytes = 0;
@@ -226,12 +232,13 @@ struct vitsdec_decoder {
   int l_pre = -1, l_post = -1, l_cond = -1;
   std::vector<int> l_ups;
   std::vector<int> l_mrf;              // per stage: virtual fused-MRF layer id, or -1 (fp32 accumulator path)
+  std::vector<int> l_mrfp;             // per stage: kMrfPair layer id (last pairs + MRF in one launch), or -1
   int num_real_layers = 0;
   std::vector<std::vector<int>> l_rb;  // per resblock: conv layer ids in forward order
   std::vector<int> stage_ch;
   int hop = 1;
   float* scale_scratch = nullptr;
-  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1, par = 1;
+  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1, par = 1, mrfp = 1;
   int c_z = 0;   // initial_channel rounded up to a multiple of 32: the packed latent and conv_pre's K are zero-padded
   int pdl = 1;   // option "pdl": programmatic dependent launch for launches that leave SMs idle (0 off, 2 every launch)
   int fp16 = 0;  // option "fp16": weights and stored activations are IEEE fp16 instead of bf16 (ConvEpilogue::f16)
@@ -281,6 +288,10 @@ static int add_layer(vitsdec_decoder* d, const std::string& name, LayerKind kind
 }
 
 static int alloc_layer(Layer& l) {
+  if (l.kind == kMrfPair) {
+    VD_CUDA(cudaMalloc(&l.w, (size_t)l.k * l.c_out * l.c_in * sizeof(bf16)));   // l.k = total taps of the packed set
+    return 0;
+  }
   if (l.kind == kPair) {
     VD_CUDA(cudaMalloc(&l.w, (size_t)2 * l.k * l.c_out * l.c_in * sizeof(bf16)));
     if (l.fold_r) VD_CUDA(cudaMalloc(&l.wfold, (size_t)l.fgeom.ntaps * 128 * 128 * sizeof(bf16)));
@@ -431,6 +442,8 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     keep("ups." + std::to_string(i), ch, L, 1.f / kSlope);
     const float next_slope = (i == nstage - 1) ? kPostSlope : kSlope;
     const bool fused = d->l_mrf[i] >= 0;
+    // last pairs of all branches + MRF average as one launch (conv_mrfp.cu)
+    const bool use_mrfp = fused && d->impl == 0 && d->mrfp && d->fuse_pairs && d->l_mrfp[i] >= 0 ;
     float* S = reinterpret_cast<float*>(slot(5));
     const bf16* seg_in[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
     const bf16* seg_res[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
@@ -479,6 +492,10 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
           cur = dst;
           continue;
         }
+        if (last && use_mrfp) {   // the whole last pair runs inside the stage's conv_mrfp launch
+          seg_res[j] = cur;
+          break;
+        }
         if (d->hp.resblock == 1) {
           ConvEpilogue e1 = ep0(convs[2 * m]);
           e1.out = last ? Hj : T1j;
@@ -516,7 +533,21 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
       if (fused)
         for (size_t si = first_step; si < pl.steps.size(); ++si) pl.steps[si].branch = j;
     }
-    if (fused) {
+    if (use_mrfp) {
+      const Layer& v = d->layers[d->l_mrfp[i]];
+      Step s{};
+      s.layer = d->l_mrfp[i];
+      s.L = L;
+      s.is_mrfp = true;
+      s.ep = ep0(v.members[0]);
+      s.ep.out = X;
+      s.mrfp_out_slope = next_slope;
+      s.tc.p.g.B = B;
+      int ks[kMpMaxBr] = {0, 0, 0}, dl[kMpMaxBr] = {1, 1, 1};
+      for (int j = 0; j < nk; ++j) { ks[j] = d->layers[v.members[j]].k; dl[j] = d->layers[v.members[j]].dil; }
+      if (plan_conv_mrfp(&s.mrfp, B, L, ch, nk, ks, dl, seg_res, v.w, d->num_sms)) return 1;
+      pl.steps.push_back(s);
+    } else if (fused) {
       // models.py:279-284: x = (rb0(x) + rb1(x) + rb2(x)) / nk -- the three last convs accumulate in one TMEM tile
       ConvEpilogue e = ep0(d->l_mrf[i]);
       for (int j = 0; j < nk; ++j) e.res[j] = seg_res[j];
@@ -539,7 +570,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   // launch takes).  Long launches gain nothing (one CTA per SM, no room for the dependent's CTAs) and measured slower.
   for (Step& s : pl.steps) {
     const int tiles = s.is_pair ? s.pair.p.total_tiles : s.tc.p.total_tiles;   // at most two tile rounds: a short launch
-    const bool on = d->impl == 0 && !s.is_pairf && (d->pdl == 2 || (d->pdl == 1 && tiles <= 2 * d->num_sms));
+    const bool on = d->impl == 0 && !s.is_pairf && !s.is_mrfp && (d->pdl == 2 || (d->pdl == 1 && tiles <= 2 * d->num_sms));
     s.tc.pdl = on && !s.is_pair;
     s.pair.pdl = on && s.is_pair;
   }
@@ -568,6 +599,14 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
 
 static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
   Layer& ly = d->layers[s.layer];
+  if (s.is_mrfp) {
+    const int nk = (int)ly.members.size() / 2;
+    const float* b1[kMpMaxBr] = {nullptr, nullptr, nullptr};
+    for (int j = 0; j < nk; ++j) b1[j] = d->layers[ly.members[j]].bias;
+    // sum of the c2 biases: the fused-MRF virtual layer of the same stage keeps it (rebuilt at every load)
+    const float* b2 = d->layers[d->layers[ly.members[nk]].mrf_group].bias;
+    return launch_conv_mrfp(s.mrfp, b1, b2, kSlope, s.mrfp_out_slope, s.ep.out, st, d->fp16);
+  }
   if (s.is_pairf)
     return launch_conv_pairf(s.pairf, d->layers[ly.members[0]].bias, d->layers[ly.members[1]].bias, kSlope, s.ep.out,
                              st, d->fp16);
@@ -784,6 +823,39 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
       }
     }
   }
+  // Fused last pairs: the LAST (c1, c2) pair of every MRF branch of a stage, the branch sum and the average in ONE launch
+  // (conv_mrfp.cu) where both weight sets of all branches fit in shared memory next to the tiles (C = 32).
+  d->l_mrfp.assign(hp->num_upsamples, -1);
+  if (hp->resblock == 1) {
+    for (int i = 0; i < hp->num_upsamples; ++i) {
+      if (d->l_mrf[i] < 0 || hp->num_kernels > kMpMaxBr) continue;
+      int ks[kMpMaxBr] = {0, 0, 0}, dl[kMpMaxBr] = {1, 1, 1};
+      for (int j = 0; j < hp->num_kernels; ++j) {
+        const std::vector<int>& convs = d->l_rb[i * hp->num_kernels + j];
+        ks[j] = d->layers[convs[convs.size() - 2]].k;
+        dl[j] = d->layers[convs[convs.size() - 2]].dil;
+      }
+      if (!mrfp_supported(d->stage_ch[i], hp->num_kernels, ks, dl)) continue;
+      Layer v;
+      v.name = "mrfp." + std::to_string(i);
+      v.kind = kMrfPair;
+      v.c_in = v.c_out = d->stage_ch[i];
+      const int vid = (int)d->layers.size();
+      int tap = 0;
+      for (int pass = 0; pass < 2; ++pass)       // packed order: c1 of every branch, then c2 of every branch
+        for (int j = 0; j < hp->num_kernels; ++j) {
+          const std::vector<int>& convs = d->l_rb[i * hp->num_kernels + j];
+          const int lid = convs[convs.size() - 2 + pass];
+          d->layers[lid].mrfp_group = vid;
+          d->layers[lid].mrfp_tap_base = tap;
+          tap += d->layers[lid].k;
+          v.members.push_back(lid);
+        }
+      v.k = tap;
+      d->layers.push_back(v);
+      d->l_mrfp[i] = vid;
+    }
+  }
   for (Layer& l : d->layers)
     if (alloc_layer(l)) return 1;
   VD_CUDA(cudaMalloc(&d->scale_scratch, 4096 * sizeof(float)));
@@ -859,6 +931,12 @@ int vitsdec_load_layer(vitsdec_decoder* d, const char* name, const float* w, con
       if (launch_sum_bias(bs[0], bs[1], bs[2], bs[3], v.bias, v.c_out, st)) return 1;
       if (v.fold_r && launch_replicate_bias(v.bias, v.bias_fold, v.c_out, v.fold_r, st)) return 1;
     }
+    if (l.mrfp_group >= 0) {
+      Layer& v = d->layers[l.mrfp_group];
+      if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.mrfp_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
+                           st, 0, d->fp16, ci_s, co_s))
+        return 1;
+    }
     if (l.pair_group >= 0) {
       Layer& v = d->layers[l.pair_group];
       if (launch_pack_conv(w, d->scale_scratch, v.w + (size_t)l.pair_tap_base * l.c_out * l.c_in, l.c_out, l.c_in, l.k,
@@ -915,7 +993,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, d->desc_mode * 256 + d->pdl * 64 + d->par * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
+    const PlanKey key{B, T, d->impl, d->desc_mode * 512 + d->mrfp * 256 + d->pdl * 64 + d->par * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -1100,6 +1178,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "par")) d->par = value ? 1 : 0;
+  else if (!strcmp(key, "mrfp")) d->mrfp = value ? 1 : 0;
   else if (!strcmp(key, "pdl")) d->pdl = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "fp16")) {
     // the 16-bit storage format of weights AND activations: packed weights of the other format are useless, so every
@@ -1149,6 +1228,7 @@ int vitsdec_get_option(const vitsdec_decoder* d, const char* key, int* value) {
   else if (!strcmp(key, "fold")) *value = d->fold;
   else if (!strcmp(key, "pairf")) *value = d->pairf;
   else if (!strcmp(key, "par")) *value = d->par;
+  else if (!strcmp(key, "mrfp")) *value = d->mrfp;
   else if (!strcmp(key, "pdl")) *value = d->pdl;
   else if (!strcmp(key, "fp16")) *value = d->fp16;
   else if (!strcmp(key, "graph_failed")) *value = d->graph_failures.load();

@@ -570,3 +570,31 @@ def test_default_path_keeps_plans_and_reports_graph_failures():
     assert G.get_option("testing_build") == 0    # the product library has no second backend
     with pytest.raises(Exception):
         vitsdec._capi.check(vitsdec._capi.lib().vitsdec_set_option(G._handle, b"impl", 1), "set_option")
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 7), (3, 32), (2, 100), (16, 20)])
+def test_fused_last_pairs_launch_matches_separate_launches(B, T):
+    """conv_mrfp.cu (option "mrfp", default on): the last ResBlock pair of every MRF branch of the C = 32 stage, the branch
+    sum and the average in ONE launch.  Against the schedule it replaces (three c1 launches + the fused-MRF launch): bit
+    for bit on plain tiles (fold=0: same accumulation order), and within bf16 re-rounding of each other on the default
+    folded schedule; both inside the stated tolerance of the fp32 restatement.  Three launches fewer per decode."""
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 41)
+    rs = np.random.RandomState(B * 31 + T)
+    z = torch.from_numpy(rs.standard_normal((B, hp.initial_channel, T)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((B, hp.gin_channels, 1)).astype(np.float32))
+    ref = generator_forward_torch(hp, to_torch_state_dict(sd), z, g)
+    out = {}
+    with torch.no_grad():
+        for fold in (0, 1):
+            for mrfp in (0, 1):
+                G.set_option("fold", fold)
+                G.set_option("mrfp", mrfp)
+                out[fold, mrfp] = G(z.to(DEV), g.to(DEV)).cpu()
+                out["n", fold, mrfp] = G.last_launch_count()
+    assert torch.equal(out[0, 0], out[0, 1])
+    assert snr_db(out[1, 0], out[1, 1]) > 45.0
+    assert out["n", 1, 1] == out["n", 1, 0] - 3 and out["n", 0, 1] == out["n", 0, 0] - 3
+    if T >= 7:
+        for k in ((0, 1), (1, 1)):
+            check(ref, out[k])
