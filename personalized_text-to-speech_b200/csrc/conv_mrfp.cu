@@ -1,20 +1,29 @@
-// The LAST ResBlock1 pair of every MRF branch of a stage, the branch sum, the 1/nk average and the next leaky-relu
-// in ONE launch (narrow stages, C = 32):
-//     X = lrelu( ( sum_j  c2_j( lrelu( c1_j(P_j) + b1_j ) ) + b2_j + x(P_j) ) / nk )     models.py:278-284, modules.py:211-221
-// P_j = a-form input of branch j's last pair, c1_j = Conv1d(C, C, k_j, dilation d_j), c2_j = Conv1d(C, C, k_j, 1).
+// Fused ResBlock1 pairs of the C = 32 stage on the sm_100a tensor cores, on the 2-sample time-folded view:
+//     X = lrelu( ( sum_j  c2_j( lrelu( c1_j(P_j) + b1_j ) ) + b2_j + x(P_j) ) / nbr , out_slope )
+//   nbr = 1: one ResBlock1 iteration (modules.py:211-221)       c1 = Conv1d(C, C, k, dilation d), c2 = Conv1d(C, C, k, 1)
+//   nbr = 3: the LAST iteration of every MRF branch of the stage, the branch sum, the 1/nk average and the next
+//            leaky-relu (models.py:278-284) -- three h tiles that never leave the SM, one output tensor.
 //
-// Why: before, each branch's last c1 was its own launch (HBM-bound: one tensor read, one written) and the fused MRF
-// launch then re-read SIX tensors (three h, three residuals): 9 tensor reads + 4 writes per stage for three pairs.
-// Here the three h tiles never leave the SM and the residuals come from the activation tiles that are resident for
-// c1 anyway: 3 reads + 1 write.
+// Why the folded view.  With 32 channels a time-as-M MMA (M = 128 samples, N = 32, K = 16) reads 4 KB of activations
+// + 1 KB of weights from shared memory for 16 cycles of math: measured 40 cycles (tools/probes/mma_rate_probe.cu:
+// cycles = 32 + N/4 below N = 128, the operand fetch at 128 B/cycle), 40 % of the tensor rate at best, and the fused
+// kernels were bound by the hand-offs between MMA issue and the epilogue groups per 256-sample tile on top of that.
+// [B][L][32] is bit for bit [B][L/2][64]: row m holds samples 2m, 2m+1 ("phases").  On that view
+//   * a dilation-1 conv is a conv over folded rows with N = 64: phase-0 outputs take tap t0, phase-1 outputs tap
+//     t0 - 1 of the SAME input chunk (row shift s, input phase psi; t0 = 2s + psi + hk), so with the taps stored in
+//     reverse order two neighbouring tap blocks ARE the stacked 64-row B operand: k + 1 chunks, no extra weights, 48
+//     cycles per MMA for twice the samples of the 40-cycle N = 32 form;
+//   * a dilated conv (odd dilation flips the phase) runs as 2k N = 32 block jobs (tap, output phase) -> (s, psi);
+//   * a tile of 2 x 128 folded rows covers 512 samples: twice the work per hand-off of the plain kernels.
+// MMA jobs are a host-built table (MrfpParams::jobs): the issuing warps just walk it.
 //
-// Tile: every branch's h tile covers the SAME 256 time rows [t0 - hmax, t0 - hmax + 256), hmax = max_j (k_j - 1)/2, so
-// that the three c2 convs accumulate into one TMEM tile of 256 - 2*hmax valid output rows; branch j's c2 reads its h
-// tile at row offset hmax - hk_j + tap.  Pipeline per CTA (tile i, branch j):
-//   TMA A(i,j) -> c1(i,j) [acc1, double buffered] -> epi1: h(i,j) -> smem [double buffered] -> c2(i,j) [+= acc2(i)]
-//   after j = nbr-1: epi2(i): acc2 + sum b2 + sum_j x(P_j) (from the resident tiles) -> /nk -> lrelu -> global
-// Two MMA-issuing warps (c1 stream, c2 stream) and two epilogue groups of 8 warps, as in conv_pair.cu; all weights
-// (2 * sum k_j taps x 2 KB) stay resident.
+// Per CTA (tile i, branch j; n = running (i, j) index):
+//   TMA A(n) -> c1(n) [acc1, 2 TMEM buffers] -> epi1: h(n) = lrelu(acc1 + b1_j), 0 outside the utterance -> smem
+//   [swizzled K-major A operand of c2, 1-2 buffers] -> c2(n) [+= acc2(i), 2 TMEM buffers]
+//   after the last branch: epi2(i) = (acc2 + sum b2 + sum_j x(P_j)) / nbr -> lrelu -> global.
+// The residual rows x(P_j) are re-read from global memory (the tile passed through L2 a moment ago), so an activation
+// stage is free again as soon as c1 has retired.  Two MMA-issuing warps (c1 stream / c2 stream), two epilogue groups of
+// 8 warps (h producer / output), as in conv_pair.cu.
 #include <algorithm>
 
 #include "common.cuh"
@@ -26,33 +35,33 @@ namespace vd {
 constexpr int kMpEpiWarps = 16;
 constexpr int kMpThreads = 64 + 32 * kMpEpiWarps + 32;  // producer, c1 issuer, 16 epilogue warps, c2 issuer
 constexpr int kMpC2Warp = 2 + kMpEpiWarps;
-constexpr int kMpHRows = 272;                           // 256 + 2*hmax rounded up (hmax <= 8)
+constexpr int kMpRowB = 128;                            // folded row: 2 samples x 32 channels x 2 bytes
+constexpr int kMpWBlock = 32 * 64;                      // one tap: [32 out][32 in] bf16, 64-byte rows (SWIZZLE_64B)
 
 struct MrfpMaps {
   CUtensorMap a[kMpMaxBr];
 };
 
-template <int CH, bool F16>
+template <int NACC, bool F16>
 __global__ void __launch_bounds__(kMpThreads, 1)
 conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ MrfpParams p) {
-  constexpr int KC = CH, ROWB = KC * 2;
-  constexpr int B_STAGE = CH * ROWB;      // one tap's weights [CH][KC]
-  constexpr int ACC_COLS = 2 * CH;        // two 128-row accumulators per conv
+  constexpr int ROWB = kMpRowB;
+  constexpr int MROWS = 128 * NACC;       // folded rows per tile (h rows; output rows incl. the invalid margin)
+  constexpr int ACC_COLS = NACC * 64;     // NACC accumulators of 128 rows x (2 phases x 32 channels)
   constexpr int TMEM_COLS = 4 * ACC_COLS; // acc1[2] + acc2[2]
-  constexpr int CHUNKS = CH / 16, NW = kMpEpiWarps / 8;   // warps per quadrant per group
-  static_assert(CH == 32, "mrfp kernel: C = 32 (one 16-column chunk per epilogue warp)");
-  static_assert(TMEM_COLS <= 512 && CHUNKS == NW, "mrfp kernel: a warp owns one 16-column chunk of both accumulators");
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int NA = p.na_stages;
+  const int NA = p.na_stages, NH = p.nh;
+  const int hrows_bytes = (MROWS + 2 * p.hm + 7) / 8 * 8 * ROWB;   // h buffer: MROWS written rows + the rows c2's taps reach
   uint8_t* smemA = smem;
-  uint8_t* smemW = smemA + NA * p.a_stage_bytes;
-  uint8_t* smemH = smemW + p.ntaps * B_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemH + 2 * kMpHRows * ROWB);
+  uint8_t* smemH = smemA + NA * p.a_stage_bytes;
+  uint8_t* smemW = smemH + NH * hrows_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemW + p.ntaps * kMpWBlock);
   uint64_t* a_full = bars;                  // [kMpMaxNA]
-  uint64_t* a_empty = a_full + kMpMaxNA;    // [kMpMaxNA]  1 (c1 retired) + 8 (epi2 warps read the residual)
+  uint64_t* a_empty = a_full + kMpMaxNA;    // [kMpMaxNA]  c1 retired
   uint64_t* acc1_full = a_empty + kMpMaxNA;
   uint64_t* acc1_empty = acc1_full + 2;
   uint64_t* acc2_full = acc1_empty + 2;
@@ -61,7 +70,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
   uint64_t* h_empty = h_full + 2;
   uint64_t* w_full = h_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* sbias = reinterpret_cast<float*>(bars + 32);    // 256 B of barriers, then (nbr + 1) * CH floats
+  float* sbias = reinterpret_cast<float*>(bars + 32);    // 256 B of barriers, then (kMpMaxBr + 1) * 32 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,7 +80,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < nbr; ++j) tma_prefetch_desc(&tm.a[j]);
     tma_prefetch_desc(&tmW);
-    for (int i = 0; i < kMpMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kMpEpiWarps / 2); }
+    for (int i = 0; i < kMpMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kMpEpiWarps / 2);
       mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kMpEpiWarps / 2);
@@ -85,8 +94,8 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < (kMpMaxBr + 1) * CH; i += kMpThreads) {
-    const int j = i / CH, c = i % CH;
+  for (int i = threadIdx.x; i < (kMpMaxBr + 1) * 32; i += kMpThreads) {
+    const int j = i >> 5, c = i & 31;
     sbias[i] = j < kMpMaxBr ? (j < nbr ? p.bias1[j][c] : 0.f) : p.bias2sum[c];
   }
   tc_fence_before();
@@ -94,44 +103,64 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int hmax = p.hmax;
+  const int hm = p.hm;
   const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(w_full, p.ntaps * B_STAGE);
-      for (int tap = 0; tap < p.ntaps; ++tap) tma_load_3d(&tmW, w_full, smemW + tap * B_STAGE, 0, 0, tap);
+      // weights: every tap block once; within a conv the blocks are stored in REVERSE tap order, so that the blocks of
+      // taps t0, t0 - 1 form the stacked [64][32] operand of a dilation-1 chunk
+      mbar_expect_tx(w_full, p.ntaps * kMpWBlock);
+      for (int c = 0; c < 2 * nbr; ++c)
+        for (int t = 0; t < p.conv_k[c]; ++t)
+          tma_load_3d(&tmW, w_full, smemW + (p.conv_base[c] + p.conv_k[c] - 1 - t) * kMpWBlock, 0, 0, p.conv_base[c] + t);
       pdl_wait();   // the weights (static) load while the previous launch drains; activations only from here on
       uint32_t sa = 0, pa = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t tile = blockIdx.x + i * gridDim.x;
         uint32_t b, mt;
         p.div_m.divmod(tile, b, mt);
-        const int t0 = mt * p.bmo;
+        const int m0 = mt * p.bmo;
         for (int j = 0; j < nbr; ++j) {
           mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_expect_tx(&a_full[sa], p.nboxes[j] * 64 * ROWB);
-          for (int bx = 0; bx < p.nboxes[j]; ++bx)
-            tma_load_3d(&tm.a[j], &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 64 * ROWB, 0,
-                        t0 + p.a_lo[j] + bx * 64, (int)b);
+          mbar_expect_tx(&a_full[sa], p.a_boxes[j] * 32 * ROWB);
+          for (int bx = 0; bx < p.a_boxes[j]; ++bx)
+            tma_load_3d(&tm.a[j], &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 32 * ROWB, 0,
+                        m0 + p.a_lo[j] + bx * 32, (int)b);
           if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1; }
         }
       }
     }
   } else if (warp == 1 || warp == kMpC2Warp) {
     // ------------------------------------------------------------ MMA issuers (warp-uniform; elected lane issues)
-    constexpr uint32_t idesc = umma_idesc_f16(CH, F16);
-    constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
+    constexpr uint32_t idesc32 = umma_idesc_f16(32, F16), idesc64 = umma_idesc_f16(64, F16);
+    constexpr uint32_t a_hi = umma_desc_hi(ROWB);    // activations / h: 128-byte rows, SWIZZLE_128B
+    constexpr uint32_t w_hi = umma_desc_hi(64);      // weight blocks: 64-byte rows, SWIZZLE_64B
     const uint32_t leader = elect_one();
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smemA)), w_lo0 = umma_desc_lo(smem_u32(smemW));
     const uint32_t h_lo0 = umma_desc_lo(smem_u32(smemH));
     const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
-    constexpr uint32_t h_buf16 = (uint32_t)(kMpHRows * ROWB) >> 4;
+    const uint32_t h_buf16 = (uint32_t)hrows_bytes >> 4;
     mbar_wait(w_full, 0);
     tc_fence_after();
+    // all MMAs of one conv on one operand tile: NACC accumulators x K = 32 per job
+    auto run_jobs = [&](int jb, int je, uint32_t src_lo, uint32_t d_base, bool always_acc) {
+      for (int q = jb; q < je; ++q) {
+        const MpJob job = p.jobs[q];
+        const uint32_t idesc = (job.flags & 1) ? idesc64 : idesc32;
+        const uint32_t init = (job.flags & 2) && !always_acc ? 0u : 1u;
+        const uint32_t a0 = src_lo + job.a_off16, w0 = w_lo0 + job.w_off16, d0 = d_base + job.d_off;
+#pragma unroll
+        for (int acc = 0; acc < NACC; ++acc)
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_f16_lohi(d0 + acc * 64, a0 + ((acc * 128 * ROWB + kk * 32) >> 4), a_hi, w0 + ((kk * 32) >> 4), w_hi, idesc,
+                          kk == 0 ? init : 1u, leader);
+      }
+    };
     if (warp == 1) {
-      // c1 stream: acc1[n & 1] = c1_j(A(i, j)), n = running (tile, branch) index
+      // c1 stream: acc1[n & 1] = c1_j(A(n))
       uint32_t sa = 0, pa = 0, n = 0;
       for (int i = 0; i < my_tiles; ++i) {
         for (int j = 0; j < nbr; ++j, ++n) {
@@ -139,18 +168,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
           mbar_wait(&acc1_empty[as], ((n >> 1) & 1) ^ 1);
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
-          const uint32_t d_base = tmem_base + as * ACC_COLS;
-          const uint32_t tap_step16 = (uint32_t)(p.dil[j] * ROWB) >> 4;
-          uint32_t at = a_lo0 + sa * a_stage16, wt = w_lo0 + p.w1_tap[j] * (B_STAGE >> 4);
-          const int k = p.k[j];
-          for (int tap = 0; tap < k; ++tap, at += tap_step16, wt += B_STAGE >> 4) {
-#pragma unroll
-            for (int acc = 0; acc < 2; ++acc)
-#pragma unroll
-              for (int kk = 0; kk < KC / 16; ++kk)
-                umma_f16_lohi(d_base + acc * CH, at + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
-                              desc_hi, idesc, (tap > 0 || kk > 0) ? 1u : 0u, leader);
-          }
+          run_jobs(p.job_beg[2 * j], p.job_beg[2 * j + 1], a_lo0 + sa * a_stage16, tmem_base + as * ACC_COLS, false);
           if (leader) {
             umma_commit(&acc1_full[as]);
             umma_commit(&a_empty[sa]);
@@ -159,31 +177,21 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
         }
       }
     } else {
-      // c2 stream: acc2[i & 1] (+)= c2_j(h(i, j)); the branch sum is formed in the accumulator
-      uint32_t n = 0;
+      // c2 stream: acc2[i & 1] (+)= c2_j(h(n)); the branch sum is formed in the accumulator
+      uint32_t hb = 0, ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t as = i & 1;
-        const uint32_t d_base = tmem_base + 2 * ACC_COLS + as * ACC_COLS;
-        for (int j = 0; j < nbr; ++j, ++n) {
-          const uint32_t hb = n & 1;
-          mbar_wait(&h_full[hb], (n >> 1) & 1);
+        for (int j = 0; j < nbr; ++j) {
+          mbar_wait(&h_full[hb], ph);
           if (j == 0) mbar_wait(&acc2_empty[as], ((i >> 1) & 1) ^ 1);
           tc_fence_after();
-          uint32_t ht = h_lo0 + hb * h_buf16 + ((uint32_t)((hmax - p.hk[j]) * ROWB) >> 4);
-          uint32_t wt = w_lo0 + p.w2_tap[j] * (B_STAGE >> 4);
-          const int k = p.k[j];
-          for (int tap = 0; tap < k; ++tap, ht += ROWB >> 4, wt += B_STAGE >> 4) {
-#pragma unroll
-            for (int acc = 0; acc < 2; ++acc)
-#pragma unroll
-              for (int kk = 0; kk < KC / 16; ++kk)
-                umma_f16_lohi(d_base + acc * CH, ht + ((acc * 128 * ROWB + kk * 32) >> 4), desc_hi, wt + ((kk * 32) >> 4),
-                              desc_hi, idesc, (j > 0 || tap > 0 || kk > 0) ? 1u : 0u, leader);
-          }
+          run_jobs(p.job_beg[2 * j + 1], p.job_beg[2 * j + 2], h_lo0 + hb * h_buf16, tmem_base + 2 * ACC_COLS + as * ACC_COLS,
+                   j > 0);
           if (leader) {
             umma_commit(&h_empty[hb]);
             if (j == nbr - 1) umma_commit(&acc2_full[as]);
           }
+          if (++hb == (uint32_t)NH) { hb = 0; ph ^= 1; }
         }
       }
     }
@@ -193,41 +201,42 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
     const int q = warp & 3;
     const int grp = (warp - 2) >> 3;          // 0: epi1 (h producer), 1: epi2 (output)
     const int hsel = ((warp - 2) & 7) >> 2;   // which of the group's two warps on this TMEM lane quadrant
-    const int c0 = hsel * 16;                 // this warp's 16-column chunk (of both 128-row accumulators)
-    const int L = p.L, C = CH;
+    const int ch0 = hsel * 16;                // this warp's 16 channels, of both time phases (columns ch0 and 32 + ch0)
+    const int Lf = p.Lf;
     const float slope = p.slope, res_gain = p.res_gain;
     pdl_wait();   // output stores may overwrite a buffer the previous launch still reads
 
     if (grp == 0) {
-      // h(i, j) = lrelu(c1_j + b1_j), zero outside the utterance, written as c2's swizzled K-major A operand
-      float4 breg[kMpMaxBr][4];   // biases of this warp's 16 columns, per branch, in registers
+      // h(n) = lrelu(c1_j + b1_j), zero outside the utterance, written as c2's swizzled K-major A operand
+      float4 breg[kMpMaxBr][4];   // biases of this warp's 16 channels, per branch, in registers
 #pragma unroll
       for (int j = 0; j < kMpMaxBr; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) breg[j][e] = *reinterpret_cast<const float4*>(sbias + j * CH + c0 + 4 * e);
-      uint32_t n = 0;
+        for (int e = 0; e < 4; ++e) breg[j][e] = *reinterpret_cast<const float4*>(sbias + j * 32 + ch0 + 4 * e);
+      uint32_t n = 0, hb = 0, ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t tile = blockIdx.x + i * gridDim.x;
         uint32_t b, mt;
         p.div_m.divmod(tile, b, mt);
-        const int t0 = mt * p.bmo;
+        const int m0 = mt * p.bmo;
 #pragma unroll
         for (int j = 0; j < kMpMaxBr; ++j) {
           if (j >= nbr) break;
-          const uint32_t as = n & 1, hb = n & 1, ph = (n >> 1) & 1;
-          uint8_t* const hbuf = smemH + hb * kMpHRows * ROWB;
-          mbar_wait(&acc1_full[as], ph);
+          const uint32_t as = n & 1;
+          uint8_t* const hbuf = smemH + hb * hrows_bytes;
+          mbar_wait(&acc1_full[as], (n >> 1) & 1);
           tc_fence_after();
           bool h_free = false;
 #pragma unroll
-          for (int acc = 0; acc < 2; ++acc) {
+          for (int it = 0; it < 2 * NACC; ++it) {
+            const int acc = it >> 1, c0 = ch0 + (it & 1) * 32;   // column chunk: (phase it & 1, channels ch0 ..)
             const int r = acc * 128 + q * 32 + lane;
-            const int th = t0 - hmax + r;
+            const int fr = m0 - hm + r;
             uint32_t a[16];
             __syncwarp();
-            tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + acc * CH + c0, a);
+            tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + acc * 64 + c0, a);
             tmem_ld_wait();
-            const bool inside = th >= 0 && th < L;
+            const bool inside = fr >= 0 && fr < Lf;
             uint4 o[2];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -247,7 +256,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
               mbar_wait(&h_empty[hb], ph ^ 1);
               h_free = true;
             }
-            const uint32_t sw = (r >> 1) & 3;   // 64-byte rows: 16-byte chunk index XOR address bits [7, 9)
+            const uint32_t sw = r & 7;   // 128-byte rows: 16-byte chunk index XOR address bits [7, 10)
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2)
               *reinterpret_cast<uint4*>(hbuf + r * ROWB + ((((c0 >> 3) + h2) ^ sw) << 4)) = o[h2];
@@ -260,47 +269,50 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
             mbar_arrive(&acc1_empty[as]);
           }
           ++n;
+          if (++hb == (uint32_t)NH) { hb = 0; ph ^= 1; }
         }
       }
     } else {
-      // X = lrelu((acc2 + sum b2 + sum_j x(P_j)) / nk): residuals from the resident activation tiles
+      // X = lrelu((acc2 + sum b2 + sum_j x(P_j)) / nbr): residual rows re-read from global memory (L2)
       float4 b2[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) b2[e] = *reinterpret_cast<const float4*>(sbias + kMpMaxBr * CH + c0 + 4 * e);
+      for (int e = 0; e < 4; ++e) b2[e] = *reinterpret_cast<const float4*>(sbias + kMpMaxBr * 32 + ch0 + 4 * e);
       const float scale = p.scale, out_slope = p.out_slope;
       __nv_bfloat16* const out = p.out;
-      uint32_t sa = 0;   // stage of (i, 0)
+      const __nv_bfloat16* const res0 = p.res[0];
+      const __nv_bfloat16* const res1 = p.res[1];
+      const __nv_bfloat16* const res2 = p.res[2];
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t tile = blockIdx.x + i * gridDim.x;
         uint32_t b, mt;
         p.div_m.divmod(tile, b, mt);
-        const int t0 = mt * p.bmo;
+        const int m0 = mt * p.bmo;
         const uint32_t as = i & 1;
-        mbar_wait(&acc2_full[as], (i >> 1) & 1);
-        tc_fence_after();
+        bool waited = false;
 #pragma unroll
-        for (int acc = 0; acc < 2; ++acc) {
-          const int i0 = acc * 128 + q * 32;            // first output row of this warp's 32
-          uint32_t a[16];
-          __syncwarp();
-          tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + as * ACC_COLS + acc * CH + c0, a);
-          // residual rows of the three branches from their resident tiles (issued while the TMEM load is in flight)
+        for (int it = 0; it < 2 * NACC; ++it) {
+          const int acc = it >> 1, c0 = ch0 + (it & 1) * 32;
+          const int row = acc * 128 + q * 32 + lane;      // output folded row of this thread
+          const bool valid = row < p.bmo && m0 + row < Lf;
+          const long off = ((long)b * Lf + m0 + row) * 64 + c0;
+          // residual rows of the branches: this thread's 16 columns are one aligned 32-byte sector
           uint4 rx[kMpMaxBr][2];
-          uint32_t st = sa;
 #pragma unroll
           for (int j = 0; j < kMpMaxBr; ++j) {
-            if (j >= nbr) break;
-            const uint8_t* atile = smemA + st * p.a_stage_bytes;
-            const int ra = i0 + lane + hmax + p.hk[j] * p.dil[j];   // row of x(t0 + i0 + lane) in branch j's tile
-            const uint32_t sw = (ra >> 1) & 3;
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2)
-              rx[j][h2] = *reinterpret_cast<const uint4*>(atile + ra * ROWB + ((((c0 >> 3) + h2) ^ sw) << 4));
-            if (++st == (uint32_t)NA) st = 0;
+            rx[j][0] = rx[j][1] = make_uint4(0, 0, 0, 0);
+            if (j < nbr && valid) ld_stream_v8((j == 0 ? res0 : (j == 1 ? res1 : res2)) + off, rx[j][0], rx[j][1]);
           }
+          if (!waited) {
+            mbar_wait(&acc2_full[as], (i >> 1) & 1);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t a[16];
+          __syncwarp();
+          tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + as * ACC_COLS + acc * 64 + c0, a);
           tmem_ld_wait();
-          // same summation order as the unfused schedule's MRF epilogue (epilogue.cuh EPI 3): acc + bias, + residuals in
-          // branch order, * 1/nk -- the two schedules stay bit-identical
+          // same summation order as the unfused schedule's epilogues (epilogue.cuh): acc + bias, + residuals in branch
+          // order, * 1/nbr
           float v[16];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -334,21 +346,11 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
               o2[e] = pack_act2<F16>(fmaxf(v0, v0 * out_slope), fmaxf(v1, v1 * out_slope));
             }
           }
-          const int rows_valid = min(32, max(0, min(p.bmo - i0, L - (t0 + i0))));
-          if (lane < rows_valid) st_global_v8(out + ((long)b * L + t0 + i0 + lane) * C + c0, ov[0], ov[1]);
+          if (valid) st_global_v8(out + off, ov[0], ov[1]);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&acc2_empty[as]);
-          uint32_t st = sa;
-          for (int j = 0; j < nbr; ++j) {
-            mbar_arrive(&a_empty[st]);
-            if (++st == (uint32_t)NA) st = 0;
-          }
-        }
-        sa += nbr;
-        while (sa >= (uint32_t)NA) sa -= NA;
+        if (lane == 0) mbar_arrive(&acc2_empty[as]);
       }
     }
   }
@@ -367,69 +369,136 @@ int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, u
 
 static constexpr int kMpSmemBudget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 1024 /*bias*/;
 
+static int mp_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
 struct MpGeom {
-  int hmax, ntaps, a_stage, na;
-  int nboxes[kMpMaxBr];
+  int hm, ntaps, a_stage, na, nh, njobs;
+  int lo[kMpMaxBr], rows[kMpMaxBr];   // halo rows before the h tile / rows of the activation tile (multiple of 32)
   bool ok;
 };
 
-static MpGeom mp_geom(int channels, int nbr, const int* k, const int* dil) {
+static MpGeom mp_geom(int channels, int nbr, const int* k, const int* dil, int nacc) {
   MpGeom g{};
   g.ok = false;
   if (channels != 32 || nbr < 1 || nbr > kMpMaxBr) return g;
-  const int rowb = channels * 2;
+  const int mrows = 128 * nacc;
   int sumk = 0;
   for (int j = 0; j < nbr; ++j) {
-    if (k[j] % 2 == 0 || k[j] < 1 || k[j] > 17 || dil[j] < 1) return g;
+    if (k[j] % 2 == 0 || k[j] < 1 || k[j] > 15 || dil[j] < 1 || dil[j] > 16) return g;
     const int hk = (k[j] - 1) / 2;
-    g.hmax = std::max(g.hmax, hk);
-    g.nboxes[j] = (256 + 2 * hk * dil[j] + 63) / 64;
-    g.a_stage = std::max(g.a_stage, g.nboxes[j] * 64 * rowb);
+    g.hm = std::max(g.hm, (hk + 1) / 2);
+    // c1: sample offsets -d*hk .. d*hk (+1 for phase 1) -> folded rows floor(-d*hk / 2) .. floor((1 + d*hk) / 2)
+    g.lo[j] = -mp_floordiv(-dil[j] * hk, 2);
+    const int hi = mp_floordiv(1 + dil[j] * hk, 2);
+    g.rows[j] = (mrows + g.lo[j] + hi + 31) / 32 * 32;
+    g.a_stage = std::max(g.a_stage, g.rows[j] * kMpRowB);
     sumk += k[j];
+    g.njobs += (dil[j] == 1 ? k[j] + 1 : 2 * k[j]) + k[j] + 1;
   }
-  if (256 + 2 * g.hmax > kMpHRows) return g;
+  if (g.njobs > kMpMaxJobs) return g;
   g.ntaps = 2 * sumk;
-  const int fixed = g.ntaps * channels * rowb + 2 * kMpHRows * rowb;
-  g.na = std::min(kMpMaxNA, (kMpSmemBudget - fixed) / g.a_stage);
-  if (g.na < nbr + 1) return g;   // the tiles of one output tile stay resident until its epilogue has read the residuals
+  const int hbytes = (mrows + 2 * g.hm + 7) / 8 * 8 * kMpRowB;
+  const int wbytes = g.ntaps * kMpWBlock;
+  // two h buffers when two activation stages still fit, else one
+  g.nh = (wbytes + 2 * hbytes + 2 * g.a_stage <= kMpSmemBudget) ? 2 : 1;
+  g.na = std::min(kMpMaxNA, (kMpSmemBudget - wbytes - g.nh * hbytes) / g.a_stage);
+  if (g.na < 2) return g;
   g.ok = true;
   return g;
 }
 
-bool mrfp_supported(int channels, int nbr, const int* k, const int* dil) { return mp_geom(channels, nbr, k, dil).ok; }
+bool mrfp_supported(int channels, int nbr, const int* k, const int* dil) { return mp_geom(channels, nbr, k, dil, 2).ok; }
+
+// jobs of one conv (taps k, dilation d) reading an operand buffer whose row 0 is `row_base` rows before the first
+// output row's own row; weight blocks of the conv start at smem block `wbase` in reverse tap order
+static void mp_conv_jobs(MrfpParams& p, int& nj, int k, int d, int row_base, int wbase) {
+  const int hk = (k - 1) / 2;
+  auto add = [&](int s, int psi, int tap_block, int d_off, bool n64, bool init) {
+    MpJob& j = p.jobs[nj++];
+    j.a_off16 = (uint16_t)(((s + row_base) * kMpRowB + psi * 64) >> 4);
+    j.w_off16 = (uint16_t)(((wbase + tap_block) * kMpWBlock) >> 4);
+    j.d_off = (uint8_t)d_off;
+    j.flags = (uint8_t)((n64 ? 1 : 0) | (init ? 2 : 0));
+    j.pad = 0;
+  };
+  auto blk = [&](int t) { return k - 1 - t; };   // reverse tap order in shared memory
+  if (d == 1) {
+    // chunk (s, psi) <-> t0 = 2s + psi + hk: phase-0 outputs use tap t0, phase-1 outputs tap t0 - 1
+    auto sp = [&](int t0, int& s, int& psi) { s = mp_floordiv(t0 - hk, 2); psi = (t0 - hk) - 2 * s; };
+    int s, psi;
+    sp(0, s, psi);  add(s, psi, blk(0), 0, false, true);          // t0 = 0: only phase 0 (tap 0)
+    sp(k, s, psi);  add(s, psi, blk(k - 1), 32, false, true);     // t0 = k: only phase 1 (tap k - 1)
+    for (int t0 = 1; t0 < k; ++t0) {                              // interior chunks: blocks of taps t0, t0 - 1 are adjacent
+      sp(t0, s, psi);
+      add(s, psi, blk(t0), 0, true, false);
+    }
+  } else {
+    bool started[2] = {false, false};
+    for (int t = 0; t < k; ++t)
+      for (int phi = 0; phi < 2; ++phi) {
+        const int off = phi + d * (t - hk);
+        const int s = mp_floordiv(off, 2), psi = off - 2 * s;
+        add(s, psi, blk(t), phi * 32, false, !started[phi]);
+        started[phi] = true;
+      }
+  }
+}
 
 int plan_conv_mrfp(MrfpPlan* pl, int B, int L, int channels, int nbr, const int* k, const int* dil,
                    const __nv_bfloat16* const* xs, const __nv_bfloat16* w, int num_sms) {
-  const MpGeom g = mp_geom(channels, nbr, k, dil);
-  VD_CHECK(g.ok, "conv_mrfp: unsupported shape");
+  VD_CHECK(L % 2 == 0, "conv_mrfp: the utterance length must be even (2-sample folded view)");
+  // 512-sample tiles; small problems (fewer tiles than SMs) take 256-sample tiles to occupy more SMs
+  int nacc = 2;
+  {
+    const MpGeom g2 = mp_geom(channels, nbr, k, dil, 2);
+    VD_CHECK(g2.ok, "conv_mrfp: unsupported shape");
+    const int bmo2 = 256 - 2 * g2.hm;
+    if ((long)B * ((L / 2 + bmo2 - 1) / bmo2) < num_sms && mp_geom(channels, nbr, k, dil, 1).ok) nacc = 1;
+  }
+  const MpGeom g = mp_geom(channels, nbr, k, dil, nacc);
   MrfpParams& p = pl->p;
   p = MrfpParams{};
-  p.B = B; p.L = L; p.nbr = nbr;
-  p.hmax = g.hmax;
-  p.bmo = 256 - 2 * g.hmax;
+  p.B = B; p.Lf = L / 2; p.nbr = nbr;
+  p.hm = g.hm;
+  p.bmo = 128 * nacc - 2 * g.hm;
   int tap = 0;
-  for (int j = 0; j < nbr; ++j) {
-    p.k[j] = k[j]; p.dil[j] = dil[j]; p.hk[j] = (k[j] - 1) / 2;
-    p.nboxes[j] = g.nboxes[j];
-    p.a_lo[j] = -(g.hmax + p.hk[j] * dil[j]);
-    p.w1_tap[j] = tap;
+  for (int j = 0; j < nbr; ++j) {           // global packed order: all c1 convs, then all c2 convs
+    p.conv_base[2 * j] = tap; p.conv_k[2 * j] = k[j];
     tap += k[j];
   }
-  for (int j = 0; j < nbr; ++j) { p.w2_tap[j] = tap; tap += k[j]; }
+  for (int j = 0; j < nbr; ++j) {
+    p.conv_base[2 * j + 1] = tap; p.conv_k[2 * j + 1] = k[j];
+    tap += k[j];
+  }
   p.ntaps = tap;
+  int nj = 0;
+  for (int j = 0; j < nbr; ++j) {
+    p.a_lo[j] = -(g.hm + g.lo[j]);
+    p.a_boxes[j] = g.rows[j] / 32;
+    p.job_beg[2 * j] = nj;
+    mp_conv_jobs(p, nj, k[j], dil[j], g.lo[j], p.conv_base[2 * j]);       // c1: tile row = h row + s + lo
+    p.job_beg[2 * j + 1] = nj;
+    mp_conv_jobs(p, nj, k[j], 1, g.hm, p.conv_base[2 * j + 1]);          // c2: h row = output row + s + hm
+  }
+  p.job_beg[2 * nbr] = nj;
+  VD_CHECK(nj <= kMpMaxJobs, "conv_mrfp: job table overflow");
   p.a_stage_bytes = g.a_stage;
   p.na_stages = g.na;
-  p.m_tiles = (L + p.bmo - 1) / p.bmo;
+  p.nh = g.nh;
+  p.m_tiles = (p.Lf + p.bmo - 1) / p.bmo;
   p.total_tiles = B * p.m_tiles;
   p.div_m.init(p.m_tiles);
   p.scale = 1.f / nbr;
+  for (int j = 0; j < kMpMaxBr; ++j) p.res[j] = xs[j < nbr ? j : 0];
   pl->channels = channels;
+  pl->nacc = nacc;
+  pl->pdl = false;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  const int rowb = channels * 2;
-  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + (size_t)p.ntaps * channels * rowb + 2 * kMpHRows * rowb + 256 + 1024;
+  const int hbytes = (128 * nacc + 2 * g.hm + 7) / 8 * 8 * kMpRowB;
+  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + (size_t)p.nh * hbytes + (size_t)p.ntaps * kMpWBlock + 256 + 1024;
   for (int j = 0; j < kMpMaxBr; ++j) {
-    if (j < nbr) {
-      if (encode_tmap_3d(&pl->tmA[j], xs[j], channels, L, B, channels, 64, true)) return 1;
+    if (j < nbr) {   // folded view [B][L/2][64], 32-row boxes, 128-byte rows
+      if (encode_tmap_3d(&pl->tmA[j], xs[j], 64, L / 2, B, 64, 32, true)) return 1;
     } else {
       pl->tmA[j] = pl->tmA[0];
     }
@@ -438,17 +507,31 @@ int plan_conv_mrfp(MrfpPlan* pl, int B, int L, int channels, int nbr, const int*
   return 0;
 }
 
-template <int CH, bool F16>
+template <int NACC, bool F16>
 static int launch_mrfp_typed(const MrfpPlan& pl, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VD_CUDA(cudaFuncSetAttribute(conv_mrfp_kernel<CH, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VD_CUDA(cudaFuncSetAttribute(conv_mrfp_kernel<NACC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const size_t smem = pl.smem > (size_t)120 * 1024 ? pl.smem : (size_t)120 * 1024;   // one CTA per SM, see conv_tc.cu
   MrfpMaps maps;
   for (int j = 0; j < kMpMaxBr; ++j) maps.a[j] = pl.tmA[j];
-  conv_mrfp_kernel<CH, F16><<<pl.grid, kMpThreads, smem, stream>>>(maps, pl.tmW, pl.p);
+  if (pl.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(kMpThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    VD_CUDA(cudaLaunchKernelEx(&cfg, conv_mrfp_kernel<NACC, F16>, maps, pl.tmW, pl.p));
+    return 0;
+  }
+  conv_mrfp_kernel<NACC, F16><<<pl.grid, kMpThreads, smem, stream>>>(maps, pl.tmW, pl.p);
   VD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -462,9 +545,9 @@ int launch_conv_mrfp(MrfpPlan& pl, const float* const* bias1, const float* bias2
   pl.p.res_gain = 1.f / slope;
   pl.p.out_slope = out_slope;
   pl.p.out = out;
-  if (pl.channels == 32) return f16 ? launch_mrfp_typed<32, true>(pl, stream) : launch_mrfp_typed<32, false>(pl, stream);
-  set_error("conv_mrfp: no kernel instance");
-  return 1;
+  VD_CHECK(pl.channels == 32, "conv_mrfp: no kernel instance");
+  if (pl.nacc == 2) return f16 ? launch_mrfp_typed<2, true>(pl, stream) : launch_mrfp_typed<2, false>(pl, stream);
+  return f16 ? launch_mrfp_typed<1, true>(pl, stream) : launch_mrfp_typed<1, false>(pl, stream);
 }
 
 }  // namespace vd

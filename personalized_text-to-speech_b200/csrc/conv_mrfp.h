@@ -1,4 +1,5 @@
-// Host-visible plan for the fused "last pair of every MRF branch" kernel (conv_mrfp.cu).
+// Host-visible plan for the fused ResBlock1 pair / "last pair of every MRF branch" kernel of the C = 32 stage
+// (conv_mrfp.cu), on the 2-sample time-folded view of the tensors.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -8,31 +9,43 @@
 
 namespace vd {
 
-constexpr int kMpMaxBr = 3;    // MRF branches (resblock kernels) per stage
-constexpr int kMpMaxNA = 6;    // activation stages in flight
+constexpr int kMpMaxBr = 3;     // branches per launch (1 = a plain ResBlock pair, 3 = the MRF of the shipped config)
+constexpr int kMpMaxNA = 4;     // activation stages in flight
+constexpr int kMpMaxJobs = 160; // tensor-core jobs of all convs of a launch
+
+// One tensor-core job = NACC x 2 MMAs (K = 32): D[:, d_off .. d_off + N) += A[rows + a_off, K slice] * W_block^T
+struct MpJob {
+  uint16_t a_off16;   // (row offset * 128 + input phase * 64) >> 4, relative to the tile (A) or the h buffer
+  uint16_t w_off16;   // byte offset of the weight block in shared memory >> 4
+  uint8_t d_off;      // first accumulator column: 0, or 32 for an output-phase-1 block
+  uint8_t flags;      // bit 0: N = 64 (both output phases, two stacked tap blocks), else N = 32; bit 1: first write of its columns
+  uint16_t pad;
+};
 
 struct MrfpParams {
-  int B, L;
+  int B, Lf;                    // utterances; folded rows per utterance (L / 2)
   int nbr;                      // branches
-  int k[kMpMaxBr], dil[kMpMaxBr], hk[kMpMaxBr];   // taps, dilation of c1, (k-1)/2 per branch (c2 has dilation 1)
-  int hmax;                     // max hk: every branch's h tile covers times [t0 - hmax, t0 - hmax + 256)
-  int bmo;                      // valid output rows per tile = 256 - 2*hmax
-  int nboxes[kMpMaxBr];         // 64-row TMA boxes of branch j's activation tile (256 + 2*hk*dil rows)
-  int a_lo[kMpMaxBr];           // first row of that tile relative to t0: -(hmax + hk*dil)
-  int w1_tap[kMpMaxBr];         // first tap of c1_j / c2_j inside the packed weight set
-  int w2_tap[kMpMaxBr];
-  int ntaps;                    // total taps in the packed set (2 * sum k)
-  int a_stage_bytes, na_stages;
+  int hm;                       // h halo in folded rows: every branch's h tile covers rows [m0 - hm, m0 - hm + 128*NACC)
+  int bmo;                      // valid output folded rows per tile = 128*NACC - 2*hm
+  int a_lo[kMpMaxBr];           // first folded row of branch j's activation tile relative to m0
+  int a_boxes[kMpMaxBr];        // 32-row TMA boxes of that tile
+  int job_beg[2 * kMpMaxBr + 1];// jobs of conv c = [job_beg[c], job_beg[c+1]); conv order c1_0, c2_0, c1_1, c2_1, ...
+  int conv_base[2 * kMpMaxBr];  // first tap of conv c in the packed weights (global order: all c1, then all c2)
+  int conv_k[2 * kMpMaxBr];
+  int ntaps;                    // weight blocks (2 KB each) of the launch
+  int a_stage_bytes, na_stages, nh;
   int m_tiles, total_tiles;
   FastDiv div_m;
   const float* bias1[kMpMaxBr]; // c1 biases
   const float* bias2sum;        // sum of the branches' c2 biases
+  const __nv_bfloat16* res[kMpMaxBr];  // the branch inputs again: residuals are re-read from global memory (L2-hot)
   float slope;                  // leaky-relu inside the ResBlock (h, and the a-form the inputs are stored in)
   float res_gain;               // 1 / slope
-  float out_slope;              // leaky-relu applied to the stage output (0.1, or 0.01 before conv_post)
+  float out_slope;              // leaky-relu of the output (the ResBlock slope, or the next stage's / conv_post's)
   float scale;                  // 1 / nbr
   __nv_bfloat16* out;
   int f16;
+  MpJob jobs[kMpMaxJobs];
 };
 
 struct MrfpPlan {
@@ -40,13 +53,15 @@ struct MrfpPlan {
   CUtensorMap tmW;
   MrfpParams p;
   int channels;
+  int nacc;         // 128-row accumulators per conv per tile (2; 1 for small problems)
   int grid;
   size_t smem;
+  bool pdl;
 };
 
-// true when the three (or fewer) branches' last pairs fit the kernel: C = 32, both weight sets of every branch resident
+// true when the launch fits: C = 32, even length, both weight sets of every branch resident next to the tiles
 bool mrfp_supported(int channels, int nbr, const int* k, const int* dil);
-// xs[j]: a-form input of branch j's last pair [B][L][C]; w: packed [ntaps][C][C] in the order c1_0, c1_1, .., c2_0, ..
+// xs[j]: a-form input of branch j's pair [B][L][C], L even; w: packed taps [ntaps][C][C] in the order c1_0, c1_1, .., c2_0, ..
 int plan_conv_mrfp(MrfpPlan* pl, int B, int L, int channels, int nbr, const int* k, const int* dil,
                    const __nv_bfloat16* const* xs, const __nv_bfloat16* w, int num_sms);
 int launch_conv_mrfp(MrfpPlan& pl, const float* const* bias1, const float* bias2sum, float slope, float out_slope,

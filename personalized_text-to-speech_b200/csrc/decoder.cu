@@ -470,6 +470,27 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
                             (d->pairf == 2 || pairf_preferred(d->layers[pit->second].c_out, d->layers[pit->second].k,
                                                               d->layers[pit->second].dil));
         const bool pair_p = pit != d->l_pair.end() && d->layers[pit->second].pair_plain;
+        // C = 32: the same pair on the 2-sample folded view (conv_mrfp.cu with one branch): N = 64 MMAs, 512-sample tiles
+        const bool pair_m = pit != d->l_pair.end() && d->mrfp && L % 2 == 0 && d->layers[pit->second].pair_plain &&
+                            mrfp_supported(d->layers[pit->second].c_out, 1, &d->layers[pit->second].k,
+                                           &d->layers[pit->second].dil);
+        if (!last && d->impl == 0 && d->fuse_pairs && pair_m && !(pair_f && d->pairf == 2)) {
+          bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2j;
+          const Layer& pv = d->layers[pit->second];
+          Step s{};
+          s.layer = pit->second;
+          s.L = L;
+          s.xs[0] = cur;
+          s.ep = ep0(convs[2 * m]);
+          s.ep.out = dst;
+          s.is_mrfp = true;
+          s.mrfp_out_slope = kSlope;
+          s.tc.p.g.B = B;
+          if (plan_conv_mrfp(&s.mrfp, B, L, pv.c_out, 1, &pv.k, &pv.dil, &cur, pv.w, d->num_sms)) return 1;
+          pl.steps.push_back(s);
+          cur = dst;
+          continue;
+        }
         if (!last && d->impl == 0 && d->fuse_pairs && (pair_f || pair_p)) {
           // whole pair in one launch: h stays in shared memory
           bf16* dst = ((npairs - 2 - m) % 2 == 0) ? Pj : T2j;
@@ -569,10 +590,11 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   // prologue early (barrier init, TMEM allocation, descriptor prefetch, resident-weight loads: a few of the ~15 us a small
   // launch takes).  Long launches gain nothing (one CTA per SM, no room for the dependent's CTAs) and measured slower.
   for (Step& s : pl.steps) {
-    const int tiles = s.is_pair ? s.pair.p.total_tiles : s.tc.p.total_tiles;   // at most two tile rounds: a short launch
-    const bool on = d->impl == 0 && !s.is_pairf && !s.is_mrfp && (d->pdl == 2 || (d->pdl == 1 && tiles <= 2 * d->num_sms));
-    s.tc.pdl = on && !s.is_pair;
+    const int tiles = s.is_mrfp ? s.mrfp.p.total_tiles : (s.is_pair ? s.pair.p.total_tiles : s.tc.p.total_tiles);
+    const bool on = d->impl == 0 && !s.is_pairf && (d->pdl == 2 || (d->pdl == 1 && tiles <= 2 * d->num_sms));   // a short launch
+    s.tc.pdl = on && !s.is_pair && !s.is_mrfp;
     s.pair.pdl = on && s.is_pair;
+    s.mrfp.pdl = on && s.is_mrfp;
   }
   pl.post_tc = false;
   Layer& lp = d->layers[d->l_post];
@@ -600,11 +622,12 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
 static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
   Layer& ly = d->layers[s.layer];
   if (s.is_mrfp) {
-    const int nk = (int)ly.members.size() / 2;
+    const int nk = (int)ly.members.size() / 2;   // kPair: {c1, c2}; kMrfPair: c1 of every branch, then c2 of every branch
     const float* b1[kMpMaxBr] = {nullptr, nullptr, nullptr};
     for (int j = 0; j < nk; ++j) b1[j] = d->layers[ly.members[j]].bias;
-    // sum of the c2 biases: the fused-MRF virtual layer of the same stage keeps it (rebuilt at every load)
-    const float* b2 = d->layers[d->layers[ly.members[nk]].mrf_group].bias;
+    // MRF: sum of the c2 biases, kept by the fused-MRF virtual layer of the same stage (rebuilt at every load)
+    const float* b2 = ly.kind == kMrfPair ? d->layers[d->layers[ly.members[nk]].mrf_group].bias
+                                          : d->layers[ly.members[1]].bias;
     return launch_conv_mrfp(s.mrfp, b1, b2, kSlope, s.mrfp_out_slope, s.ep.out, st, d->fp16);
   }
   if (s.is_pairf)

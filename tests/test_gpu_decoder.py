@@ -196,15 +196,20 @@ def test_fused_pairs_equal_unfused_schedule():
     B, T = 2, 150
     z = torch.randn(B, hp.initial_channel, T, device=DEV)
     g = torch.randn(B, hp.gin_channels, 1, device=DEV)
-    G.set_option("fold", 0)   # the time-folded form sums in a different order; compare like with like
+    G.set_option("fold", 0)   # the time-folded forms sum in a different order; compare like with like:
+    G.set_option("mrfp", 0)   # conv_pair.cu (plain tiles, taps in order) against one launch per conv
     with torch.no_grad():
         a = G(z, g)
         n_fused = G.last_launch_count()
         G.set_option("fuse_pairs", 0)
         b = G(z, g)
         n_plain = G.last_launch_count()
+        G.set_option("fuse_pairs", 1)
+        G.set_option("mrfp", 1)   # default: the C = 32 pairs on the 2-sample folded view (conv_mrfp.cu), another tap order
+        c = G(z, g)
     assert n_fused < n_plain
     assert torch.equal(a, b)
+    assert snr_db(a.cpu(), c.cpu()) > 45.0
 
 
 def test_time_folded_schedule_tracks_the_unfolded_one():
@@ -574,10 +579,11 @@ def test_default_path_keeps_plans_and_reports_graph_failures():
 
 @pytest.mark.parametrize("B,T", [(1, 1), (1, 7), (3, 32), (2, 100), (16, 20)])
 def test_fused_last_pairs_launch_matches_separate_launches(B, T):
-    """conv_mrfp.cu (option "mrfp", default on): the last ResBlock pair of every MRF branch of the C = 32 stage, the branch
-    sum and the average in ONE launch.  Against the schedule it replaces (three c1 launches + the fused-MRF launch): bit
-    for bit on plain tiles (fold=0: same accumulation order), and within bf16 re-rounding of each other on the default
-    folded schedule; both inside the stated tolerance of the fp32 restatement.  Three launches fewer per decode."""
+    """conv_mrfp.cu (option "mrfp", default on): every ResBlock pair of the C = 32 stage on the 2-sample folded view, and
+    the last pair of every MRF branch, the branch sum and the average in ONE launch.  Against the schedule it replaces
+    (conv_pair.cu pairs, three c1 launches + the fused-MRF launch): within bf16 re-rounding of each other (the folded
+    kernels accumulate the taps in another order), both inside the stated tolerance of the fp32 restatement.  Three
+    launches fewer per decode."""
     hp = oracle.FINETUNE_SPEAKER
     G, sd = build(hp, 41)
     rs = np.random.RandomState(B * 31 + T)
@@ -592,7 +598,7 @@ def test_fused_last_pairs_launch_matches_separate_launches(B, T):
                 G.set_option("mrfp", mrfp)
                 out[fold, mrfp] = G(z.to(DEV), g.to(DEV)).cpu()
                 out["n", fold, mrfp] = G.last_launch_count()
-    assert torch.equal(out[0, 0], out[0, 1])
+    assert snr_db(out[0, 0], out[0, 1]) > 45.0
     assert snr_db(out[1, 0], out[1, 1]) > 45.0
     assert out["n", 1, 1] == out["n", 1, 0] - 3 and out["n", 0, 1] == out["n", 0, 0] - 3
     if T >= 7:

@@ -136,7 +136,7 @@ def test_infer_runs_unchanged_and_matches_the_stock_model(ref_models, flow):
     assert torch.equal(mask, mask_ref)
     tol = dict(snr_min=30.0, frac=0.05) if flow else {}
     check(o_ref.cpu(), o.cpu(), **tol)
-    audio = o[0][0, 0].data.cpu().float().numpy()     # cmd_inference.py:114
+    audio = (o, attn, mask)[0][0, 0].data.cpu().float().numpy()     # cmd_inference.py:114 indexes the returned tuple
     assert audio.shape == (o.shape[2],) and np.isfinite(audio).all()
     # the decoder alone on exactly the latent the stock decoder saw
     with torch.no_grad():
