@@ -28,6 +28,10 @@ if os.environ.get("VITSDEC_TRACE") == "1":   # debug build with per-tile clock64
     NVCC_FLAGS = NVCC_FLAGS + ["-DVITSDEC_TRACE=1"]
 
 
+if os.environ.get("VITSDEC_WAIT_HINT_NS"):   # experiment: suspend-time hint of mbarrier.try_wait (ptx.cuh)
+    NVCC_FLAGS = NVCC_FLAGS + ["-DVITSDEC_WAIT_HINT_NS=" + os.environ["VITSDEC_WAIT_HINT_NS"]]
+
+
 if os.environ.get("VITSDEC_SPIN_SLEEP"):   # experiment: back-off (ns) between failed mbarrier polls
     NVCC_FLAGS = NVCC_FLAGS + ["-DVITSDEC_SPIN_SLEEP=" + os.environ["VITSDEC_SPIN_SLEEP"]]
 

@@ -21,8 +21,11 @@
 //   TMA A(n) -> c1(n) [acc1, 2 TMEM buffers] -> epi1: h(n) = lrelu(acc1 + b1_j), 0 outside the utterance -> smem
 //   [swizzled K-major A operand of c2, 1-2 buffers] -> c2(n) [+= acc2(i), 2 TMEM buffers]
 //   after the last branch: epi2(i) = (acc2 + sum b2 + sum_j x(P_j)) / nbr -> lrelu -> global.
-// The residual rows x(P_j) are re-read from global memory (the tile passed through L2 a moment ago), so an activation
-// stage is free again as soon as c1 has retired.  Two MMA-issuing warps (c1 stream / c2 stream), two epilogue groups of
+// The residual rows x(P_j) come from the resident activation tiles when shared memory has a stage to spare beyond the
+// tile's own (single pairs: the tile stays until its output epilogue has read it); with three branches there is room for
+// two stages only, so a stage is released as soon as its c1 has retired and the residual rows are re-read from global
+// memory (they hit L2 there: 679 MB of DRAM reads for 678 MB of inputs; for the short k = 3 pairs the same re-read
+// missed L2 for 3/4 of the rows and exposed the DRAM latency once per item).  Two MMA-issuing warps (c1 stream / c2 stream), two epilogue groups of
 // 8 warps (h producer / output), as in conv_pair.cu.
 #include <algorithm>
 
@@ -61,7 +64,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
   uint8_t* smemW = smemH + NH * hrows_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smemW + p.ntaps * kMpWBlock);
   uint64_t* a_full = bars;                  // [kMpMaxNA]
-  uint64_t* a_empty = a_full + kMpMaxNA;    // [kMpMaxNA]  c1 retired
+  uint64_t* a_empty = a_full + kMpMaxNA;    // [kMpMaxNA]
   uint64_t* acc1_full = a_empty + kMpMaxNA;
   uint64_t* acc1_empty = acc1_full + 2;
   uint64_t* acc2_full = acc1_empty + 2;
@@ -80,7 +83,9 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < nbr; ++j) tma_prefetch_desc(&tm.a[j]);
     tma_prefetch_desc(&tmW);
-    for (int i = 0; i < kMpMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    // an activation stage is free when c1 has retired -- and, when the residual is read from it, when the 8 output
+    // epilogue warps are done with it too
+    for (int i = 0; i < kMpMaxNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], p.res_smem ? 1 + kMpEpiWarps / 2 : 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kMpEpiWarps / 2);
       mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kMpEpiWarps / 2);
@@ -219,6 +224,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
         uint32_t b, mt;
         p.div_m.divmod(tile, b, mt);
         const int m0 = mt * p.bmo;
+        const bool edge_tile = m0 - hm < 0 || m0 - hm + MROWS > Lf;   // warp-uniform
 #pragma unroll
         for (int j = 0; j < kMpMaxBr; ++j) {
           if (j >= nbr) break;
@@ -236,7 +242,10 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
             __syncwarp();
             tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + acc * 64 + c0, a);
             tmem_ld_wait();
+            // leaky-relu as max(v, slope * v) (slope in (0, 1]); rows outside the utterance are c2's zero padding -- only
+            // the first / last tiles of an utterance have any, the others skip the per-element select
             const bool inside = fr >= 0 && fr < Lf;
+            const float2 sl2 = make_float2(slope, slope);
             uint4 o[2];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -245,13 +254,13 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
               for (int e = 0; e < 4; ++e) {
                 const int jj = h2 * 8 + e * 2;
                 const float4 bq = breg[j][jj >> 2];
-                float v0 = __uint_as_float(a[jj]) + ((jj & 3) == 0 ? bq.x : bq.z);
-                float v1 = __uint_as_float(a[jj + 1]) + ((jj & 3) == 0 ? bq.y : bq.w);
-                v0 = inside ? fmaxf(v0, v0 * slope) : 0.f;
-                v1 = inside ? fmaxf(v1, v1 * slope) : 0.f;
-                o2[e] = pack_act2<F16>(v0, v1);
+                const float2 v = fadd2(make_float2(__uint_as_float(a[jj]), __uint_as_float(a[jj + 1])),
+                                       (jj & 3) == 0 ? make_float2(bq.x, bq.y) : make_float2(bq.z, bq.w));
+                const float2 t = fmul2(v, sl2);
+                o2[e] = pack_act2<F16>(fmaxf(v.x, t.x), fmaxf(v.y, t.y));
               }
             }
+            if (edge_tile && !inside) o[0] = o[1] = make_uint4(0, 0, 0, 0);
             if (!h_free) {  // the c2 that last read this h buffer must have retired before it is overwritten
               mbar_wait(&h_empty[hb], ph ^ 1);
               h_free = true;
@@ -282,6 +291,8 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
       const __nv_bfloat16* const res0 = p.res[0];
       const __nv_bfloat16* const res1 = p.res[1];
       const __nv_bfloat16* const res2 = p.res[2];
+      const bool res_smem = p.res_smem != 0;
+      uint32_t sa = 0;   // activation stage of (tile i, branch 0)
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t tile = blockIdx.x + i * gridDim.x;
         uint32_t b, mt;
@@ -297,30 +308,46 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
           const long off = ((long)b * Lf + m0 + row) * 64 + c0;
           // residual rows of the branches: this thread's 16 columns are one aligned 32-byte sector
           uint4 rx[kMpMaxBr][2];
+          if (!res_smem) {
 #pragma unroll
-          for (int j = 0; j < kMpMaxBr; ++j) {
-            rx[j][0] = rx[j][1] = make_uint4(0, 0, 0, 0);
-            if (j < nbr && valid) ld_stream_v8((j == 0 ? res0 : (j == 1 ? res1 : res2)) + off, rx[j][0], rx[j][1]);
+            for (int j = 0; j < kMpMaxBr; ++j) {
+              rx[j][0] = rx[j][1] = make_uint4(0, 0, 0, 0);
+              if (j < nbr && valid) ld_stream_v8((j == 0 ? res0 : (j == 1 ? res1 : res2)) + off, rx[j][0], rx[j][1]);
+            }
           }
           if (!waited) {
-            mbar_wait(&acc2_full[as], (i >> 1) & 1);
+            mbar_wait(&acc2_full[as], (i >> 1) & 1);   // (implies that every c1 of the tile has retired: the tiles are complete)
             tc_fence_after();
             waited = true;
           }
           uint32_t a[16];
           __syncwarp();
           tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + as * ACC_COLS + acc * 64 + c0, a);
+          if (res_smem) {
+            uint32_t st = sa;
+#pragma unroll
+            for (int j = 0; j < kMpMaxBr; ++j) {
+              if (j >= nbr) break;
+              const uint8_t* atile = smemA + st * p.a_stage_bytes;
+              const int ra = row - p.a_lo[j];             // row of this output row's own samples in branch j's tile
+              const uint32_t sw = ra & 7;
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2)
+                rx[j][h2] = *reinterpret_cast<const uint4*>(atile + ra * ROWB + ((((c0 >> 3) + h2) ^ sw) << 4));
+              if (++st == (uint32_t)NA) st = 0;
+            }
+          }
           tmem_ld_wait();
           // same summation order as the unfused schedule's epilogues (epilogue.cuh): acc + bias, + residuals in branch
-          // order, * 1/nbr
-          float v[16];
+          // order, * 1/nbr; packed fp32 adds / multiplies (two elements per issue slot)
+          float2 v[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            v[4 * e] = __uint_as_float(a[4 * e]) + b2[e].x;
-            v[4 * e + 1] = __uint_as_float(a[4 * e + 1]) + b2[e].y;
-            v[4 * e + 2] = __uint_as_float(a[4 * e + 2]) + b2[e].z;
-            v[4 * e + 3] = __uint_as_float(a[4 * e + 3]) + b2[e].w;
+            v[2 * e] = fadd2(make_float2(__uint_as_float(a[4 * e]), __uint_as_float(a[4 * e + 1])), make_float2(b2[e].x, b2[e].y));
+            v[2 * e + 1] = fadd2(make_float2(__uint_as_float(a[4 * e + 2]), __uint_as_float(a[4 * e + 3])),
+                                 make_float2(b2[e].z, b2[e].w));
           }
+          const float2 g2 = make_float2(res_gain, res_gain);
 #pragma unroll
           for (int j = 0; j < kMpMaxBr; ++j) {
             if (j >= nbr) break;
@@ -330,27 +357,41 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 xr = unpack_act2<F16>(r2[e]);
-                v[h2 * 8 + e * 2] += xr.x >= 0.f ? xr.x : xr.x * res_gain;        // a-form -> residual stream
-                v[h2 * 8 + e * 2 + 1] += xr.y >= 0.f ? xr.y : xr.y * res_gain;
+                const float2 xg = fmul2(xr, g2);
+                // a-form -> residual stream: a >= 0 ? a : a * res_gain  ==  min(a, a * res_gain) for res_gain >= 1
+                v[h2 * 4 + e] = fadd2(v[h2 * 4 + e], make_float2(fminf(xr.x, xg.x), fminf(xr.y, xg.y)));
               }
             }
           }
+          const float2 os2 = make_float2(out_slope, out_slope), sc2 = make_float2(scale, scale);
           uint4 ov[2];
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             uint32_t* o2 = reinterpret_cast<uint32_t*>(&ov[h2]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int jj = h2 * 8 + e * 2;
-              const float v0 = v[jj] * scale, v1 = v[jj + 1] * scale;
-              o2[e] = pack_act2<F16>(fmaxf(v0, v0 * out_slope), fmaxf(v1, v1 * out_slope));
+              float2 w = v[h2 * 4 + e];
+              if (nbr > 1) w = fmul2(w, sc2);     // (x 1 would be exact anyway; a single pair skips the instruction)
+              const float2 t = fmul2(w, os2);
+              o2[e] = pack_act2<F16>(fmaxf(w.x, t.x), fmaxf(w.y, t.y));
             }
           }
           if (valid) st_global_v8(out + off, ov[0], ov[1]);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc2_empty[as]);
+        if (lane == 0) {
+          mbar_arrive(&acc2_empty[as]);
+          if (res_smem) {
+            uint32_t st = sa;
+            for (int j = 0; j < nbr; ++j) {
+              mbar_arrive(&a_empty[st]);
+              if (++st == (uint32_t)NA) st = 0;
+            }
+          }
+        }
+        sa += nbr;
+        while (sa >= (uint32_t)NA) sa -= NA;
       }
     }
   }
@@ -485,6 +526,7 @@ int plan_conv_mrfp(MrfpPlan* pl, int B, int L, int channels, int nbr, const int*
   p.a_stage_bytes = g.a_stage;
   p.na_stages = g.na;
   p.nh = g.nh;
+  p.res_smem = g.na > nbr ? 1 : 0;   // room to keep a tile's stages until its output epilogue and still prefetch
   p.m_tiles = (p.Lf + p.bmo - 1) / p.bmo;
   p.total_tiles = B * p.m_tiles;
   p.div_m.init(p.m_tiles);

@@ -34,11 +34,13 @@ struct MrfpParams {
   int conv_k[2 * kMpMaxBr];
   int ntaps;                    // weight blocks (2 KB each) of the launch
   int a_stage_bytes, na_stages, nh;
+  int res_smem;                 // 1: the residual rows come from the resident activation tiles (which then stay until the
+                                // output epilogue has read them: needs na_stages > nbr); 0: re-read from global memory / L2
   int m_tiles, total_tiles;
   FastDiv div_m;
   const float* bias1[kMpMaxBr]; // c1 biases
   const float* bias2sum;        // sum of the branches' c2 biases
-  const __nv_bfloat16* res[kMpMaxBr];  // the branch inputs again: residuals are re-read from global memory (L2-hot)
+  const __nv_bfloat16* res[kMpMaxBr];  // the branch inputs again, for res_smem = 0
   float slope;                  // leaky-relu inside the ResBlock (h, and the a-form the inputs are stored in)
   float res_gain;               // 1 / slope
   float out_slope;              // leaky-relu of the output (the ResBlock slope, or the next stage's / conv_post's)

@@ -28,26 +28,35 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or a time limit passes.  Without a hint that limit
+// is short: a warp that waits for a few thousand cycles comes back hundreds of times, and every failed attempt costs ~6
+// issue slots (try_wait, branch, spin counter, compare, branch, yield).  In the fused narrow-stage kernels those polls
+// were a third of ALL instructions issued by the SM while the epilogue warps were issue-bound
+// (profiles/r02_ncu_mrfp_pairs.txt).  With a suspend-time hint the hardware keeps the thread asleep until the barrier
+// flips (wake-up after the arrive is ~60 cycles) or the hint expires.
+#ifndef VITSDEC_WAIT_HINT_NS
+#define VITSDEC_WAIT_HINT_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)VITSDEC_WAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
 // Bounded spin: a protocol bug traps (-> cudaErrorLaunchFailure on the host) instead of
-// hanging the GPU box.  2^26 polls of a HW-sleeping try_wait is tens of seconds.
+// hanging the GPU box.  2^20 attempts of up to 20 us each is tens of seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
 #ifdef VITSDEC_SPIN_SLEEP
     __nanosleep(VITSDEC_SPIN_SLEEP);
 #endif
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 20)) {
       printf("vitsdec: mbarrier timeout block %d thread %d bar@%u parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
@@ -74,6 +83,26 @@ __device__ __forceinline__ void ld_stream_v8(const void* p, uint4& lo, uint4& hi
   asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                : "l"(p));
+}
+
+// ---------------------------------------------------------------- packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2)
+// Two fp32 operations per issue slot.  The epilogues of the fused narrow-stage kernels are bound by instruction issue
+// (7-8 SASS instructions per output element and convolution before this), not by memory or the tensor pipe.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
 }
 
 // ---------------------------------------------------------------- TMA

@@ -402,6 +402,7 @@ def test_fp16_mode_schedules_agree():
     with torch.no_grad():
         y = G(z, g).clone()
         G.set_option("fold", 0)
+        G.set_option("mrfp", 0)   # plain-tile pairs (conv_pair.cu): the like-for-like partner of single launches
         a = G(z, g).clone()
         G.set_option("fuse_pairs", 0)
         b = G(z, g).clone()
