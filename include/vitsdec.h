@@ -167,6 +167,16 @@ VITSDEC_API int vitsdec_op_resblock_pair_folded(int device, const void* x_dev, c
                                                 int length, int channels, int k, int dilation, float slope,
                                                 void* stream);
 
+/* The fused narrow-stage kernel (conv_mrfp.cu) on its own: nbr ResBlock1 iterations whose results are summed and averaged,
+ *   y = lrelu( ( sum_j  c2_j( lrelu( c1_j(x_j) + b1_j ) ) + b2_j + unlrelu(x_j) ) / nbr , out_slope )
+ * nbr = 1 is one ResBlock1 loop iteration (modules.py:211-221); nbr = 3 is the last iteration of the three MRF branches plus
+ * the branch average (models.py:278-284).  xs[j]: bf16 [batch, length, 32] a-form (slope `slope`), length even;
+ * w1[j], w2[j]: fp32 [32, 32, k[j]]; c1_j has dilation[j], c2_j dilation 1.  Arrays of nbr host pointers to device data. */
+VITSDEC_API int vitsdec_op_mrf_pairs(int device, int nbr, const void* const* xs, const float* const* w1, const float* const* b1,
+                                     const float* const* w2, const float* const* b2, void* y_dev, int batch, int length,
+                                     int channels, const int* k, const int* dilation, float slope, float out_slope,
+                                     void* stream);
+
 /* Same for ConvTranspose1d(c_in, c_out, k, stride, padding=(k-stride)/2) in polyphase form:
  *   w_dev fp32 [c_in, c_out, k]; y_dev bf16 [batch, length*stride, c_out]. */
 VITSDEC_API int vitsdec_op_conv_transpose1d(int device, const void* x_dev, const float* w_dev, const float* bias_dev,

@@ -35,6 +35,11 @@
 
 namespace vd {
 
+#ifndef VITSDEC_TRACE
+#define VITSDEC_TRACE 0
+#endif
+constexpr bool kMpTrace = VITSDEC_TRACE != 0;   // tools/trace_mrfp.py: stamps 0/1 c1 issue, 2/3 c2 issue, 4/5 epi1, 6/7 epi2,
+                                                // 8 epi2 wait begin, 9 epi1 wait begin, 10 TMA issued, 11 c1 wait begin
 constexpr int kMpEpiWarps = 16;
 constexpr int kMpThreads = 64 + 32 * kMpEpiWarps + 32;  // producer, c1 issuer, 16 epilogue warps, c2 issuer
 constexpr int kMpC2Warp = 2 + kMpEpiWarps;
@@ -129,6 +134,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
         const int m0 = mt * p.bmo;
         for (int j = 0; j < nbr; ++j) {
           mbar_wait(&a_empty[sa], pa ^ 1);
+          if (kMpTrace && p.trace && blockIdx.x == 0 && i * nbr + j < 256) p.trace[(i * nbr + j) * 12 + 10] = clock64();
           mbar_expect_tx(&a_full[sa], p.a_boxes[j] * 32 * ROWB);
           for (int bx = 0; bx < p.a_boxes[j]; ++bx)
             tma_load_3d(&tm.a[j], &a_full[sa], smemA + sa * p.a_stage_bytes + bx * 32 * ROWB, 0,
@@ -170,32 +176,39 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
       for (int i = 0; i < my_tiles; ++i) {
         for (int j = 0; j < nbr; ++j, ++n) {
           const uint32_t as = n & 1;
+          const bool tr = kMpTrace && p.trace && blockIdx.x == 0 && n < 256 && lane == 0;
+          if (tr) p.trace[n * 12 + 11] = clock64();
           mbar_wait(&acc1_empty[as], ((n >> 1) & 1) ^ 1);
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
+          if (tr) p.trace[n * 12 + 0] = clock64();
           run_jobs(p.job_beg[2 * j], p.job_beg[2 * j + 1], a_lo0 + sa * a_stage16, tmem_base + as * ACC_COLS, false);
           if (leader) {
             umma_commit(&acc1_full[as]);
             umma_commit(&a_empty[sa]);
           }
+          if (tr) p.trace[n * 12 + 1] = clock64();
           if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1; }
         }
       }
     } else {
       // c2 stream: acc2[i & 1] (+)= c2_j(h(n)); the branch sum is formed in the accumulator
-      uint32_t hb = 0, ph = 0;
+      uint32_t hb = 0, ph = 0, n = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t as = i & 1;
-        for (int j = 0; j < nbr; ++j) {
+        for (int j = 0; j < nbr; ++j, ++n) {
           mbar_wait(&h_full[hb], ph);
           if (j == 0) mbar_wait(&acc2_empty[as], ((i >> 1) & 1) ^ 1);
           tc_fence_after();
+          const bool tr = kMpTrace && p.trace && blockIdx.x == 0 && n < 256 && lane == 0;
+          if (tr) p.trace[n * 12 + 2] = clock64();
           run_jobs(p.job_beg[2 * j + 1], p.job_beg[2 * j + 2], h_lo0 + hb * h_buf16, tmem_base + 2 * ACC_COLS + as * ACC_COLS,
                    j > 0);
           if (leader) {
             umma_commit(&h_empty[hb]);
             if (j == nbr - 1) umma_commit(&acc2_full[as]);
           }
+          if (tr) p.trace[n * 12 + 3] = clock64();
           if (++hb == (uint32_t)NH) { hb = 0; ph ^= 1; }
         }
       }
@@ -230,8 +243,11 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
           if (j >= nbr) break;
           const uint32_t as = n & 1;
           uint8_t* const hbuf = smemH + hb * hrows_bytes;
+          const bool tr = kMpTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && n < 256;
+          if (tr) p.trace[n * 12 + 9] = clock64();
           mbar_wait(&acc1_full[as], (n >> 1) & 1);
           tc_fence_after();
+          if (tr) p.trace[n * 12 + 4] = clock64();
           bool h_free = false;
 #pragma unroll
           for (int it = 0; it < 2 * NACC; ++it) {
@@ -277,6 +293,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
             mbar_arrive(&h_full[hb]);
             mbar_arrive(&acc1_empty[as]);
           }
+          if (tr) p.trace[n * 12 + 5] = clock64();
           ++n;
           if (++hb == (uint32_t)NH) { hb = 0; ph ^= 1; }
         }
@@ -300,6 +317,9 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
         const int m0 = mt * p.bmo;
         const uint32_t as = i & 1;
         bool waited = false;
+        const int ntr = i * nbr + nbr - 1;
+        const bool tr = kMpTrace && p.trace && blockIdx.x == 0 && warp == 2 + kMpEpiWarps / 2 && lane == 0 && ntr < 256;
+        if (tr) p.trace[ntr * 12 + 8] = clock64();
 #pragma unroll
         for (int it = 0; it < 2 * NACC; ++it) {
           const int acc = it >> 1, c0 = ch0 + (it & 1) * 32;
@@ -319,6 +339,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
             mbar_wait(&acc2_full[as], (i >> 1) & 1);   // (implies that every c1 of the tile has retired: the tiles are complete)
             tc_fence_after();
             waited = true;
+            if (tr) p.trace[ntr * 12 + 6] = clock64();
           }
           uint32_t a[16];
           __syncwarp();
@@ -390,6 +411,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
             }
           }
         }
+        if (tr) p.trace[ntr * 12 + 7] = clock64();
         sa += nbr;
         while (sa >= (uint32_t)NA) sa -= NA;
       }

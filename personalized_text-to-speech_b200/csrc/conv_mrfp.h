@@ -47,6 +47,7 @@ struct MrfpParams {
   float scale;                  // 1 / nbr
   __nv_bfloat16* out;
   int f16;
+  unsigned long long* trace;    // debug (VITSDEC_TRACE=1 builds): per-(tile, branch) clock64 stamps of CTA 0, [n][12]
   MpJob jobs[kMpMaxJobs];
 };
 

@@ -1414,6 +1414,54 @@ int vitsdec_op_resblock_pair(int device, const void* x, const float* w1, const f
   return rc;
 }
 
+int vitsdec_op_mrf_pairs(int device, int nbr, const void* const* xs, const float* const* w1, const float* const* b1,
+                         const float* const* w2, const float* const* b2, void* y, int B, int L, int channels, const int* k,
+                         const int* dilation, float slope, float out_slope, void* stream) {
+  VD_CHECK(xs && w1 && b1 && w2 && b2 && y && k && dilation, "vitsdec_op_mrf_pairs: null argument");
+  VD_CHECK(nbr >= 1 && nbr <= kMpMaxBr && L % 2 == 0 && mrfp_supported(channels, nbr, k, dilation),
+           "vitsdec_op_mrf_pairs: shape not supported by the fused kernel (C = 32, even length, <= 3 branches)");
+  DeviceGuard guard(device);
+  VD_CHECK(guard.ok, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  VD_CUDA(cudaGetDeviceProperties(&prop, device));
+  VD_CHECK(prop.major == 10, "vitsdec needs an sm_100 (B200) device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sumk = 0;
+  for (int j = 0; j < nbr; ++j) sumk += k[j];
+  bf16* w = nullptr;
+  float *scale = nullptr, *bias = nullptr;
+  const size_t tapsz = (size_t)channels * channels;
+  VD_CUDA(cudaMalloc(&w, 2 * sumk * tapsz * sizeof(bf16)));
+  VD_CUDA(cudaMalloc(&scale, 4096 * sizeof(float)));
+  VD_CUDA(cudaMalloc(&bias, (size_t)(2 * kMpMaxBr + 1) * channels * sizeof(float)));
+  int rc = 0, tap = 0;
+  for (int pass = 0; pass < 2 && !rc; ++pass)        // packed order: c1 of every branch, then c2 of every branch
+    for (int j = 0; j < nbr && !rc; ++j) {
+      const float* src = pass == 0 ? w1[j] : w2[j];
+      rc = launch_wn_scale(src, nullptr, scale, channels, channels * k[j], st) ||
+           launch_pack_conv(src, scale, w + tap * tapsz, channels, channels, k[j], st) ||
+           launch_replicate_bias(pass == 0 ? b1[j] : b2[j], bias + (pass * kMpMaxBr + j) * channels, channels, 1, st);
+      tap += k[j];
+    }
+  float* b2sum = bias + 2 * kMpMaxBr * channels;
+  if (!rc)
+    rc = launch_sum_bias(bias + kMpMaxBr * channels, nbr > 1 ? bias + (kMpMaxBr + 1) * channels : nullptr,
+                         nbr > 2 ? bias + (kMpMaxBr + 2) * channels : nullptr, nullptr, b2sum, channels, st);
+  if (!rc) {
+    MrfpPlan pl{};
+    const bf16* xin[kMpMaxBr] = {nullptr, nullptr, nullptr};
+    const float* bb[kMpMaxBr] = {nullptr, nullptr, nullptr};
+    for (int j = 0; j < nbr; ++j) { xin[j] = static_cast<const bf16*>(xs[j]); bb[j] = bias + j * channels; }
+    rc = plan_conv_mrfp(&pl, B, L, channels, nbr, k, dilation, xin, w, prop.multiProcessorCount);
+    pl.p.trace = g_trace_buffer.load();
+    rc = rc || launch_conv_mrfp(pl, bb, b2sum, slope, out_slope, static_cast<bf16*>(y), st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(w); cudaFree(scale); cudaFree(bias);
+  if (!rc && se != cudaSuccess) { set_error(std::string("op_mrf_pairs: ") + cudaGetErrorString(se)); rc = 1; }
+  return rc;
+}
+
 int vitsdec_op_resblock_pair_folded(int device, const void* x, const float* w1, const float* b1, const float* w2,
                                     const float* b2, void* y, int B, int L, int channels, int k, int dilation,
                                     float slope, void* stream) {

@@ -79,3 +79,26 @@ def resblock_pair_cl(x, w1, b1, w2, b2, dilation=1, slope=0.1, folded=False):
                                                      _ptr(ts[3]), _ptr(y), B, L, C, k, int(dilation), float(slope), st),
                 "vitsdec_op_resblock_pair")
     return y
+
+
+def mrf_pairs_cl(xs, w1s, b1s, w2s, b2s, dilations, slope=0.1, out_slope=0.1):
+    """conv_mrfp.cu on its own: len(xs) ResBlock1 iterations (C = 32, even length) summed and averaged.
+    xs[j]: bf16 [B, L, 32] a-form; w1s[j], w2s[j]: fp32 [32, 32, k_j]; c1_j has dilations[j].  -> bf16 [B, L, 32]."""
+    import ctypes
+    nbr = len(xs)
+    x0 = xs[0]
+    assert all(x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape == x0.shape for x in xs)
+    B, L, C = x0.shape
+    y = torch.empty_like(x0)
+    keep = [[t.float().contiguous() for t in ts] for ts in (w1s, b1s, w2s, b2s)]
+
+    def arr(ts):
+        return (ctypes.c_void_p * nbr)(*[t.data_ptr() for t in ts])
+
+    ks = (ctypes.c_int * nbr)(*[int(w.shape[2]) for w in w1s])
+    ds = (ctypes.c_int * nbr)(*[int(d) for d in dilations])
+    st = torch.cuda.current_stream(x0.device).cuda_stream
+    _capi.check(_capi.lib().vitsdec_op_mrf_pairs(x0.device.index or 0, nbr, arr(xs), arr(keep[0]), arr(keep[1]), arr(keep[2]),
+                                                 arr(keep[3]), _ptr(y), B, L, C, ks, ds, float(slope), float(out_slope), st),
+                "vitsdec_op_mrf_pairs")
+    return y

@@ -225,6 +225,48 @@ def test_time_folded_fused_pair_matches_torch(case):
     assert rel_err(y, y2) < 1.5e-2
 
 
+@pytest.mark.parametrize("case", [
+    # (B, L, [(k, dilation), ...]): one branch = one ResBlock1 iteration, three = the last pairs of the MRF + average
+    (1, 512, [(3, 1)]), (2, 1000, [(7, 3)]), (3, 778, [(11, 5)]), (2, 500, [(11, 1)]), (1, 2, [(3, 1)]), (1, 6, [(7, 1)]),
+    (1, 498, [(11, 3)]), (1, 502, [(11, 3)]), (1, 9000, [(3, 5)]), (16, 960, [(7, 1)]), (2, 3000, [(5, 2)]), (1, 4098, [(9, 4)]),
+    (2, 1200, [(3, 5), (7, 5), (11, 5)]), (1, 256, [(3, 5), (7, 5), (11, 5)]), (3, 2, [(3, 1), (7, 3), (11, 5)]),
+    (1, 5000, [(3, 1), (5, 3)]), (2, 2048, [(11, 5), (3, 5), (7, 5)]), (40, 600, [(3, 5), (7, 5), (11, 5)])],
+    ids=lambda c: "B%d_L%d_%s" % (c[0], c[1], "+".join("k%dd%d" % kd for kd in c[2])))
+def test_folded_narrow_stage_kernel_matches_torch(case):
+    """conv_mrfp.cu (C = 32 on the 2-sample folded view): single pairs with dilation-1 (N = 64 chunk jobs) and dilated
+    (N = 32 block jobs, odd and even dilations) first convs, and the three-branch form with the average; lengths around
+    the 500-sample tile edge, shorter than one folded row's halo, and small problems that take the 256-sample tiles."""
+    B, L, branches = case
+    torch.manual_seed(L + 7 * len(branches))
+    dev = torch.device("cuda:0")
+    C = 32
+    xs, w1s, b1s, w2s, b2s = [], [], [], [], []
+    for k, d in branches:
+        xs.append(torch.randn(B, L, C, device=dev).bfloat16())
+        w1s.append(torch.randn(C, C, k, device=dev) / (C * k) ** 0.5)
+        w2s.append(torch.randn(C, C, k, device=dev) / (C * k) ** 0.5)
+        b1s.append(torch.randn(C, device=dev) * 0.1)
+        b2s.append(torch.randn(C, device=dev) * 0.1)
+    out_slope = 0.1 if len(branches) == 1 else 0.01
+    y = ops.mrf_pairs_cl(xs, w1s, b1s, w2s, b2s, [d for _, d in branches], slope=0.1, out_slope=out_slope)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all()
+    total = 0
+    for (k, d), x, w1, b1, w2, b2 in zip(branches, xs, w1s, b1s, w2s, b2s):
+        a = x.float().transpose(1, 2)
+        h = F.conv1d(a, w1.bfloat16().float(), b1, dilation=d, padding=(k - 1) // 2 * d)
+        h = torch.where(h >= 0, h, h * 0.1).bfloat16().float()
+        total = total + F.conv1d(h, w2.bfloat16().float(), b2, padding=(k - 1) // 2) + torch.where(a >= 0, a, a / 0.1)
+    total = total / len(branches)
+    ref = torch.where(total >= 0, total, total * out_slope).transpose(1, 2)
+    assert rel_err(y, ref) < 1.5e-2   # h is re-rounded to bf16 from a sum formed in another tap order
+    if len(branches) == 1:            # and against the plain-tile pair kernel of the same iteration
+        k, d = branches[0]
+        if k % 2 == 1 and k <= 15:
+            y2 = ops.resblock_pair_cl(xs[0], w1s[0], b1s[0], w2s[0], b2s[0], dilation=d, slope=0.1)
+            assert rel_err(y, y2) < 1.5e-2
+
+
 def test_randomised_conv_shapes():
     """Seeded sweep over the supported shape space (channels, taps, dilation, ragged lengths, residual on/off, plain and
     time-folded forms): every case against torch on the same bf16 operands."""
