@@ -107,8 +107,9 @@ VITSDEC_API int vitsdec_wav_pcm16(int device, const float* wav_dev, int16_t* pcm
  *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph from the
  *          plan's third use on; 2: capture at the first use);
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
- *          "pairf" = 2 runs fused pairs through the time-folded conv_pairf.cu wherever it exists (tests / experiments);
- *          0 / 1 (default): conv_pair.cu -- the folded pair kernel is not preferred anywhere in the default schedule;
+ *          "pairf" = 1 (default) runs the k = 3 ResBlock pairs of a 128-channel stage through conv_pairf.cu (both convs as
+ *          channels-as-M tiles, h kept in shared memory); 2: every pair that kernel supports, also the time-folded C = 32 /
+ *          64 forms (tests / experiments); 0: never;
  *          "mrfp" = 0 runs the last ResBlock pair of every MRF branch as separate launches + one fused-MRF launch (default 1:
  *          where the stage is narrow enough (C = 32) one launch computes the three last pairs, the branch sum and the
  *          average, conv_mrfp.cu);

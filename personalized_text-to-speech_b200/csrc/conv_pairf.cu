@@ -1,4 +1,6 @@
-// Time-folded fused ResBlock1 pair on the sm_100a tensor cores (narrow stages, C = 32 / 64):
+// Fused ResBlock1 pair on 128-(virtual-)channel channels-as-M tiles: time-folded for the narrow stages (C = 32 / 64), and
+// on the plain view for C = 128 (r = 1: the k = 3 pairs of stage 1, whose two convs were HBM-bound launches of their own --
+// 403 + 696 MB for 2 x 46 us of tensor work; fused: one read, one write, profiles/r02_launches_*.txt):
 //     y = lrelu( c2( lrelu( c1(a) + b1 ) ) + b2 + x(a) )          (modules.py:211-221, one loop iteration)
 // Same fusion as conv_pair.cu (h never leaves the SM), but both convs run on the folded view of decoder.cu
 // fold_geom: r = 128/C time samples per row, 128 virtual channels, block-Toeplitz weights, channels-as-M tiles
@@ -40,9 +42,9 @@ __global__ void __launch_bounds__(kPfThreads, 1)
 conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ PairFParams p) {
   constexpr int KC = 64, ROWB = 128;
-  constexpr int R = 128 / CH;              // time samples (phases) per folded row
-  constexpr int RSH = CH == 32 ? 2 : 1;    // log2(R)
-  constexpr int PPC = KC / CH;             // phases per K-chunk
+  constexpr int R = 128 / CH;              // time samples (phases) per folded row (1: plain 128-channel view)
+  constexpr int RSH = CH == 32 ? 2 : (CH == 64 ? 1 : 0);    // log2(R)
+  constexpr int PPC = CH <= KC ? KC / CH : 1;               // phases per K-chunk (a dilated view needs CH <= 64)
   constexpr int NCH = 2;                   // K-chunks per folded row
   constexpr int B_STAGE = 128 * ROWB;      // one K-chunk of one folded tap: [128 virtual out channels][64]
   constexpr int HS_SUB = 256 * ROWB;       // one K-chunk of the h tile
@@ -130,7 +132,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(x_empty, (i & 1) ^ 1);
         mbar_expect_tx(x_full, p.d * NCH * xs_sub);
         for (int rho = 0; rho < p.d; ++rho) {
-          const int row0 = nlo_of(hbase, rho) + p.smin;
+          const int row0 = nlo_of(hbase, rho) + p.xmin;
           for (int ch = 0; ch < NCH; ++ch) {
             uint8_t* dst = XS + (rho * NCH + ch) * xs_sub;
             // dilated view [C][rho][phase][row][b]: a chunk is PPC phases (box {C, 1, PPC, XR, 1} -> 128-byte rows)
@@ -162,7 +164,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int hbase = (int)mt * p.WO + p.smin;
         bool wrote = false;
         for (int rho = 0; rho < p.d; ++rho) {
-          const int idx = p.rows_rho - 1 - (nlo_of(hbase, rho) + p.smin);
+          const int idx = p.rows_rho - 1 - (nlo_of(hbase, rho) + p.xmin);
           if (idx < 0 || idx >= p.XR) continue;
           for (int psi = 0; psi < R; ++psi) {
             const int rem = p.L - rho - p.d * psi;
@@ -192,7 +194,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc_fence_after();
           const uint32_t w_lo = w_lo0 + sb * (B_STAGE >> 4);
           for (int rho = 0; rho < p.d; ++rho) {
-            const uint32_t x_lo = x_lo0 + ((uint32_t)((rho * NCH + ch) * xs_sub + tap * ROWB) >> 4);
+            const uint32_t x_lo = x_lo0 + ((uint32_t)((rho * NCH + ch) * xs_sub + tap * p.dstep * ROWB) >> 4);
 #pragma unroll
             for (int kk = 0; kk < KC / 16; ++kk)
               umma_f16_lohi(tmem_base + rho * p.N1, w_lo + kk * 2, desc_hi, x_lo + kk * 2, desc_hi, idesc1,
@@ -394,6 +396,7 @@ int encode_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, u
 static constexpr int kPfSmemBudget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 1024 /*bias*/ - 16384 /*scratch*/;
 
 static int pf_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static int hk_of(int k) { return (k - 1) / 2; }
 
 struct PfGeom {
   int r, nt, smin, WO, HR, N1, XR, nw;
@@ -403,7 +406,7 @@ struct PfGeom {
 static PfGeom pf_geom(int channels, int k, int dil) {
   PfGeom g{};
   g.ok = false;
-  if ((channels != 32 && channels != 64) || k % 2 == 0 || k > 15 || dil < 1 || dil > 8) return g;
+  if ((channels != 32 && channels != 64 && channels != 128) || k % 2 == 0 || k > 15 || dil < 1 || dil > 8) return g;
   // C = 32 with a dilated c1 would need two time phases side by side in one 128-byte shared-memory row (TMA box
   // {32, 1, 2, rows}); that load did not produce the expected layout on hardware (tools/probes/tma_box_probe.cu) and the
   // 64-byte-row alternative runs the MMAs at half rate, so those pairs stay on conv_pair.cu.
@@ -416,13 +419,16 @@ static PfGeom pf_geom(int channels, int k, int dil) {
   for (int wo = 240; wo >= 64; wo -= 16) {
     const int hr = wo + g.nt - 1;
     if (hr > 256) continue;
-    // rows of one sub-sequence that hold a sample of the h tile (hr*r consecutive samples)
-    const int need = dil == 1 ? hr : (hr * r - 1) / (dil * r) + 2;
+    // rows of one sub-sequence that hold a sample of the h tile (hr*r consecutive samples); on the plain view (r = 1) a
+    // dilated c1 is one tile whose taps are `dil` rows apart, not `dil` sub-sequences
+    const bool plain = r == 1;
+    const int nsub = plain ? 1 : dil;
+    const int need = (dil == 1 || plain) ? hr : (hr * r - 1) / (dil * r) + 2;
     const int n1 = (need + 15) / 16 * 16;
-    if (dil * n1 > 256) continue;
-    const int xr = (n1 + g.nt - 1 + 7) / 8 * 8;
+    if (nsub * n1 > 256) continue;
+    const int xr = (n1 + (g.nt - 1) * (plain ? dil : 1) + 7) / 8 * 8;
     if (xr > 256) continue;
-    const int fixed = dil * 2 * xr * rowb + 2 * 256 * rowb;
+    const int fixed = nsub * 2 * xr * rowb + 2 * 256 * rowb;
     const int nw = std::min(kPfMaxW, (kPfSmemBudget - fixed) / (128 * rowb));
     if (nw < 3) continue;
     g.WO = wo; g.HR = hr; g.N1 = n1; g.XR = xr; g.nw = nw;
@@ -440,9 +446,11 @@ bool pairf_supported(int channels, int k, int dil) { return pf_geom(channels, k,
 // 347 us) and loses for k=3: the exposed h epilogue and the output epilogue's shared-memory traffic (it slows the
 // overlapping c1 MMAs from 160 to 260 cycles) eat what the wider MMAs gain (profiles/r01_trace_pairf.txt).  The kernel
 // stays reachable through option pairf=2 (tests, experiments).
+// C = 128 (plain view): the k = 3 pairs of the 128-channel stage -- their convs are HBM-bound on their own; k >= 7 is
+// MMA-bound either way and keeps the two launches.
 bool pairf_preferred(int channels, int k, int dil) {
-  (void)channels; (void)k; (void)dil;
-  return false;
+  (void)dil;
+  return channels == 128 && k <= 5;
 }
 
 int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
@@ -451,7 +459,10 @@ int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, c
   VD_CHECK(g.ok, "conv_pairf: unsupported shape");
   VD_CHECK(L % g.r == 0, "conv_pairf: the utterance length must be a multiple of the fold factor");
   PairFParams& p = pl->p;
-  p.B = B; p.L = L; p.Lf = L / g.r; p.d = dil;
+  const bool plain = g.r == 1;
+  p.B = B; p.L = L; p.Lf = L / g.r; p.d = plain ? 1 : dil;
+  p.dstep = plain ? dil : 1;
+  p.xmin = plain ? -hk_of(k) * dil : g.smin;
   p.WO = g.WO; p.HR = g.HR; p.N1 = g.N1; p.XR = g.XR; p.nt = g.nt; p.smin = g.smin; p.nw = g.nw;
   const int hk = (k - 1) / 2;
   for (int t = 0; t < g.nt; ++t) {
@@ -459,21 +470,21 @@ int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, c
     for (int psi = 0; psi < g.r; ++psi)
       for (int phi = 0; phi < g.r; ++phi)
         if (std::abs(g.r * (g.smin + t) + psi - phi) <= hk) mask |= 1u << (psi * channels / 64);  // 64-channel chunks
-    p.kmask[t] = mask;
+    p.kmask[t] = plain ? 3u : mask;   // plain 128-channel rows: both K-chunks of every tap
   }
-  p.rows_rho = (L + dil * g.r - 1) / (dil * g.r);
+  p.rows_rho = (L + p.d * g.r - 1) / (p.d * g.r);
   p.m_tiles = (p.Lf + p.WO - 1) / p.WO;
   p.total_tiles = B * p.m_tiles;
   p.div_m.init(p.m_tiles);
-  p.div_dr.init(dil * g.r);
+  p.div_dr.init(p.d * g.r);
   p.x = x;
   p.trace = nullptr;
   pl->channels = channels;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const int rowb = 128;
-  pl->smem = 1024 + (size_t)dil * 2 * g.XR * rowb + (size_t)2 * 256 * rowb + (size_t)g.nw * 128 * rowb + 256 + 1024 +
+  pl->smem = 1024 + (size_t)p.d * 2 * g.XR * rowb + (size_t)2 * 256 * rowb + (size_t)g.nw * 128 * rowb + 256 + 1024 +
              16384;
-  if (dil > 1) {
+  if (p.d > 1) {
     // [C][rho][phase][row][utterance]: sample t = dil*(r*row + phase) + rho
     // a K-chunk = 64/C phases: box {C, 1, 64/C, XR, 1} lands as 128-byte rows [phase][channel]
     if (encode_tmap_act(&pl->tmX, x, channels, dil, channels, g.r, (uint64_t)dil * channels, p.rows_rho,
@@ -513,6 +524,7 @@ int launch_conv_pairf(PairFPlan& pl, const float* bias1, const float* bias2, flo
   pl.p.out = out;
   if (pl.channels == 32) return launch_pairf_inst<32>(pl, stream);
   if (pl.channels == 64) return launch_pairf_inst<64>(pl, stream);
+  if (pl.channels == 128) return launch_pairf_inst<128>(pl, stream);
   set_error("conv_pairf: no kernel instance");
   return 1;
 }

@@ -13,7 +13,9 @@ constexpr int kPfMaxW = 8;       // weight ring stages
 
 struct PairFParams {
   int B, L, Lf;          // utterances, samples per utterance, folded rows per utterance (L / r)
-  int d;                 // dilation of c1 = number of sub-sequences of its view
+  int d;                 // sub-sequences of c1's view: its dilation on a folded view (C = 32 / 64), 1 on the plain one
+  int dstep;             // rows between c1's taps: 1, or c1's dilation on the plain 128-channel view (r = 1)
+  int xmin;              // first row of the staged x tile relative to the h tile's first row
   int WO, HR;            // output folded rows per tile (c2's N); rows of h per tile = WO + nt - 1
   int N1, XR;            // c1's N per sub-sequence; rows per staged x sub-tile
   int nt, smin;          // folded taps per conv and the first tap's row offset (both convs share k)

@@ -204,7 +204,10 @@ def test_fused_resblock_pair_matches_torch_and_unfused(case):
 
 @pytest.mark.parametrize("case", [(1, 1024, 32, 3, 1), (2, 4000, 32, 7, 1), (3, 3108, 32, 11, 1), (1, 8, 32, 7, 1),
                                   (2, 3000, 64, 3, 1), (2, 2000, 64, 7, 1), (1, 2222, 64, 11, 1), (16, 960, 32, 11, 1),
-                                  (2, 3000, 64, 3, 3), (2, 2002, 64, 7, 3), (1, 4444, 64, 11, 3), (2, 2000, 64, 7, 2)],
+                                  (2, 3000, 64, 3, 3), (2, 2002, 64, 7, 3), (1, 4444, 64, 11, 3), (2, 2000, 64, 7, 2),
+                                  # C = 128 on the plain view (r = 1): dilation = rows between taps of one tile
+                                  (2, 1000, 128, 3, 1), (1, 2240, 128, 3, 3), (3, 225, 128, 3, 5), (1, 7, 128, 3, 1),
+                                  (2, 900, 128, 7, 3), (1, 500, 128, 11, 1), (16, 448, 128, 3, 3)],
                          ids=lambda c: "B%d_L%d_C%d_k%d_d%d" % c)
 def test_time_folded_fused_pair_matches_torch(case):
     B, L, C, k, d = case
