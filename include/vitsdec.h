@@ -110,9 +110,10 @@ VITSDEC_API int vitsdec_wav_pcm16(int device, const float* wav_dev, int16_t* pcm
  *          "pairf" = 1 (default) runs the k = 3 ResBlock pairs of a 128-channel stage through conv_pairf.cu (both convs as
  *          channels-as-M tiles, h kept in shared memory); 2: every pair that kernel supports, also the time-folded C = 32 /
  *          64 forms (tests / experiments); 0: never;
- *          "mrfp" = 0 runs the last ResBlock pair of every MRF branch as separate launches + one fused-MRF launch (default 1:
- *          where the stage is narrow enough (C = 32) one launch computes the three last pairs, the branch sum and the
- *          average, conv_mrfp.cu);
+ *          "mrfp": bit 0 (C = 32 stage): every ResBlock pair on the 2-sample folded view, and the last pair of every MRF
+ *          branch + the branch sum + the average as ONE launch (conv_mrfp.cu) instead of three c1 launches and a fused-MRF
+ *          launch; bit 1: the C = 64 pairs whose weights fit (k <= 7) through the same kernel on plain rows instead of
+ *          conv_pair.cu (measured neutral: 9.05 vs 9.07 ms per step, so off by default).  Default 1; 0 = the round-1 schedule;
  *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph);
  *          "pdl" = 0 no programmatic dependent launch (default 1: launches whose grid leaves SMs idle let the next launch
  *          of the stream start its prologue early; 2: every launch);
@@ -171,8 +172,9 @@ VITSDEC_API int vitsdec_op_resblock_pair_folded(int device, const void* x_dev, c
 /* The fused narrow-stage kernel (conv_mrfp.cu) on its own: nbr ResBlock1 iterations whose results are summed and averaged,
  *   y = lrelu( ( sum_j  c2_j( lrelu( c1_j(x_j) + b1_j ) ) + b2_j + unlrelu(x_j) ) / nbr , out_slope )
  * nbr = 1 is one ResBlock1 loop iteration (modules.py:211-221); nbr = 3 is the last iteration of the three MRF branches plus
- * the branch average (models.py:278-284).  xs[j]: bf16 [batch, length, 32] a-form (slope `slope`), length even;
- * w1[j], w2[j]: fp32 [32, 32, k[j]]; c1_j has dilation[j], c2_j dilation 1.  Arrays of nbr host pointers to device data. */
+ * the branch average (models.py:278-284).  xs[j]: bf16 [batch, length, C] a-form (slope `slope`), C = 32 (length even) or
+ * C = 64 (as long as both weight sets fit in shared memory: k <= 7 for one branch); w1[j], w2[j]: fp32 [C, C, k[j]]; c1_j
+ * has dilation[j], c2_j dilation 1.  Arrays of nbr host pointers to device data. */
 VITSDEC_API int vitsdec_op_mrf_pairs(int device, int nbr, const void* const* xs, const float* const* w1, const float* const* b1,
                                      const float* const* w2, const float* const* b2, void* y_dev, int batch, int length,
                                      int channels, const int* k, const int* dilation, float slope, float out_slope,

@@ -67,7 +67,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
   uint8_t* smemA = smem;
   uint8_t* smemH = smemA + NA * p.a_stage_bytes;
   uint8_t* smemW = smemH + NH * hrows_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemW + p.ntaps * kMpWBlock);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemW + p.wbytes);
   uint64_t* a_full = bars;                  // [kMpMaxNA]
   uint64_t* a_empty = a_full + kMpMaxNA;    // [kMpMaxNA]
   uint64_t* acc1_full = a_empty + kMpMaxNA;
@@ -78,7 +78,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
   uint64_t* h_empty = h_full + 2;
   uint64_t* w_full = h_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* sbias = reinterpret_cast<float*>(bars + 32);    // 256 B of barriers, then (kMpMaxBr + 1) * 32 floats
+  float* sbias = reinterpret_cast<float*>(bars + 32);    // 256 B of barriers, then (kMpMaxBr + 1) * 64 floats (per column)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,8 +104,8 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < (kMpMaxBr + 1) * 32; i += kMpThreads) {
-    const int j = i >> 5, c = i & 31;
+  for (int i = threadIdx.x; i < (kMpMaxBr + 1) * 64; i += kMpThreads) {   // bias per accumulator column
+    const int j = i >> 6, c = p.fold == 2 ? (i & 31) : (i & 63);           // folded view: column = phase * 32 + channel
     sbias[i] = j < kMpMaxBr ? (j < nbr ? p.bias1[j][c] : 0.f) : p.bias2sum[c];
   }
   tc_fence_before();
@@ -121,10 +121,15 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
     if (lane == 0) {
       // weights: every tap block once; within a conv the blocks are stored in REVERSE tap order, so that the blocks of
       // taps t0, t0 - 1 form the stacked [64][32] operand of a dilation-1 chunk
-      mbar_expect_tx(w_full, p.ntaps * kMpWBlock);
-      for (int c = 0; c < 2 * nbr; ++c)
-        for (int t = 0; t < p.conv_k[c]; ++t)
-          tma_load_3d(&tmW, w_full, smemW + (p.conv_base[c] + p.conv_k[c] - 1 - t) * kMpWBlock, 0, 0, p.conv_base[c] + t);
+      mbar_expect_tx(w_full, p.wbytes);
+      if (p.fold == 2) {
+        for (int c = 0; c < 2 * nbr; ++c)
+          for (int t = 0; t < p.conv_k[c]; ++t)
+            tma_load_3d(&tmW, w_full, smemW + (p.conv_base[c] + p.conv_k[c] - 1 - t) * kMpWBlock, 0, 0, p.conv_base[c] + t);
+      } else {   // C = 64: a tap is two [64 out][32 in] K-halves of 4 KB, natural order
+        for (int t = 0; t < p.ntaps; ++t)
+          for (int kh = 0; kh < 2; ++kh) tma_load_3d(&tmW, w_full, smemW + (2 * t + kh) * 2 * kMpWBlock, kh * 32, 0, t);
+      }
       pdl_wait();   // the weights (static) load while the previous launch drains; activations only from here on
       uint32_t sa = 0, pa = 0;
       for (int i = 0; i < my_tiles; ++i) {
@@ -226,11 +231,6 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
 
     if (grp == 0) {
       // h(n) = lrelu(c1_j + b1_j), zero outside the utterance, written as c2's swizzled K-major A operand
-      float4 breg[kMpMaxBr][4];   // biases of this warp's 16 channels, per branch, in registers
-#pragma unroll
-      for (int j = 0; j < kMpMaxBr; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) breg[j][e] = *reinterpret_cast<const float4*>(sbias + j * 32 + ch0 + 4 * e);
       uint32_t n = 0, hb = 0, ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t tile = blockIdx.x + i * gridDim.x;
@@ -243,6 +243,12 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
           if (j >= nbr) break;
           const uint32_t as = n & 1;
           uint8_t* const hbuf = smemH + hb * hrows_bytes;
+          // biases of this warp's two 16-column chunks: shared-memory reads issued before the wait, which hides them
+          float4 breg[2][4];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) breg[hh][e] = *reinterpret_cast<const float4*>(sbias + j * 64 + ch0 + hh * 32 + 4 * e);
           const bool tr = kMpTrace && p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && n < 256;
           if (tr) p.trace[n * 12 + 9] = clock64();
           mbar_wait(&acc1_full[as], (n >> 1) & 1);
@@ -269,7 +275,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int jj = h2 * 8 + e * 2;
-                const float4 bq = breg[j][jj >> 2];
+                const float4 bq = breg[it & 1][jj >> 2];
                 const float2 v = fadd2(make_float2(__uint_as_float(a[jj]), __uint_as_float(a[jj + 1])),
                                        (jj & 3) == 0 ? make_float2(bq.x, bq.y) : make_float2(bq.z, bq.w));
                 const float2 t = fmul2(v, sl2);
@@ -300,9 +306,11 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
       }
     } else {
       // X = lrelu((acc2 + sum b2 + sum_j x(P_j)) / nbr): residual rows re-read from global memory (L2)
-      float4 b2[4];
+      float4 b2r[2][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) b2[e] = *reinterpret_cast<const float4*>(sbias + kMpMaxBr * 32 + ch0 + 4 * e);
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b2r[hh][e] = *reinterpret_cast<const float4*>(sbias + kMpMaxBr * 64 + ch0 + hh * 32 + 4 * e);
       const float scale = p.scale, out_slope = p.out_slope;
       __nv_bfloat16* const out = p.out;
       const __nv_bfloat16* const res0 = p.res[0];
@@ -361,6 +369,7 @@ conv_mrfp_kernel(const __grid_constant__ MrfpMaps tm, const __grid_constant__ CU
           tmem_ld_wait();
           // same summation order as the unfused schedule's epilogues (epilogue.cuh): acc + bias, + residuals in branch
           // order, * 1/nbr; packed fp32 adds / multiplies (two elements per issue slot)
+          const float4 (&b2)[4] = b2r[it & 1];
           float2 v[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -443,25 +452,26 @@ struct MpGeom {
 static MpGeom mp_geom(int channels, int nbr, const int* k, const int* dil, int nacc) {
   MpGeom g{};
   g.ok = false;
-  if (channels != 32 || nbr < 1 || nbr > kMpMaxBr) return g;
+  if ((channels != 32 && channels != 64) || nbr < 1 || nbr > kMpMaxBr) return g;
+  const int fold = 64 / channels;   // samples per row
   const int mrows = 128 * nacc;
   int sumk = 0;
   for (int j = 0; j < nbr; ++j) {
     if (k[j] % 2 == 0 || k[j] < 1 || k[j] > 15 || dil[j] < 1 || dil[j] > 16) return g;
     const int hk = (k[j] - 1) / 2;
-    g.hm = std::max(g.hm, (hk + 1) / 2);
-    // c1: sample offsets -d*hk .. d*hk (+1 for phase 1) -> folded rows floor(-d*hk / 2) .. floor((1 + d*hk) / 2)
-    g.lo[j] = -mp_floordiv(-dil[j] * hk, 2);
-    const int hi = mp_floordiv(1 + dil[j] * hk, 2);
+    // sample offsets -d*hk .. d*hk (+ fold - 1 for the last phase) -> rows floor(-d*hk / fold) .. floor((fold - 1 + d*hk) / fold)
+    g.hm = std::max(g.hm, -mp_floordiv(-hk, fold));
+    g.lo[j] = -mp_floordiv(-dil[j] * hk, fold);
+    const int hi = mp_floordiv(fold - 1 + dil[j] * hk, fold);
     g.rows[j] = (mrows + g.lo[j] + hi + 31) / 32 * 32;
     g.a_stage = std::max(g.a_stage, g.rows[j] * kMpRowB);
     sumk += k[j];
-    g.njobs += (dil[j] == 1 ? k[j] + 1 : 2 * k[j]) + k[j] + 1;
+    g.njobs += fold == 2 ? (dil[j] == 1 ? k[j] + 1 : 2 * k[j]) + k[j] + 1 : 4 * k[j];
   }
   if (g.njobs > kMpMaxJobs) return g;
   g.ntaps = 2 * sumk;
   const int hbytes = (mrows + 2 * g.hm + 7) / 8 * 8 * kMpRowB;
-  const int wbytes = g.ntaps * kMpWBlock;
+  const int wbytes = g.ntaps * channels * channels * 2;
   // two h buffers when two activation stages still fit, else one
   g.nh = (wbytes + 2 * hbytes + 2 * g.a_stage <= kMpSmemBudget) ? 2 : 1;
   g.na = std::min(kMpMaxNA, (kMpSmemBudget - wbytes - g.nh * hbytes) / g.a_stage);
@@ -473,18 +483,24 @@ static MpGeom mp_geom(int channels, int nbr, const int* k, const int* dil, int n
 bool mrfp_supported(int channels, int nbr, const int* k, const int* dil) { return mp_geom(channels, nbr, k, dil, 2).ok; }
 
 // jobs of one conv (taps k, dilation d) reading an operand buffer whose row 0 is `row_base` rows before the first
-// output row's own row; weight blocks of the conv start at smem block `wbase` in reverse tap order
+// output row's own row; the conv's weights start at tap `wbase` of the set in shared memory
 static void mp_conv_jobs(MrfpParams& p, int& nj, int k, int d, int row_base, int wbase) {
   const int hk = (k - 1) / 2;
-  auto add = [&](int s, int psi, int tap_block, int d_off, bool n64, bool init) {
+  auto add = [&](int s, int psi, int w_byte_off, int d_off, bool n64, bool init) {
     MpJob& j = p.jobs[nj++];
     j.a_off16 = (uint16_t)(((s + row_base) * kMpRowB + psi * 64) >> 4);
-    j.w_off16 = (uint16_t)(((wbase + tap_block) * kMpWBlock) >> 4);
+    j.w_off16 = (uint16_t)(w_byte_off >> 4);
     j.d_off = (uint8_t)d_off;
     j.flags = (uint8_t)((n64 ? 1 : 0) | (init ? 2 : 0));
     j.pad = 0;
   };
-  auto blk = [&](int t) { return k - 1 - t; };   // reverse tap order in shared memory
+  if (p.fold == 1) {
+    // C = 64, plain rows: tap t is two K = 32 jobs (input channels 0-31 / 32-63) with [64 out][32 in] weight blocks
+    for (int t = 0; t < k; ++t)
+      for (int kh = 0; kh < 2; ++kh) add((t - hk) * d, kh, ((wbase + t) * 2 + kh) * 2 * kMpWBlock, 0, true, t == 0 && kh == 0);
+    return;
+  }
+  auto blk = [&](int t) { return (wbase + k - 1 - t) * kMpWBlock; };   // C = 32: reverse tap order in shared memory
   if (d == 1) {
     // chunk (s, psi) <-> t0 = 2s + psi + hk: phase-0 outputs use tap t0, phase-1 outputs tap t0 - 1
     auto sp = [&](int t0, int& s, int& psi) { s = mp_floordiv(t0 - hk, 2); psi = (t0 - hk) - 2 * s; };
@@ -509,19 +525,23 @@ static void mp_conv_jobs(MrfpParams& p, int& nj, int k, int d, int row_base, int
 
 int plan_conv_mrfp(MrfpPlan* pl, int B, int L, int channels, int nbr, const int* k, const int* dil,
                    const __nv_bfloat16* const* xs, const __nv_bfloat16* w, int num_sms) {
-  VD_CHECK(L % 2 == 0, "conv_mrfp: the utterance length must be even (2-sample folded view)");
-  // 512-sample tiles; small problems (fewer tiles than SMs) take 256-sample tiles to occupy more SMs
+  VD_CHECK(channels == 32 || channels == 64, "conv_mrfp: 32 or 64 channels");
+  const int fold = 64 / channels;
+  VD_CHECK(L % fold == 0, "conv_mrfp: the utterance length must be even (2-sample folded view)");
+  const int Lf = L / fold;
+  // tiles of 256 rows; small problems (fewer tiles than SMs) take 128-row tiles to occupy more SMs
   int nacc = 2;
   {
     const MpGeom g2 = mp_geom(channels, nbr, k, dil, 2);
     VD_CHECK(g2.ok, "conv_mrfp: unsupported shape");
     const int bmo2 = 256 - 2 * g2.hm;
-    if ((long)B * ((L / 2 + bmo2 - 1) / bmo2) < num_sms && mp_geom(channels, nbr, k, dil, 1).ok) nacc = 1;
+    if ((long)B * ((Lf + bmo2 - 1) / bmo2) < num_sms && mp_geom(channels, nbr, k, dil, 1).ok) nacc = 1;
   }
   const MpGeom g = mp_geom(channels, nbr, k, dil, nacc);
   MrfpParams& p = pl->p;
   p = MrfpParams{};
-  p.B = B; p.Lf = L / 2; p.nbr = nbr;
+  p.B = B; p.Lf = Lf; p.nbr = nbr;
+  p.fold = fold;
   p.hm = g.hm;
   p.bmo = 128 * nacc - 2 * g.hm;
   int tap = 0;
@@ -534,6 +554,7 @@ int plan_conv_mrfp(MrfpPlan* pl, int B, int L, int channels, int nbr, const int*
     tap += k[j];
   }
   p.ntaps = tap;
+  p.wbytes = tap * channels * channels * 2;
   int nj = 0;
   for (int j = 0; j < nbr; ++j) {
     p.a_lo[j] = -(g.hm + g.lo[j]);
@@ -559,15 +580,16 @@ int plan_conv_mrfp(MrfpPlan* pl, int B, int L, int channels, int nbr, const int*
   pl->pdl = false;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const int hbytes = (128 * nacc + 2 * g.hm + 7) / 8 * 8 * kMpRowB;
-  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + (size_t)p.nh * hbytes + (size_t)p.ntaps * kMpWBlock + 256 + 1024;
+  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + (size_t)p.nh * hbytes + (size_t)p.wbytes + 256 + 1024;
   for (int j = 0; j < kMpMaxBr; ++j) {
-    if (j < nbr) {   // folded view [B][L/2][64], 32-row boxes, 128-byte rows
-      if (encode_tmap_3d(&pl->tmA[j], xs[j], 64, L / 2, B, 64, 32, true)) return 1;
+    if (j < nbr) {   // rows of 64 (virtual) channels: [B][L / fold][64], 32-row boxes, 128-byte rows
+      if (encode_tmap_3d(&pl->tmA[j], xs[j], 64, Lf, B, 64, 32, true)) return 1;
     } else {
       pl->tmA[j] = pl->tmA[0];
     }
   }
-  if (encode_tmap_3d(&pl->tmW, w, channels, channels, p.ntaps, channels, channels, true)) return 1;
+  // weight blocks with 64-byte rows: [32 out][32 in] per tap (C = 32), two [64 out][32 in] K-halves per tap (C = 64)
+  if (encode_tmap_3d(&pl->tmW, w, channels, channels, p.ntaps, 32, channels, true)) return 1;
   return 0;
 }
 
@@ -609,7 +631,7 @@ int launch_conv_mrfp(MrfpPlan& pl, const float* const* bias1, const float* bias2
   pl.p.res_gain = 1.f / slope;
   pl.p.out_slope = out_slope;
   pl.p.out = out;
-  VD_CHECK(pl.channels == 32, "conv_mrfp: no kernel instance");
+  VD_CHECK(pl.channels == 32 || pl.channels == 64, "conv_mrfp: no kernel instance");
   if (pl.nacc == 2) return f16 ? launch_mrfp_typed<2, true>(pl, stream) : launch_mrfp_typed<2, false>(pl, stream);
   return f16 ? launch_mrfp_typed<1, true>(pl, stream) : launch_mrfp_typed<1, false>(pl, stream);
 }

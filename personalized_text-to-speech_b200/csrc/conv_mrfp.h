@@ -1,5 +1,5 @@
-// Host-visible plan for the fused ResBlock1 pair / "last pair of every MRF branch" kernel of the C = 32 stage
-// (conv_mrfp.cu), on the 2-sample time-folded view of the tensors.
+// Host-visible plan for the fused ResBlock1 pair / "last pair of every MRF branch" kernel of the narrow stages
+// (conv_mrfp.cu): 64 (virtual) channels per row -- C = 32 on the 2-sample time-folded view, C = 64 on the plain one.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -32,7 +32,9 @@ struct MrfpParams {
   int job_beg[2 * kMpMaxBr + 1];// jobs of conv c = [job_beg[c], job_beg[c+1]); conv order c1_0, c2_0, c1_1, c2_1, ...
   int conv_base[2 * kMpMaxBr];  // first tap of conv c in the packed weights (global order: all c1, then all c2)
   int conv_k[2 * kMpMaxBr];
-  int ntaps;                    // weight blocks (2 KB each) of the launch
+  int ntaps;                    // taps of all convs of the launch
+  int fold;                     // samples per row: 2 (C = 32, two phases side by side) or 1 (C = 64, plain rows)
+  int wbytes;                   // bytes of all weight blocks in shared memory
   int a_stage_bytes, na_stages, nh;
   int res_smem;                 // 1: the residual rows come from the resident activation tiles (which then stay until the
                                 // output epilogue has read them: needs na_stages > nbr); 0: re-read from global memory / L2
@@ -62,7 +64,7 @@ struct MrfpPlan {
   bool pdl;
 };
 
-// true when the launch fits: C = 32, even length, both weight sets of every branch resident next to the tiles
+// true when the launch fits: C = 32 (even length) or C = 64, both weight sets of every branch resident next to the tiles
 bool mrfp_supported(int channels, int nbr, const int* k, const int* dil);
 // xs[j]: a-form input of branch j's pair [B][L][C], L even; w: packed taps [ntaps][C][C] in the order c1_0, c1_1, .., c2_0, ..
 int plan_conv_mrfp(MrfpPlan* pl, int B, int L, int channels, int nbr, const int* k, const int* dil,

@@ -443,7 +443,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     const float next_slope = (i == nstage - 1) ? kPostSlope : kSlope;
     const bool fused = d->l_mrf[i] >= 0;
     // last pairs of all branches + MRF average as one launch (conv_mrfp.cu)
-    const bool use_mrfp = fused && d->impl == 0 && d->mrfp && d->fuse_pairs && d->l_mrfp[i] >= 0 ;
+    const bool use_mrfp = fused && d->impl == 0 && (d->mrfp & 1) && d->fuse_pairs && d->l_mrfp[i] >= 0 ;
     float* S = reinterpret_cast<float*>(slot(5));
     const bf16* seg_in[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
     const bf16* seg_res[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
@@ -471,7 +471,8 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
                                                               d->layers[pit->second].dil));
         const bool pair_p = pit != d->l_pair.end() && d->layers[pit->second].pair_plain;
         // C = 32: the same pair on the 2-sample folded view (conv_mrfp.cu with one branch): N = 64 MMAs, 512-sample tiles
-        const bool pair_m = pit != d->l_pair.end() && d->mrfp && L % 2 == 0 && d->layers[pit->second].pair_plain &&
+        const bool pair_m = pit != d->l_pair.end() && (d->mrfp & 1) && L % 2 == 0 && d->layers[pit->second].pair_plain &&
+                            (d->layers[pit->second].c_out == 32 || (d->mrfp & 2)) &&
                             mrfp_supported(d->layers[pit->second].c_out, 1, &d->layers[pit->second].k,
                                            &d->layers[pit->second].dil);
         if (!last && d->impl == 0 && d->fuse_pairs && pair_m && !(pair_f && d->pairf == 2)) {
@@ -1016,7 +1017,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, d->desc_mode * 512 + d->mrfp * 256 + d->pdl * 64 + d->par * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
+    const PlanKey key{B, T, d->impl, d->desc_mode * 1024 + d->mrfp * 256 + d->pdl * 64 + d->par * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -1201,7 +1202,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "par")) d->par = value ? 1 : 0;
-  else if (!strcmp(key, "mrfp")) d->mrfp = value ? 1 : 0;
+  else if (!strcmp(key, "mrfp")) d->mrfp = value < 0 ? 0 : (value > 3 ? 3 : value);   // bit 0: C = 32 stage, bit 1: C = 64 pairs
   else if (!strcmp(key, "pdl")) d->pdl = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "fp16")) {
     // the 16-bit storage format of weights AND activations: packed weights of the other format are useless, so every
@@ -1418,8 +1419,10 @@ int vitsdec_op_mrf_pairs(int device, int nbr, const void* const* xs, const float
                          const float* const* w2, const float* const* b2, void* y, int B, int L, int channels, const int* k,
                          const int* dilation, float slope, float out_slope, void* stream) {
   VD_CHECK(xs && w1 && b1 && w2 && b2 && y && k && dilation, "vitsdec_op_mrf_pairs: null argument");
-  VD_CHECK(nbr >= 1 && nbr <= kMpMaxBr && L % 2 == 0 && mrfp_supported(channels, nbr, k, dilation),
-           "vitsdec_op_mrf_pairs: shape not supported by the fused kernel (C = 32, even length, <= 3 branches)");
+  VD_CHECK(nbr >= 1 && nbr <= kMpMaxBr && (channels == 32 || channels == 64) && L % (64 / channels) == 0 &&
+               mrfp_supported(channels, nbr, k, dilation),
+           "vitsdec_op_mrf_pairs: shape not supported by the fused kernel (C = 32 with an even length or C = 64, <= 3 "
+           "branches, all weights resident in shared memory)");
   DeviceGuard guard(device);
   VD_CHECK(guard.ok, "cudaSetDevice failed");
   cudaDeviceProp prop;

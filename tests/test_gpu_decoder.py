@@ -594,13 +594,14 @@ def test_fused_last_pairs_launch_matches_separate_launches(B, T):
     out = {}
     with torch.no_grad():
         for fold in (0, 1):
-            for mrfp in (0, 1):
+            for mrfp in (0, 1, 3):   # 3: the C = 64 pairs through the same kernel as well (plain rows)
                 G.set_option("fold", fold)
                 G.set_option("mrfp", mrfp)
                 out[fold, mrfp] = G(z.to(DEV), g.to(DEV)).cpu()
                 out["n", fold, mrfp] = G.last_launch_count()
     assert snr_db(out[0, 0], out[0, 1]) > 45.0
     assert snr_db(out[1, 0], out[1, 1]) > 45.0
+    assert snr_db(out[1, 0], out[1, 3]) > 45.0 and out["n", 1, 3] == out["n", 1, 1]
     assert out["n", 1, 1] == out["n", 1, 0] - 3 and out["n", 0, 1] == out["n", 0, 0] - 3
     if T >= 7:
         for k in ((0, 1), (1, 1)):

@@ -233,16 +233,19 @@ def test_time_folded_fused_pair_matches_torch(case):
     (1, 512, [(3, 1)]), (2, 1000, [(7, 3)]), (3, 778, [(11, 5)]), (2, 500, [(11, 1)]), (1, 2, [(3, 1)]), (1, 6, [(7, 1)]),
     (1, 498, [(11, 3)]), (1, 502, [(11, 3)]), (1, 9000, [(3, 5)]), (16, 960, [(7, 1)]), (2, 3000, [(5, 2)]), (1, 4098, [(9, 4)]),
     (2, 1200, [(3, 5), (7, 5), (11, 5)]), (1, 256, [(3, 5), (7, 5), (11, 5)]), (3, 2, [(3, 1), (7, 3), (11, 5)]),
-    (1, 5000, [(3, 1), (5, 3)]), (2, 2048, [(11, 5), (3, 5), (7, 5)]), (40, 600, [(3, 5), (7, 5), (11, 5)])],
-    ids=lambda c: "B%d_L%d_%s" % (c[0], c[1], "+".join("k%dd%d" % kd for kd in c[2])))
+    (1, 5000, [(3, 1), (5, 3)]), (2, 2048, [(11, 5), (3, 5), (7, 5)]), (40, 600, [(3, 5), (7, 5), (11, 5)]),
+    # C = 64 on plain rows (third field): one pair, weights resident up to k = 7
+    (2, 1000, [(3, 1)], 64), (1, 777, [(7, 3)], 64), (3, 251, [(3, 5)], 64), (1, 3, [(7, 1)], 64), (16, 300, [(5, 2)], 64),
+    (2, 2001, [(3, 1), (3, 3)], 64)],
+    ids=lambda c: "B%d_L%d_%s%s" % (c[0], c[1], "+".join("k%dd%d" % kd for kd in c[2]), "_C64" if len(c) > 3 else ""))
 def test_folded_narrow_stage_kernel_matches_torch(case):
     """conv_mrfp.cu (C = 32 on the 2-sample folded view): single pairs with dilation-1 (N = 64 chunk jobs) and dilated
     (N = 32 block jobs, odd and even dilations) first convs, and the three-branch form with the average; lengths around
     the 500-sample tile edge, shorter than one folded row's halo, and small problems that take the 256-sample tiles."""
-    B, L, branches = case
+    B, L, branches = case[:3]
+    C = case[3] if len(case) > 3 else 32
     torch.manual_seed(L + 7 * len(branches))
     dev = torch.device("cuda:0")
-    C = 32
     xs, w1s, b1s, w2s, b2s = [], [], [], [], []
     for k, d in branches:
         xs.append(torch.randn(B, L, C, device=dev).bfloat16())
