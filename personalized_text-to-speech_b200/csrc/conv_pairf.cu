@@ -1,6 +1,5 @@
 // Fused ResBlock1 pair on 128-(virtual-)channel channels-as-M tiles: time-folded for the narrow stages (C = 32 / 64), and
-// on the plain view for C = 128 (r = 1: the k = 3 pairs of stage 1, whose two convs were HBM-bound launches of their own --
-// 403 + 696 MB for 2 x 46 us of tensor work; fused: one read, one write, profiles/r02_launches_*.txt):
+// on the plain view for C = 128 (r = 1: the k = 3 pairs of stage 1):
 //     y = lrelu( c2( lrelu( c1(a) + b1 ) ) + b2 + x(a) )          (modules.py:211-221, one loop iteration)
 // Same fusion as conv_pair.cu (h never leaves the SM), but both convs run on the folded view of decoder.cu
 // fold_geom: r = 128/C time samples per row, 128 virtual channels, block-Toeplitz weights, channels-as-M tiles
@@ -16,8 +15,15 @@
 //        produces samples d*(r*n+phi)+rho, so this store is where the sub-sequences are interleaved back
 //   c2 (dilation 1): D2 = sum_taps W2' . H
 //   out: D2 + b2 + x (residual re-read from global memory: the tile was loaded a moment ago, L2-hot) -> lrelu -> bf16
-// TMEM: D1 = columns [0, d*N1), D2 = columns [256, 256+WO).  MMA order c1(0) c2(0) c1(1) c2(1) ...: the output
-// epilogue of tile i overlaps c1(i+1); only the h epilogue is exposed.
+//
+// Two tiles in flight.  A tile owns one SLOT = 256 TMEM columns + one shared-memory buffer for its whole life:
+//   buffer:  x(i) --c1--> dead --h epilogue writes h(i) IN PLACE--> c2 --> dead --> x(i+2)
+//   columns: D1(i) --h epilogue--> dead --c2 writes D2(i) over it--> output epilogue --> D1(i+2)
+// so the tensor pipe runs c1(i+1) / c2(i+1) of the other slot while this slot's accumulator is in an epilogue.  (The
+// first version held one tile: D1 and D2 side by side, x and h side by side, and every h epilogue was exposed:
+// cycles/tile = c1 + h epilogue + c2, profiles/r01_trace_pairf.txt.)
+//   MMA order       c1(0) c1(1) | c2(j) c2(j+1) c1(j+2) c1(j+3) | ...       j = 0, 2, 4, ...
+//   epilogue order  h(0)  h(1)  | o(j)  o(j+1)  h(j+2)  h(j+3)  | ...       (all 16 warps work on one accumulator at a time)
 #include <algorithm>
 
 #include "common.cuh"
@@ -33,6 +39,7 @@ namespace vd {
 constexpr bool kPfTrace = VITSDEC_TRACE != 0;
 constexpr int kPfEpiWarps = 16;
 constexpr int kPfThreads = 96 + 32 * kPfEpiWarps;  // warp 0: weight producer, 1: MMA issuer, 2: x producer, 3..18: epilogue
+constexpr int kPfMaxOItems = 4;                    // output items (16 columns) per epilogue warp and tile: WO <= 256
 
 // K-chunks are always 64 virtual channels = 128-byte rows (SWIZZLE_128B): with 64-byte rows (one 32-channel phase
 // per chunk) the 32-byte K=16 slices of 8 consecutive rows fall on the same banks twice and every MMA ran at half
@@ -48,21 +55,22 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   constexpr int NCH = 2;                   // K-chunks per folded row
   constexpr int B_STAGE = 128 * ROWB;      // one K-chunk of one folded tap: [128 virtual out channels][64]
   constexpr int HS_SUB = 256 * ROWB;       // one K-chunk of the h tile
+  constexpr int SLOT_COLS = 256;           // TMEM columns of one tile slot
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int xs_sub = p.XR * ROWB;
-  uint8_t* XS = smem;                               // [d][NCH] sub-tiles of XR rows
-  uint8_t* HS = XS + p.d * NCH * xs_sub;            // [NCH] chunks of 256 rows
-  uint8_t* WS = HS + NCH * HS_SUB;                  // weight ring
+  const int buf_bytes = p.buf_bytes;                // one slot: x as [d][NCH] sub-tiles of XR rows, then h as [NCH] chunks of 256 rows
+  uint8_t* BUF = smem;
+  uint8_t* WS = BUF + 2 * buf_bytes;                // weight ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(WS + p.nw * B_STAGE);
-  uint64_t* x_full = bars;
-  uint64_t* x_empty = bars + 1;
-  uint64_t* d1_full = bars + 2;
-  uint64_t* h_ready = bars + 3;
-  uint64_t* d2_full = bars + 4;
-  uint64_t* d2_empty = bars + 5;
-  uint64_t* w_full = bars + 8;
+  uint64_t* x_full = bars;            // [2] per slot
+  uint64_t* x_empty = bars + 2;       // [2] c2 of the slot's tile has retired: the buffer may take the next x tile
+  uint64_t* d1_full = bars + 4;       // [2]
+  uint64_t* h_ready = bars + 6;       // [2]
+  uint64_t* d2_full = bars + 8;       // [2]
+  uint64_t* d2_empty = bars + 10;     // [2] the output epilogue has read D2: the slot's columns may take the next D1
+  uint64_t* w_full = bars + 12;
   uint64_t* w_empty = w_full + kPfMaxW;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + kPfMaxW);
   float* sbias = reinterpret_cast<float*>(bars + 32);                 // 256 B of barriers, then 2 x 128 floats
@@ -75,12 +83,14 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    mbar_init(x_full, 1);
-    mbar_init(x_empty, 1);
-    mbar_init(d1_full, 1);
-    mbar_init(h_ready, kPfEpiWarps);
-    mbar_init(d2_full, 1);
-    mbar_init(d2_empty, kPfEpiWarps);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+      mbar_init(&d1_full[s], 1);
+      mbar_init(&h_ready[s], kPfEpiWarps);
+      mbar_init(&d2_full[s], 1);
+      mbar_init(&d2_empty[s], kPfEpiWarps);
+    }
     for (int i = 0; i < kPfMaxW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
   }
@@ -103,22 +113,27 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------ weight producer: c1's chunks, then c2's, per tile
+    // ------------------------------------------------------------ weight producer: the chunks of every conv, in MMA order
     if (lane == 0) {
-      uint32_t itw = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        for (int conv = 0; conv < 2; ++conv) {
-          for (int ch = 0; ch < NCH; ++ch) {
-            for (int tap = 0; tap < p.nt; ++tap) {
-              if (!((p.kmask[tap] >> ch) & 1u)) continue;
-              const uint32_t sb = itw % NW;
-              mbar_wait(&w_empty[sb], ((itw / NW) & 1) ^ 1);
-              mbar_expect_tx(&w_full[sb], B_STAGE);
-              tma_load_3d(&tmW, &w_full[sb], WS + sb * B_STAGE, ch * KC, 0, conv * p.nt + tap);
-              ++itw;
-            }
+      uint32_t sw = 0, pw = 0;   // ring stage / phase
+      auto stream = [&](int conv) {
+        for (int ch = 0; ch < NCH; ++ch) {
+          for (int tap = 0; tap < p.nt; ++tap) {
+            if (!((p.kmask[tap] >> ch) & 1u)) continue;
+            mbar_wait(&w_empty[sw], pw ^ 1);
+            mbar_expect_tx(&w_full[sw], B_STAGE);
+            tma_load_3d(&tmW, &w_full[sw], WS + sw * B_STAGE, ch * KC, 0, conv * p.nt + tap);
+            if (++sw == (uint32_t)NW) { sw = 0; pw ^= 1; }
           }
         }
+      };
+      if (my_tiles > 0) stream(0);
+      if (my_tiles > 1) stream(0);
+      for (int j = 0; j < my_tiles; j += 2) {
+        stream(1);
+        if (j + 1 < my_tiles) stream(1);
+        if (j + 2 < my_tiles) stream(0);
+        if (j + 3 < my_tiles) stream(0);
       }
     }
   } else if (warp == 2) {
@@ -129,15 +144,17 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         uint32_t b, mt;
         p.div_m.divmod(tile, b, mt);
         const int hbase = (int)mt * p.WO + p.smin;
-        mbar_wait(x_empty, (i & 1) ^ 1);
-        mbar_expect_tx(x_full, p.d * NCH * xs_sub);
+        const int slot = i & 1;
+        uint8_t* XS = BUF + slot * buf_bytes;
+        mbar_wait(&x_empty[slot], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&x_full[slot], p.d * NCH * xs_sub);
         for (int rho = 0; rho < p.d; ++rho) {
           const int row0 = nlo_of(hbase, rho) + p.xmin;
           for (int ch = 0; ch < NCH; ++ch) {
             uint8_t* dst = XS + (rho * NCH + ch) * xs_sub;
             // dilated view [C][rho][phase][row][b]: a chunk is PPC phases (box {C, 1, PPC, XR, 1} -> 128-byte rows)
-            if (p.d > 1) tma_load_5d(&tmX, x_full, dst, 0, rho, ch * PPC, row0, (int)b);
-            else tma_load_5d(&tmX, x_full, dst, 0, ch, 0, row0, (int)b);
+            if (p.d > 1) tma_load_5d(&tmX, &x_full[slot], dst, 0, rho, ch * PPC, row0, (int)b);
+            else tma_load_5d(&tmX, &x_full[slot], dst, 0, ch, 0, row0, (int)b);
           }
         }
       }
@@ -147,13 +164,19 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t idesc1 = umma_idesc_f16(p.N1, F16), idesc2 = umma_idesc_f16(p.WO, F16);
     constexpr uint32_t desc_hi = umma_desc_hi(ROWB);
     const uint32_t leader = elect_one();
-    const uint32_t x_lo0 = umma_desc_lo(smem_u32(XS)), h_lo0 = umma_desc_lo(smem_u32(HS));
+    const uint32_t buf_lo0 = umma_desc_lo(smem_u32(BUF));
     const uint32_t w_lo0 = umma_desc_lo(smem_u32(WS));
-    uint32_t itw = 0;
+    uint32_t sw = 0, pw = 0;   // ring stage / phase
     auto c1 = [&](int i) {
+      const int slot = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      uint8_t* XS = BUF + slot * buf_bytes;
+      const uint32_t x_lo0 = buf_lo0 + ((uint32_t)(slot * buf_bytes) >> 4);
+      const uint32_t d_base = tmem_base + slot * SLOT_COLS;
       const bool tr = kPfTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
       if (tr) p.trace[i * 12 + 8] = clock64();
-      mbar_wait(x_full, i & 1);
+      mbar_wait(&d2_empty[slot], par ^ 1);   // the slot's columns: output epilogue of tile i - 2 done
+      mbar_wait(&x_full[slot], par);
       tc_fence_after();
       if (tr) p.trace[i * 12 + 0] = clock64();
       if (p.d > 1) {
@@ -189,64 +212,67 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int ch = 0; ch < NCH; ++ch) {
         for (int tap = 0; tap < p.nt; ++tap) {
           if (!((p.kmask[tap] >> ch) & 1u)) continue;
-          const uint32_t sb = itw % NW;
-          mbar_wait(&w_full[sb], (itw / NW) & 1);
+          mbar_wait(&w_full[sw], pw);
           tc_fence_after();
-          const uint32_t w_lo = w_lo0 + sb * (B_STAGE >> 4);
+          const uint32_t w_lo = w_lo0 + sw * (B_STAGE >> 4);
           for (int rho = 0; rho < p.d; ++rho) {
             const uint32_t x_lo = x_lo0 + ((uint32_t)((rho * NCH + ch) * xs_sub + tap * p.dstep * ROWB) >> 4);
 #pragma unroll
             for (int kk = 0; kk < KC / 16; ++kk)
-              umma_f16_lohi(tmem_base + rho * p.N1, w_lo + kk * 2, desc_hi, x_lo + kk * 2, desc_hi, idesc1,
+              umma_f16_lohi(d_base + rho * p.N1, w_lo + kk * 2, desc_hi, x_lo + kk * 2, desc_hi, idesc1,
                             kk == 0 ? started : 1u, leader);
           }
           started = 1;
-          if (leader) umma_commit(&w_empty[sb]);
-          ++itw;
+          if (leader) umma_commit(&w_empty[sw]);
+          if (++sw == (uint32_t)NW) { sw = 0; pw ^= 1; }
         }
       }
-      if (leader) {
-        umma_commit(d1_full);
-        umma_commit(x_empty);
-      }
+      if (leader) umma_commit(&d1_full[slot]);
       if (tr) p.trace[i * 12 + 1] = clock64();
     };
     auto c2 = [&](int i) {
+      const int slot = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      const uint32_t h_lo0 = buf_lo0 + ((uint32_t)(slot * buf_bytes) >> 4);
+      const uint32_t d_base = tmem_base + slot * SLOT_COLS;
       const bool tr = kPfTrace && p.trace && blockIdx.x == 0 && i < 256 && lane == 0;
       if (tr) p.trace[i * 12 + 9] = clock64();
-      mbar_wait(h_ready, i & 1);
-      mbar_wait(d2_empty, (i & 1) ^ 1);
+      mbar_wait(&h_ready[slot], par);   // (the h epilogue has also finished reading D1: D2 may overwrite it)
       tc_fence_after();
       if (tr) p.trace[i * 12 + 2] = clock64();
       uint32_t started = 0;
       for (int ch = 0; ch < NCH; ++ch) {
         for (int tap = 0; tap < p.nt; ++tap) {
           if (!((p.kmask[tap] >> ch) & 1u)) continue;
-          const uint32_t sb = itw % NW;
-          mbar_wait(&w_full[sb], (itw / NW) & 1);
+          mbar_wait(&w_full[sw], pw);
           tc_fence_after();
-          const uint32_t w_lo = w_lo0 + sb * (B_STAGE >> 4);
+          const uint32_t w_lo = w_lo0 + sw * (B_STAGE >> 4);
           const uint32_t h_lo = h_lo0 + ((uint32_t)(ch * HS_SUB + tap * ROWB) >> 4);
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk)
-            umma_f16_lohi(tmem_base + 256, w_lo + kk * 2, desc_hi, h_lo + kk * 2, desc_hi, idesc2,
-                          kk == 0 ? started : 1u, leader);
+            umma_f16_lohi(d_base, w_lo + kk * 2, desc_hi, h_lo + kk * 2, desc_hi, idesc2, kk == 0 ? started : 1u, leader);
           started = 1;
-          if (leader) umma_commit(&w_empty[sb]);
-          ++itw;
+          if (leader) umma_commit(&w_empty[sw]);
+          if (++sw == (uint32_t)NW) { sw = 0; pw ^= 1; }
         }
       }
-      if (leader) umma_commit(d2_full);
+      if (leader) {
+        umma_commit(&d2_full[slot]);
+        umma_commit(&x_empty[slot]);
+      }
       if (tr) p.trace[i * 12 + 3] = clock64();
     };
     if (my_tiles > 0) c1(0);
-    for (int i = 0; i < my_tiles; ++i) {
-      c2(i);
-      if (i + 1 < my_tiles) c1(i + 1);
+    if (my_tiles > 1) c1(1);
+    for (int j = 0; j < my_tiles; j += 2) {
+      c2(j);
+      if (j + 1 < my_tiles) c2(j + 1);
+      if (j + 2 < my_tiles) c1(j + 2);
+      if (j + 3 < my_tiles) c1(j + 3);
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue warps: h of tile i, then its output
+    // ------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                 // TMEM lane quadrant (hardware rule: warp % 4)
     const int sub = (warp - 3) >> 2;        // which of the quadrant's four warps
     uint8_t* scratch = scratch_base + (warp - 3) * 1024;
@@ -269,32 +295,17 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     ep.out = p.out;
     ep.epi_smem = 1;
 
-    for (int i = 0; i < my_tiles; ++i) {
+    // ---- h(i) = lrelu(c1 + b1), zero outside the utterance, stored over x(i) as c2's B operand (natural folded layout)
+    auto hepi = [&](int i) {
+      const int slot = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      uint8_t* HS = BUF + slot * buf_bytes;
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + slot * SLOT_COLS;
       const uint32_t tile = blockIdx.x + i * gridDim.x;
       uint32_t b, mt;
       p.div_m.divmod(tile, b, mt);
-      const int n0 = (int)mt * WO;
-      const int hbase = n0 + p.smin;
-
-      // ---- output items of this warp: residual loads of the first one go out before anything is waited for
-      auto ocoords = [&](int it, EpiItem& e) {
-        const int t = n0 + it * 16;
-        e.b = (int)b;
-        e.n = q * 32;
-        e.rows_valid = min(16, max(0, Lf - t));
-        e.row0 = (long)b * Lf + t;
-        e.base = e.row0 * 128 + q * 32;
-        e.tcol = 256 + it * 16;
-      };
-      EpiLoads ld;
-      EpiItem cur{};
-      if (sub < n_oitems) {
-        ocoords(sub, cur);
-        epiT_issue_loads<2>(ep, cur, 128, lane, ld);
-      }
-
-      // ---- h = lrelu(c1 + b1), zero outside the utterance, stored as c2's B operand in the natural folded layout
-      mbar_wait(d1_full, i & 1);
+      const int hbase = (int)mt * WO + p.smin;
+      mbar_wait(&d1_full[slot], par);   // every c1 MMA of the tile has retired: x(i) is dead, D1(i) complete
       tc_fence_after();
       const bool tr = kPfTrace && p.trace && blockIdx.x == 0 && warp == 3 && lane == 0 && i < 256;
       if (tr) p.trace[i * 12 + 4] = clock64();
@@ -306,7 +317,7 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int rel0 = d * (nlo_of(hbase, rho) + jn * 16) + rowoff - hbase;  // h-tile row of column 0; +d per column
         uint32_t a[16];
         __syncwarp();
-        tmem_ld_frag(tmem_base + ((uint32_t)(q * 32) << 16) + it * 16, a);
+        tmem_ld_frag(t_base + it * 16, a);
         // stmatrix row addresses: lane i stores row (i & 7) of the 8-channel chunk (i >> 3), for columns cg*8 + (i & 7)
         uint32_t haddr[2];
 #pragma unroll
@@ -345,39 +356,85 @@ conv_pairf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(h_ready);
+      if (lane == 0) mbar_arrive(&h_ready[slot]);
       if (tr) p.trace[i * 12 + 5] = clock64();
+    };
 
-      // ---- y = lrelu(c2 + b2 + x): same item pipeline as conv_tc.cu's channels-as-M epilogue
-      mbar_wait(d2_full, i & 1);
+    // ---- y(i) = lrelu(c2 + b2 + x): same item pipeline as conv_tc.cu's channels-as-M epilogue; the residual rows of ALL
+    // of this warp's items are requested before the accumulator is waited for (they come from L2)
+    auto oepi = [&](int i) {
+      const int slot = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + slot * SLOT_COLS;
+      const uint32_t tile = blockIdx.x + i * gridDim.x;
+      uint32_t b, mt;
+      p.div_m.divmod(tile, b, mt);
+      const int n0 = (int)mt * WO;
+      auto ocoords = [&](int it, EpiItem& e) {
+        const int t = n0 + it * 16;
+        e.b = (int)b;
+        e.n = q * 32;
+        e.rows_valid = min(16, max(0, Lf - t));
+        e.row0 = (long)b * Lf + t;
+        e.base = e.row0 * 128 + q * 32;
+        e.tcol = it * 16;
+      };
+      // residual rows of the first two items are requested before the accumulator is waited for, the others two items
+      // ahead of their use (they come from L2: the tile was loaded a moment ago)
+      EpiLoads ld[2];
+#pragma unroll
+      for (int kq = 0; kq < 2; ++kq) {
+        const int it = sub + 4 * kq;
+        if (it < n_oitems) {
+          EpiItem e{};
+          ocoords(it, e);
+          epiT_issue_loads<2>(ep, e, 128, lane, ld[kq]);
+        }
+      }
+      mbar_wait(&d2_full[slot], par);
       tc_fence_after();
+      const bool tr = kPfTrace && p.trace && blockIdx.x == 0 && warp == 3 && lane == 0 && i < 256;
       if (tr) p.trace[i * 12 + 6] = clock64();
-      for (int it = sub; it < n_oitems; it += 4) {
-        uint32_t acc[kIW];
-        float v[kIW];
-        __syncwarp();
-        tmem_ld_frag(tmem_base + ((uint32_t)(q * 32) << 16) + cur.tcol, acc);
-        tmem_ld_wait();
-        epiT_accumulate<2, F16>(ep, b2f, scratch, cur, 128, lane, res_gain, acc, ld, v);
-        const bool last = it + 4 >= n_oitems;
-        if (last) {  // accumulator fully read by this warp: hand D2 back before the stores
-          tc_fence_before();
+#pragma unroll
+      for (int kq = 0; kq < kPfMaxOItems; ++kq) {
+        const int it = sub + 4 * kq;
+        if (it < n_oitems) {
+          EpiItem cur{};
+          ocoords(it, cur);
+          uint32_t acc[kIW];
+          float v[kIW];
           __syncwarp();
-          if (lane == 0) mbar_arrive(d2_empty);
+          tmem_ld_frag(t_base + cur.tcol, acc);
+          tmem_ld_wait();
+          epiT_accumulate<2, F16>(ep, b2f, scratch, cur, 128, lane, res_gain, acc, ld[kq & 1], v);
+          if (it + 4 >= n_oitems) {  // accumulator fully read by this warp: hand the slot's columns back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d2_empty[slot]);
+          }
+          if (kq + 2 < kPfMaxOItems && it + 8 < n_oitems) {
+            EpiItem e{};
+            ocoords(it + 8, e);
+            epiT_issue_loads<2>(ep, e, 128, lane, ld[kq & 1]);
+          }
+          epiT_store<2, F16>(ep, scratch, cur, 128, lane, slope, 1.f, v);
         }
-        const EpiItem done = cur;
-        if (!last) {
-          ocoords(it + 4, cur);
-          epiT_issue_loads<2>(ep, cur, 128, lane, ld);
-        }
-        epiT_store<2, F16>(ep, scratch, done, 128, lane, slope, 1.f, v);
       }
       if (tr) p.trace[i * 12 + 7] = clock64();
       if (sub >= n_oitems) {  // a warp without output items still owes its arrival
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(d2_empty);
+        if (lane == 0) mbar_arrive(&d2_empty[slot]);
       }
+    };
+
+    if (my_tiles > 0) hepi(0);
+    if (my_tiles > 1) hepi(1);
+    for (int j = 0; j < my_tiles; j += 2) {
+      oepi(j);
+      if (j + 1 < my_tiles) oepi(j + 1);
+      if (j + 2 < my_tiles) hepi(j + 2);
+      if (j + 3 < my_tiles) hepi(j + 3);
     }
   }
 
@@ -399,7 +456,7 @@ static int pf_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) 
 static int hk_of(int k) { return (k - 1) / 2; }
 
 struct PfGeom {
-  int r, nt, smin, WO, HR, N1, XR, nw;
+  int r, nt, smin, WO, HR, N1, XR, nw, buf;
   bool ok;
 };
 
@@ -428,10 +485,11 @@ static PfGeom pf_geom(int channels, int k, int dil) {
     if (nsub * n1 > 256) continue;
     const int xr = (n1 + (g.nt - 1) * (plain ? dil : 1) + 7) / 8 * 8;
     if (xr > 256) continue;
-    const int fixed = nsub * 2 * xr * rowb + 2 * 256 * rowb;
-    const int nw = std::min(kPfMaxW, (kPfSmemBudget - fixed) / (128 * rowb));
+    // one slot buffer holds the x sub-tiles, then (in place) the h tile; two slots
+    const int buf = (std::max(nsub * 2 * xr * rowb, 2 * 256 * rowb) + 1023) / 1024 * 1024;
+    const int nw = std::min(kPfMaxW, (kPfSmemBudget - 2 * buf) / (128 * rowb));
     if (nw < 3) continue;
-    g.WO = wo; g.HR = hr; g.N1 = n1; g.XR = xr; g.nw = nw;
+    g.WO = wo; g.HR = hr; g.N1 = n1; g.XR = xr; g.nw = nw; g.buf = buf;
     g.ok = true;
     return g;
   }
@@ -440,17 +498,15 @@ static PfGeom pf_geom(int channels, int k, int dil) {
 
 int pairf_taps(int channels, int k) { return pf_geom(channels, k, 1).nt; }
 bool pairf_supported(int channels, int k, int dil) { return pf_geom(channels, k, dil).ok; }
-// Where the folded kernel beats conv_pair.cu inside the 16 x 10 s decode (ncu launch lists, profiles/): nowhere any
-// more.  It won C=32 k=11 d=1 (271 vs 300 us) until conv_pair.cu got its second MMA-issuing warp (now 224 us at d=5,
-// profiles/r01_launches_final.txt); it ties for C=32 k=7 and for C=64 k=11 against the two unfused folded convs (358 vs
-// 347 us) and loses for k=3: the exposed h epilogue and the output epilogue's shared-memory traffic (it slows the
-// overlapping c1 MMAs from 160 to 260 cycles) eat what the wider MMAs gain (profiles/r01_trace_pairf.txt).  The kernel
-// stays reachable through option pairf=2 (tests, experiments).
-// C = 128 (plain view): the k = 3 pairs of the 128-channel stage -- their convs are HBM-bound on their own; k >= 7 is
-// MMA-bound either way and keeps the two launches.
+// Where this kernel is the default inside the 16 x 10 s decode (ncu launch lists under profiles/):
+//   C = 64 (2-sample folded view): every non-final pair -- the N = 64 time-as-M tiles of conv_pair.cu run the tensor pipe
+//           at 48 cycles per 32-cycle MMA and the k = 11 pairs did not fit there at all (two launches, 5 tensor passes);
+//   C = 128 (plain view): the k = 3 pairs, whose two convs are HBM-bound launches on their own; k >= 7 is MMA-bound
+//           either way and keeps the two launches (resident-free streaming costs the pair kernel ~20 % of the MMA rate);
+//   C = 32: conv_mrfp.cu (the 4-sample fold doubles the MACs of a k = 3 conv).
+// Option pairf: 0 never, 1 this rule, 2 wherever the kernel exists (tests), 3 the C = 128 rule only (A/B).
 bool pairf_preferred(int channels, int k, int dil) {
-  (void)dil;
-  return channels == 128 && k <= 5;
+  return (channels == 128 && k <= 5) || (channels == 64 && dil == 1 && k >= 7);
 }
 
 int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
@@ -463,7 +519,7 @@ int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, c
   p.B = B; p.L = L; p.Lf = L / g.r; p.d = plain ? 1 : dil;
   p.dstep = plain ? dil : 1;
   p.xmin = plain ? -hk_of(k) * dil : g.smin;
-  p.WO = g.WO; p.HR = g.HR; p.N1 = g.N1; p.XR = g.XR; p.nt = g.nt; p.smin = g.smin; p.nw = g.nw;
+  p.WO = g.WO; p.HR = g.HR; p.N1 = g.N1; p.XR = g.XR; p.nt = g.nt; p.smin = g.smin; p.nw = g.nw; p.buf_bytes = g.buf;
   const int hk = (k - 1) / 2;
   for (int t = 0; t < g.nt; ++t) {
     uint32_t mask = 0;
@@ -482,8 +538,7 @@ int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, c
   pl->channels = channels;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const int rowb = 128;
-  pl->smem = 1024 + (size_t)p.d * 2 * g.XR * rowb + (size_t)2 * 256 * rowb + (size_t)g.nw * 128 * rowb + 256 + 1024 +
-             16384;
+  pl->smem = 1024 + (size_t)2 * g.buf + (size_t)g.nw * 128 * rowb + 256 + 1024 + 16384;
   if (p.d > 1) {
     // [C][rho][phase][row][utterance]: sample t = dil*(r*row + phase) + rho
     // a K-chunk = 64/C phases: box {C, 1, 64/C, XR, 1} lands as 128-byte rows [phase][channel]

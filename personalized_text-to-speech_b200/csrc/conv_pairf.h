@@ -22,6 +22,7 @@ struct PairFParams {
   uint32_t kmask[kPfMaxTaps];  // bit c: 64-channel K-chunk c of the folded tap is non-zero
   int rows_rho;          // rows per sub-sequence of c1's view = ceil(L / (d*r))
   int nw;                // weight ring stages
+  int buf_bytes;         // one tile slot's shared-memory buffer: the x sub-tiles, then (in place) the h tile
   int m_tiles, total_tiles;
   FastDiv div_m, div_dr;
   const float* bias1;

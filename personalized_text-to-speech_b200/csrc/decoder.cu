@@ -467,8 +467,9 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
         // pairf: 1 = where it is the faster kernel (pairf_preferred), 2 = wherever it exists (tests)
         const bool pair_f = pit != d->l_pair.end() && d->fold && d->pairf && d->layers[pit->second].fold_r &&
                             L % d->layers[pit->second].fold_r == 0 &&
-                            (d->pairf == 2 || pairf_preferred(d->layers[pit->second].c_out, d->layers[pit->second].k,
-                                                              d->layers[pit->second].dil));
+                            (d->pairf == 2 || (pairf_preferred(d->layers[pit->second].c_out, d->layers[pit->second].k,
+                                                               d->layers[pit->second].dil) &&
+                                               (d->pairf == 1 || d->layers[pit->second].c_out == 128)));
         const bool pair_p = pit != d->l_pair.end() && d->layers[pit->second].pair_plain;
         // C = 32: the same pair on the 2-sample folded view (conv_mrfp.cu with one branch): N = 64 MMAs, 512-sample tiles
         const bool pair_m = pit != d->l_pair.end() && (d->mrfp & 1) && L % 2 == 0 && d->layers[pit->second].pair_plain &&
@@ -1017,7 +1018,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, d->desc_mode * 1024 + d->mrfp * 256 + d->pdl * 64 + d->par * 32 + d->pairf * 8 + d->fold * 4 + d->debug_keep * 2 + d->fuse_pairs, ws};
+    const PlanKey key{B, T, d->impl, ((((((((d->desc_mode * 4 + d->mrfp) * 4 + d->pdl) * 2 + d->par) * 4 + d->pairf) * 2 + d->fold) * 2 + d->debug_keep) * 2) + d->fuse_pairs), ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -1200,7 +1201,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "fuse_pairs")) d->fuse_pairs = value ? 1 : 0;
   else if (!strcmp(key, "graph")) d->use_graph = value < 0 ? 0 : (value > 2 ? 2 : value);  // 2: capture on first use
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
-  else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 2 ? 2 : value);
+  else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 3 ? 3 : value);
   else if (!strcmp(key, "par")) d->par = value ? 1 : 0;
   else if (!strcmp(key, "mrfp")) d->mrfp = value < 0 ? 0 : (value > 3 ? 3 : value);   // bit 0: C = 32 stage, bit 1: C = 64 pairs
   else if (!strcmp(key, "pdl")) d->pdl = value < 0 ? 0 : (value > 2 ? 2 : value);

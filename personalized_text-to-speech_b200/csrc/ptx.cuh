@@ -63,6 +63,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// (One polling lane per warp + __syncwarp instead of 32 polling lanes was tried in round 2 -- the polls looked like a
+// quarter of the L1 data-pipe wavefronts in ncu -- and measured SLOWER: +20 % per step when the MMA-issuing warps wait
+// that way (their issue loop loses its warp-uniform control flow), +2 % for the epilogue warps alone (later wake-up).)
 
 // ---------------------------------------------------------------- programmatic dependent launch
 // launch_dependents: the next kernel of the stream (if it was launched with the programmatic-serialization attribute)

@@ -40,9 +40,13 @@ def main(path, out_json=None):
     conv = {"us": 0.0, "rd": 0.0, "wr": 0.0, "n": 0}
     for i, r in enumerate(step):
         rd, wr = r.get("dram__bytes_read.sum", 0), r.get("dram__bytes_write.sum", 0)
-        tp = r.get("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", float("nan"))
+        tp = float("nan")   # tensor-pipe active %: the first of the requested spellings this ncu build answers
+        for key in r:
+            if "pipe_tensor" in key and r[key] == r[key]:
+                tp = r[key]
+                break
         print("%3d %-38s %8.1f %6.2f%% %10.1f %10.1f %10.1f" % (i, r["name"][:38], r[T], 100 * r[T] / tot, rd, wr, tp))
-        if "conv_tc" in r["name"] or "conv_pair" in r["name"] or "conv_mrfp" in r["name"]:
+        if "conv_tc" in r["name"] or "conv_pair" in r["name"] or "conv_mrfp" in r["name"]:   # conv_pair matches conv_pairf too
             conv["us"] += r[T]; conv["rd"] += rd; conv["wr"] += wr; conv["n"] += 1
     print("# tcgen05 conv kernels: %d launches, %.1f us (%.1f%% of the step), DRAM read %.0f MB + write %.0f MB per step"
           % (conv["n"], conv["us"], 100 * conv["us"] / tot, conv["rd"], conv["wr"]))

@@ -12,7 +12,8 @@ ops = importlib.import_module("personalized_text-to-speech_b200.ops")
 lib = vitsdec._capi.lib()
 dev = torch.device("cuda:0")
 trace = torch.zeros(256 * 12, dtype=torch.int64, device=dev)
-for (C, L, k, d) in ((32, 220672, 3, 1), (32, 220672, 11, 1), (32, 220672, 7, 3), (64, 110336, 3, 1), (64, 110336, 11, 3)):
+for (C, L, k, d) in ((64, 110336, 3, 1), (64, 110336, 3, 3), (64, 110336, 7, 1), (64, 110336, 7, 3), (64, 110336, 11, 1),
+                     (64, 110336, 11, 3), (128, 55168, 3, 1), (128, 55168, 3, 3), (32, 220672, 11, 1)):
     x = torch.randn(16, L, C, device=dev).bfloat16()
     w1 = torch.randn(C, C, k, device=dev) / (C * k) ** 0.5
     w2 = torch.randn(C, C, k, device=dev) / (C * k) ** 0.5
