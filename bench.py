@@ -34,14 +34,23 @@ FLOP_PER_UTT = 262144            # cond(g)
 
 
 def load_traffic(launches_per_step):
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the tcgen05 conv launches of one 16 x 10 s step,
-    from the committed ncu pass (profiles/r01_launches_final.csv -> profiles/r01_traffic.json), per launch."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the tcgen05 conv launches of one 16 x 10 s step, per
+    launch, from the committed ncu pass (tools/final_profiles.sh -> profiles/r02_traffic.json).  An ncu pass cannot run
+    inside the timed run, so the capture carries the digest of the kernel sources it was taken on (build._digest()) and
+    its launch count: a number from other kernels or another schedule is not quoted (null)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
     if d.get("conv_launches_per_step") != launches_per_step:
         return None  # the schedule changed since the capture: do not quote a stale number
+    try:
+        import importlib
+        digest = importlib.import_module("personalized_text-to-speech_b200.build")._digest()
+    except Exception:
+        return None
+    if d.get("csrc_digest") != digest:
+        return None  # the kernels changed since the capture
     return d["conv_dram_bytes_per_step"] / launches_per_step
 
 
@@ -526,7 +535,7 @@ def main():
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor",
-                     "kernel": "conv_tc_kernel + conv_pair_kernel (tcgen05 implicit-GEMM convs: %d launches/step, "
+                     "kernel": "conv_tc / conv_pair / conv_pairf / conv_mrfp kernels (tcgen05 implicit-GEMM convs: %d launches/step, "
                                ">98%% of step time; figures are per launch, averaged over them)" % launches_conv,
                      "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                      "frac_of_sustained": achieved / sustained, "peak_source": peak_src + ", bf16 dense burst",

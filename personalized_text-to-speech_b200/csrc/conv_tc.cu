@@ -30,7 +30,7 @@ constexpr int kMaxNB = 8;      // weight-tile stages when weights are streamed
 constexpr bool kTrace = VITSDEC_TRACE != 0;
 constexpr int kEpiWarps = 16;  // four warps per TMEM lane quadrant: the epilogue is instruction-latency bound, TLP hides it
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
-constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - 8192 /*bias*/ - 16384 /*scratch*/;
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - 8192 /*bias*/ - 32768 /*scratch*/;
 
 template <int BN, int KC>
 struct TcCfg {
@@ -282,7 +282,12 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
     const int NITEMS = SWAP ? p.swap_rows / kIW : NACC * CHUNKS;   // swap_rows >= 64: at least one item per warp
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
-    uint8_t* scratch = reinterpret_cast<uint8_t*>(sbias) + 8192 + (warp - 2) * 1024;
+    // two 1 KB transposition buffers per warp: with TMA output stores an item's buffer is still being read by the TMA
+    // engine while the next item is staged in the other one
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(sbias) + 8192 + (warp - 2) * 2048;
+    constexpr bool kTmaEpi = SWAP && EPI >= 1 && EPI <= 3;
+    const bool tma_out = kTmaEpi && p.tma_epi != 0;   // launch constant: plain [B][L][n_total] output view
+    uint32_t nitem = 0;
     // launch constants live in registers for the whole loop (each read of the __grid_constant__ block is an LDC)
     const FastDiv div_n = p.div_n, div_m = p.div_m;
     const int L = p.g.L, n_total = p.g.n_total, total_tiles = p.total_tiles, tile_step = gridDim.x;
@@ -311,6 +316,7 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
         e.row0 = (long)e.b * L + t;
         e.base = (long)e.b * bstride + (((int)rho + rho_d * phi) << c_shift) + c + (long)t * rowstride;
         e.tcol = it * kIW;
+        e.t = t;
       } else {
         const int acc = it / CHUNKS, c0 = (it % CHUNKS) * kIW;
         const int t = mt * BM + acc * 128 + q * 32;
@@ -377,7 +383,17 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
               if (lane < 4 && col < cur.rows_valid) o[(long)col * r] = tanhf(x);
             }
         }
-      } else if constexpr (SWAP) epiT_accumulate<EPI, F16>(ep, bias4, scratch, cur, n_total, lane, res_gain, acc, ld, v);
+      } else if constexpr (SWAP) {
+        uint8_t* buf = scratch;
+        if constexpr (kTmaEpi) {
+          if (tma_out) {   // the store that last read this buffer (two items ago) must have drained it
+            buf = scratch + (nitem & 1) * 1024;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+        }
+        epiT_accumulate<EPI, F16>(ep, bias4, buf, cur, n_total, lane, res_gain, acc, ld, v);
+      }
       else epi_accumulate<EPI, F16>(ep, bv, scratch, cur, n_total, lane, res_gain, acc, ld, v);
       if (tr) p.trace[itt * 12 + 6] = clock64();
       if (last) {  // accumulator fully read: hand the TMEM buffer back before the stores
@@ -397,10 +413,21 @@ conv_tc_kernel(const __grid_constant__ TmapPack tm, const __grid_constant__ CUte
       }
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 9] = clock64();
       if constexpr (EPI == 4) { (void)done; }
-      else if constexpr (SWAP) epiT_store<EPI, F16>(ep, scratch, done, rowstride, lane, out_slope, mrf_scale, v);
+      else if constexpr (SWAP) {
+        if constexpr (kTmaEpi) {
+          if (tma_out) epiT_store_tma<EPI, F16>(&tm.o, scratch + (nitem & 1) * 1024, done, lane, out_slope, mrf_scale, v);
+          else epiT_store<EPI, F16>(ep, scratch, done, rowstride, lane, out_slope, mrf_scale, v);
+          ++nitem;
+        } else {
+          epiT_store<EPI, F16>(ep, scratch, done, rowstride, lane, out_slope, mrf_scale, v);
+        }
+      }
       else epi_store<EPI, F16>(ep, scratch, done, n_total, lane, out_slope, mrf_scale, v);
       if (tr) p.trace[(itt - (last ? 1 : 0)) * 12 + 7] = clock64();
       tile = ntile; it = nit;
+    }
+    if constexpr (kTmaEpi) {
+      if (tma_out && lane == 0) bulk_wait<0>();   // every output store of this warp has completed before the CTA retires
     }
   }
 
@@ -575,6 +602,8 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   // loads/stores cost far more: 11.97 vs 10.52 ms per 16 x 10 s step.
   pl->epi_smem = (desc_mode & 128) == 0;
   pl->pdl = false;
+  pl->no_tma_epi = (desc_mode & 2048) != 0;   // experiment knob: LSU output stores everywhere (the round-1 epilogue)
+  pl->out_bound = nullptr;
   const int na_stream = (desc_mode & 32) ? 3 : ((desc_mode & 64) ? 4 : 2);  // experiment knob: activation stages when streaming
   desc_mode &= 1;
   VD_CHECK(g.c_in % 32 == 0, "conv_tc: c_in must be a multiple of 32");
@@ -656,6 +685,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   p.div_dr.init(rho_d * p.r_fold);
   p.desc_mode = desc_mode;
   p.res_prefetch = 0;
+  p.tma_epi = 0;
   p.trace = nullptr;
   pl->bn = bn;
   pl->kc = kc;
@@ -682,7 +712,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
     p.nb_stages = std::min(kMaxNB, (kSmemBudget - p.na_stages * p.a_stage_bytes) / b_stage);
     p.b_region_bytes = p.nb_stages * b_stage;
   }
-  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + 8192 + 16384;
+  pl->smem = 1024 + (size_t)p.na_stages * p.a_stage_bytes + p.b_region_bytes + 512 + 8192 + 32768;
   for (int sg = 0; sg < kMaxSeg; ++sg) {
     if (sg >= g.nseg) {   // unused segments: valid placeholders without another driver call (an encode costs ~5 us)
       pl->tm.a[sg] = pl->tm.a[0];
@@ -708,8 +738,21 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   return 0;
 }
 
+// true when the launch takes one of the channels-as-M epilogues that can write its output through the TMA engine:
+// a plain [B][L][n_total] 16-bit output view, specialised epilogue (launch_swapped: EPI 1-3)
+static bool tma_epilogue_ok(const ConvTcPlan& pl, const ConvEpilogue& ep) {
+  const bool simple = ep.bias_b == nullptr && ep.mrf == nullptr && !ep.split_col && !ep.gate && ep.rowmask == nullptr;
+  const bool epi123 = (ep.mrf_mode == 0 && ep.nres <= 1) || (ep.mrf_mode == 3 && ep.nres == 3);
+  return pl.swap && pl.kc == 64 && pl.p.rho_d == 1 && simple && epi123 && ep.out != nullptr && !pl.no_tma_epi;
+}
+
 int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep) {
   VD_CHECK(ep.nres >= 0 && ep.nres <= kMaxSeg - 1, "conv_tc: at most 3 residual tensors");
+  if (tma_epilogue_ok(pl, ep) && pl.out_bound != ep.out) {
+    // output items of the channels-as-M epilogue: {32 channels, 16 rows} boxes, SWIZZLE_64B (= the scratch layout)
+    if (encode_3d(&pl.tm.o, ep.out, pl.p.g.n_total, pl.p.g.L, pl.p.g.B, 32, 16)) return 1;
+    pl.out_bound = ep.out;
+  }
   if (pl.p.rho_d > 1 || ep.split_col) return 0;  // strided / split residual rows: no L2 prefetch maps
   for (int i = 0; i < ep.nres; ++i) {
     if (pl.res_bound[i] != ep.res[i]) {
@@ -726,6 +769,8 @@ int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) 
   pl.p.ep.epi_smem = pl.epi_smem ? 1 : 0;
   if (bind_residual_tc(pl, ep)) return 1;  // no-op when the plan was built with these residuals
   pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch && pl.p.rho_d == 1 && !ep.split_col) ? 1 : 0;
+  pl.p.tma_epi = tma_epilogue_ok(pl, ep) ? 1 : 0;
+  if (!pl.p.tma_epi) { pl.tm.o = pl.tm.a[0]; pl.out_bound = nullptr; }   // valid placeholder
   if (pl.swap) {
     VD_CHECK(ep.rowmask == nullptr && !ep.gate && !ep.split_col,
              "conv_tc: row mask / gate / split epilogue need a time-as-M plan (allow_swap = false)");

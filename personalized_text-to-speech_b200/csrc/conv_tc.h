@@ -52,6 +52,7 @@ struct ConvTcParams {
   uint16_t w_slot[kMaxTaps];  // resident weights: shared-memory slot of the tap's first non-zero K-chunk
   uint32_t tap_delta16[kMaxTaps];  // (tap_off - seg_halo_lo) * row_bytes >> 4: descriptor start-address delta per tap
   int res_prefetch;           // 1: the producer prefetches the residual tiles (tmR) into L2
+  int tma_epi;                // 1: the channels-as-M epilogue writes its output items with TMA tensor stores (tm.o)
   unsigned long long* trace;  // debug: per-tile clock64 stamps of CTA 0 ([tile][8]) or null
   int desc_mode;              // debug knob for the A descriptor base-offset field (0 = none)
 };
@@ -59,12 +60,15 @@ struct ConvTcParams {
 struct TmapPack {
   CUtensorMap a[kMaxSeg];     // activation tensors, one per segment
   CUtensorMap r[kMaxSeg];     // residual tensors (L2 prefetch only)
+  CUtensorMap o;              // output tensor, {32 channels, 16 rows} boxes (channels-as-M epilogue, tma_epi)
 };
 
 struct ConvTcPlan {
   TmapPack tm;
   CUtensorMap tmW;
   const void* res_bound[kMaxSeg];
+  const void* out_bound;     // output tensor tm.o was encoded for
+  bool no_tma_epi;           // experiment knob (desc_mode bit 11)
   ConvTcParams p;
   int bn, kc;
   int grid;

@@ -34,6 +34,7 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 // One epilogue work item: rows [row0, row0+32) x columns [n, n+kIW) of utterance b; rows_valid of them exist.
 struct EpiItem {
   int b, n, rows_valid;
+  int t;           // channels-as-M: first time row of the item inside its utterance (TMA coordinates)
   long row0;       // b*L + t of lane 0's row
   long base;       // channels-as-M: element offset of (first row of the item, this warp's first channel)
   uint32_t tcol;   // TMEM column of the item inside its accumulator buffer
@@ -341,6 +342,37 @@ __device__ __forceinline__ void epiT_store(const ConvEpilogue& ep, uint8_t* scra
       *(reinterpret_cast<uint4*>(ep.out + it.base + (long)row * rowstride) + (lane & 3)) = ov;
   }
   __syncwarp();
+}
+
+// The same store through the TMA engine: the item is staged as above (the scratch layout IS the SWIZZLE_64B layout of a
+// {32 channels, 16 rows} box: 16-byte chunk index XOR address bits [7, 9)) and one bulk tensor store writes it, clipping
+// rows past the end of the utterance.  Against epiT_store this saves the LDS.128 read-back and the STG.128s, i.e. 0.7 K of
+// the ~13 K L1 data-pipe wavefronts a 128 x 256 tile of a k = 11 layer costs (the pipe the tensor core's operand fetch
+// and the TMEM loads share).  `buf` must not be touched again before bulk_wait_read<> says so.
+template <int EPI, bool F16 = false>
+__device__ __forceinline__ void epiT_store_tma(const CUtensorMap* tmO, uint8_t* buf, const EpiItem& it, int lane,
+                                               float out_slope, float mrf_scale, float (&v)[kIW]) {
+  if (EPI == 3) {
+#pragma unroll
+    for (int j = 0; j < kIW; ++j) v[j] *= mrf_scale;
+  }
+  const uint32_t sbase = smem_u32(buf);
+#pragma unroll
+  for (int cg = 0; cg < 2; ++cg) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float x0 = v[frag_idx(m, cg, 0)], x1 = v[frag_idx(m, cg, 1)];
+      pk[m] = pack_act2<F16>(fmaxf(x0, x0 * out_slope), fmaxf(x1, x1 * out_slope));  // slope in (0,1]
+    }
+    stmatrix_x4_trans(sbase + scrT_off(cg * 8 + (lane & 7), lane >> 3), pk[0], pk[1], pk[2], pk[3]);
+  }
+  fence_proxy_async();   // generic-proxy stores -> visible to the TMA engine's async-proxy reads
+  __syncwarp();
+  if (lane == 0) {
+    if (it.rows_valid > 0) tma_store_3d(tmO, buf, it.n, it.t, it.b);
+    bulk_commit();
+  }
 }
 
 }  // namespace vd

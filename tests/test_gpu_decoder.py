@@ -62,7 +62,8 @@ def test_golden_reference_outputs(golden_dir, case, impl):
     check(torch.from_numpy(gold["y"]), y.cpu())
 
 
-@pytest.mark.parametrize("B,T,use_g", [(1, 173, True), (3, 61, True), (2, 100, False), (1, 1, True), (16, 7, True)])
+@pytest.mark.parametrize("B,T,use_g", [(1, 173, True), (3, 61, True), (2, 100, False), (1, 1, True), (16, 7, True),
+                                       (3, 32, True), (3, 32, False)])
 def test_full_config_vs_fp32_restatement(B, T, use_g):
     hp = oracle.FINETUNE_SPEAKER
     G, sd = build(hp, 31)
@@ -119,6 +120,23 @@ def test_non_contiguous_slice_half_input_and_reload():
         G.load_state_dict({k: torch.from_numpy(v) for k, v in oracle.synth_state_dict(hp, 35, gain=2.0).items()})
         c = G(zfull[:, :, :25], g)
     assert float((a - c).abs().max()) > 1e-4            # new weights took effect
+
+
+def test_full_size_batch_several_utterances_vs_fp32_restatement():
+    """BASELINE config 3 size (16 x 862 frames), another seed: utterances 3, 9 and 15 of the batch -- interior and last
+    rows of the batch, every tile position of a 10 s utterance -- against the fp32 restatement on the CPU."""
+    hp = oracle.FINETUNE_SPEAKER
+    G, sd = build(hp, 52)
+    B, T = 16, 862
+    rs = np.random.RandomState(77)
+    z = torch.from_numpy(rs.standard_normal((B, hp.initial_channel, T)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((B, hp.gin_channels, 1)).astype(np.float32))
+    with torch.no_grad():
+        y = G(z.to(DEV), g.to(DEV)).cpu()
+    tsd = to_torch_state_dict(sd)
+    for u in (3, 9, 15):
+        ref = generator_forward_torch(hp, tsd, z[u:u + 1], g[u:u + 1])
+        check(ref, y[u:u + 1])
 
 
 def test_batch_and_determinism_properties_at_full_size():

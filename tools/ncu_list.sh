@@ -1,5 +1,8 @@
 #!/bin/bash
-# usage: tools/ncu_list.sh <tag> [VITSDEC_OPTS]   -> gpurun_out/launches_<tag>.csv (one warm-up + one timed decode step)
+# usage: tools/ncu_list.sh <tag> [VITSDEC_OPTS]   -> gpurun_out/launches_<tag>.csv
+# Device time, DRAM bytes and tensor-pipe activity of every launch of the decode (load-time packing kernels are skipped;
+# two decodes are captured, tools/summarize_launches.py reports the second).
 tag=$1; opts=$2
-VITSDEC_OPTS=$opts ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -c 2000 --csv \
+VITSDEC_OPTS=$opts ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
+  --clock-control none -k regex:"conv_|pack_z|cond_kernel" -c 130 --csv \
   --log-file gpurun_out/launches_$tag.csv python bench.py --steps 1 --warmup 3 --quick > gpurun_out/ncu_$tag.log 2>&1

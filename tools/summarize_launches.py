@@ -30,9 +30,11 @@ def load(path):
 
 def main(path, out_json=None):
     rows = load(path)
-    start = next(i for i, r in enumerate(rows) if "pack_z" in r["name"])
-    nxt = next((i for i, r in enumerate(rows) if "pack_z" in r["name"] and i > start), len(rows))
-    step = rows[start:nxt]
+    starts = [i for i, r in enumerate(rows) if "pack_z" in r["name"]] + [len(rows)]
+    n_step = starts[1] - starts[0]                       # launches of one decode
+    full = [i for i in range(len(starts) - 1) if starts[i + 1] - starts[i] == n_step]
+    start = starts[full[-1]]                             # the last complete decode of the capture
+    step = rows[start:start + n_step]
     T = "gpu__time_duration.sum"
     tot = sum(r[T] for r in step)
     print("# one decode step (16 x 10 s): %d launches, %.1f us summed device time (ncu, cold-cache, serialised)" % (len(step), tot))
@@ -51,7 +53,12 @@ def main(path, out_json=None):
     print("# tcgen05 conv kernels: %d launches, %.1f us (%.1f%% of the step), DRAM read %.0f MB + write %.0f MB per step"
           % (conv["n"], conv["us"], 100 * conv["us"] / tot, conv["rd"], conv["wr"]))
     if out_json:
+        import importlib
+        import os
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        digest = importlib.import_module("personalized_text-to-speech_b200.build")._digest()   # the kernels captured
         json.dump({"conv_launches_per_step": conv["n"], "conv_dram_bytes_per_step": (conv["rd"] + conv["wr"]) * 1e6,
+                   "csrc_digest": digest,
                    "conv_share_of_step": conv["us"] / tot, "source": path.split("/")[-1],
                    "workload": "16 x 10 s decode"}, open(out_json, "w"), indent=1)
 
