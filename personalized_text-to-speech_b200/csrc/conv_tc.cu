@@ -645,6 +645,15 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
     while (bm > 64 && 3L * g.B * rho_d * ((g.L + bm - 1) / bm) * (g.n_total / bn) <= num_sms) bm /= 2;
     if (raw_desc_mode & 512) bm = 256;   // experiment knob: always 256-row tiles
   }
+  // Paired tiles (conv_tc2.cu, tcgen05.mma.cta_group::2): layers with exactly 256 output channels whose taps all span
+  // every column and every K-chunk (the ResBlock convs and the fused MRF launch of a 256-channel stage), full-size tiles.
+  bool cta2 = want_swap && rho_d == 1 && kc == 64 && g.n_total == 256 && bm == 256 && !(raw_desc_mode & 4096);
+  for (int t = 0; t < g.ntaps && cta2; ++t)
+    cta2 = g.tap_nlo[t] <= 0 && g.tap_nhi[t] >= g.n_total && (g.tap_kmask[t] & ((1u << (g.c_in / kc)) - 1u)) == ((1u << (g.c_in / kc)) - 1u);
+  const int clusters2 = cta2 ? max_clusters_tc2((size_t)227 * 1024) : 0;
+  if (clusters2 <= 0) cta2 = false;
+  pl->cta2 = cta2;
+  const int rows_cta = cta2 ? 128 : bm;   // time rows of the tile staged by ONE CTA
   ConvTcParams& p = pl->p;
   p.g = g;
   p.swap_rows = bm;
@@ -656,14 +665,14 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
     int lo = g.tap_off[tap0], hi = g.tap_off[tap0];
     for (int i = tap0 + 1; i < tap1; ++i) { lo = std::min(lo, g.tap_off[i]); hi = std::max(hi, g.tap_off[i]); }
     p.seg_halo_lo[sg] = lo;
-    p.seg_nboxes[sg] = (bm + (hi - lo) + 63) / 64;
+    p.seg_nboxes[sg] = (rows_cta + (hi - lo) + 63) / 64;
     p.a_stage_bytes = std::max(p.a_stage_bytes, p.seg_nboxes[sg] * 64 * kc * 2);
     for (int i = tap0; i < tap1; ++i) p.tap_delta16[i] = (uint32_t)((g.tap_off[i] - lo) * kc * 2) >> 4;
     tap0 = tap1;
   }
   p.m_tiles = (g.L + bm - 1) / bm;
   p.n_tiles = g.n_total / bn;
-  p.total_tiles = g.B * rho_d * p.m_tiles * p.n_tiles;
+  p.total_tiles = cta2 ? g.B * p.m_tiles : g.B * rho_d * p.m_tiles * p.n_tiles;   // cta2: one tile = both channel halves
   p.div_n.init(p.n_tiles);
   p.div_m.init(p.m_tiles);
   p.div_rho.init(rho_d);
@@ -686,10 +695,12 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   p.desc_mode = desc_mode;
   p.res_prefetch = 0;
   p.tma_epi = 0;
+  p.cta2_relay = (raw_desc_mode & 8192) ? 1 : 0;
   p.trace = nullptr;
   pl->bn = bn;
   pl->kc = kc;
   pl->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  if (cta2) pl->grid = 2 * std::min(p.total_tiles, std::min(clusters2, num_sms / 2));
   const int b_stage = bn * kc * 2;
   int w_chunks = 0;
   for (int t = 0; t < g.ntaps; ++t) {
@@ -699,7 +710,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
   const int w_all = w_chunks * b_stage;  // non-zero K-chunks only
   // weights stay resident in shared memory when the whole layer fits next to >= 2 activation stages
   p.stationary = (p.n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= kSmemBudget) ? 1 : 0;
-  if (force_streaming) p.stationary = 0;
+  if (force_streaming || cta2) p.stationary = 0;
   if (p.stationary) {
     p.b_region_bytes = w_all;
     p.nb_stages = 0;
@@ -709,6 +720,7 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
     p.na_stages = 2;
     VD_CHECK(2 * p.a_stage_bytes + 2 * b_stage <= kSmemBudget, "conv_tc: dilation halo too large for shared memory");
     if (na_stream * p.a_stage_bytes + 3 * b_stage <= kSmemBudget) p.na_stages = na_stream;
+    if (cta2 && 3 * p.a_stage_bytes + 6 * b_stage <= kSmemBudget) p.na_stages = 3;   // half-size stages: a third one is cheap
     p.nb_stages = std::min(kMaxNB, (kSmemBudget - p.na_stages * p.a_stage_bytes) / b_stage);
     p.b_region_bytes = p.nb_stages * b_stage;
   }
@@ -771,6 +783,13 @@ int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream) 
   pl.p.res_prefetch = (ep.nres > 0 && !pl.no_res_prefetch && pl.p.rho_d == 1 && !ep.split_col) ? 1 : 0;
   pl.p.tma_epi = tma_epilogue_ok(pl, ep) ? 1 : 0;
   if (!pl.p.tma_epi) { pl.tm.o = pl.tm.a[0]; pl.out_bound = nullptr; }   // valid placeholder
+  if (pl.cta2) {
+    const bool epi123 = ep.bias_b == nullptr && ep.mrf == nullptr &&
+                        ((ep.mrf_mode == 0 && ep.nres <= 1) || (ep.mrf_mode == 3 && ep.nres == 3));
+    VD_CHECK(epi123 && ep.rowmask == nullptr && !ep.gate && !ep.split_col,
+             "conv_tc: this epilogue needs a plan built with desc_mode bit 12 (no paired tiles)");
+    return launch_conv_tc2(pl, stream);
+  }
   if (pl.swap) {
     VD_CHECK(ep.rowmask == nullptr && !ep.gate && !ep.split_col,
              "conv_tc: row mask / gate / split epilogue need a time-as-M plan (allow_swap = false)");

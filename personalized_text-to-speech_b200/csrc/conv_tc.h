@@ -52,6 +52,7 @@ struct ConvTcParams {
   uint16_t w_slot[kMaxTaps];  // resident weights: shared-memory slot of the tap's first non-zero K-chunk
   uint32_t tap_delta16[kMaxTaps];  // (tap_off - seg_halo_lo) * row_bytes >> 4: descriptor start-address delta per tap
   int res_prefetch;           // 1: the producer prefetches the residual tiles (tmR) into L2
+  int cta2_relay;             // conv_tc2.cu: 1 = the first full-barrier protocol (peer relay thread), experiment knob
   int tma_epi;                // 1: the channels-as-M epilogue writes its output items with TMA tensor stores (tm.o)
   unsigned long long* trace;  // debug: per-tile clock64 stamps of CTA 0 ([tile][8]) or null
   int desc_mode;              // debug knob for the A descriptor base-offset field (0 = none)
@@ -75,6 +76,7 @@ struct ConvTcPlan {
   bool no_res_prefetch;
   bool epi_smem;    // channels-as-M epilogue transposes through shared memory instead of registers (experiment knob)
   bool swap;        // channels-as-M variant (128 channels x 256 time rows per tile)
+  bool cta2;        // paired tiles: 256 channels x 256 time rows per 2-CTA cluster, tcgen05.mma.cta_group::2 (conv_tc2.cu)
   bool pdl;         // launch with the programmatic-serialization attribute (set by the decoder for launches that leave
                     // SMs idle: the kernel's prologue then overlaps the previous launch of the stream)
   size_t smem;
@@ -86,6 +88,8 @@ int plan_conv_tc(ConvTcPlan* pl, const ConvGeom& g, const __nv_bfloat16* const* 
                  int num_sms, int desc_mode, bool allow_swap = true);
 int bind_residual_tc(ConvTcPlan& pl, const ConvEpilogue& ep);
 int launch_conv_tc(ConvTcPlan& pl, const ConvEpilogue& ep, cudaStream_t stream);
+int launch_conv_tc2(const ConvTcPlan& pl, cudaStream_t stream);   // conv_tc2.cu; pl.p.ep already bound
+int max_clusters_tc2(size_t smem);                                // resident 2-CTA clusters of conv_tc2_kernel (0: none)
 int launch_conv_simt(const ConvGeom& g, const ConvEpilogue& ep, const __nv_bfloat16* const* xs,
                      const __nv_bfloat16* w, cudaStream_t stream);
 

@@ -396,7 +396,9 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     for (int i = 0; i < g.nseg; ++i) s.xs[i] = xs[i];
     s.tc.p.g = g;
     if (d->impl == 0) {
-      if (plan_conv_tc(&s.tc, g, s.xs, wts, d->num_sms, d->desc_mode, ep.mrf == nullptr)) return 1;
+      // conv_pre's per-utterance bias arrives at decode time (generic epilogue): never on paired tiles (desc_mode bit 12)
+      const int dm = d->desc_mode | (layer == d->l_pre ? 4096 : 0);
+      if (plan_conv_tc(&s.tc, g, s.xs, wts, d->num_sms, dm, ep.mrf == nullptr)) return 1;
       if (bind_residual_tc(s.tc, ep)) return 1;
     }
     pl.steps.push_back(s);

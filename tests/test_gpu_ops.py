@@ -126,6 +126,30 @@ def test_channels_as_m_and_time_as_m_forms_agree_bitwise():
         assert rel_err(a, ref_conv(x, w, b, d, res, 10.0, 0.1)) < REL_TOL
 
 
+def test_paired_tiles_agree_bitwise_with_single_cta_tiles():
+    """256-output-channel layers run as tcgen05.mma.cta_group::2 tiles across a 2-CTA cluster (conv_tc2.cu) once the
+    problem is large enough for 256-row tiles; desc_mode bit 12 keeps them on conv_tc.cu's single-CTA tiles, bit 13 selects
+    the relay variant of the operand barriers.  Same products, same accumulation order: bit-identical.  Ragged lengths put a
+    partial tile (and a peer CTA whose whole half lies past the utterance end) at the end of every utterance."""
+    torch.manual_seed(14)
+    dev = torch.device("cuda:0")
+    for (B, L, k, d, use_res) in ((5, 2048, 11, 5, True), (7, 1600 + 37, 7, 3, True), (6, 1793, 3, 1, False),
+                                  (16, 6896, 11, 1, True)):
+        x = torch.randn(B, L, 256, device=dev).bfloat16()
+        w = torch.randn(256, 256, k, device=dev) / (256 * k) ** 0.5
+        b = torch.randn(256, device=dev) * 0.1
+        res = torch.randn(B, L, 256, device=dev).bfloat16() if use_res else None
+        a = ops.conv1d_cl(x, w, b, dilation=d, res=res, out_slope=0.1, impl=0, desc_mode=0)
+        c = ops.conv1d_cl(x, w, b, dilation=d, res=res, out_slope=0.1, impl=0, desc_mode=4096)
+        r = ops.conv1d_cl(x, w, b, dilation=d, res=res, out_slope=0.1, impl=0, desc_mode=8192)
+        assert torch.equal(a, c) and torch.equal(a, r)
+        if B * L < 20000:
+            assert rel_err(a, ref_conv(x, w, b, d, res, 10.0, 0.1)) < REL_TOL
+    xh = torch.randn(5, 2048, 256, device=dev).half()      # fp16 storage instance
+    w = torch.randn(256, 256, 7, device=dev) / (256 * 7) ** 0.5
+    assert torch.equal(ops.conv1d_cl(xh, w, b, out_slope=0.1, desc_mode=0), ops.conv1d_cl(xh, w, b, out_slope=0.1, desc_mode=4096))
+
+
 @pytest.mark.parametrize("case", [(2, 1024, 32, 3, True), (3, 1500, 32, 7, False), (2, 3108, 32, 11, True),
                                   (2, 1000, 64, 3, True), (1, 518, 64, 7, False), (2, 2222, 64, 11, True),
                                   (1, 4, 32, 11, True), (1, 2, 64, 3, False), (16, 260, 32, 7, True)],
