@@ -386,33 +386,46 @@ def main():
         pipe = vitsdec.HostPipeline(G, depth=2)
         outs_host = [out_host, torch.empty_like(out_host).pin_memory()]
         # N > 1: the final waveform gather (north_star: the one collective of the path) is part of every e2e step: an
-        # all_gather_into_tensor of the rank's fp32 waveforms, started from the decode's stream as soon as the decode is
-        # enqueued (NCCL runs it on its own stream), overlapping the D2H copy and the next batch's H2D + decode.
-        gathers = []
-        fulls = [torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev) for _ in range(2)] \
-            if world > 1 else None
+        # all_gather_into_tensor of the rank's fp32 waveforms.
+        # The gather is a copy-engine push over NVLink peer memory (sharding.PeerGather: no kernel beside the decode); where
+        # the symmetric-memory rendezvous is not available it falls back to NCCL, in the slot's stream order
+        # (decode -> gather -> D2H) with the NEXT batch's decode waiting for it (HostPipeline decode_after): an NCCL kernel
+        # spinning for its peer while a decode runs holds a few SMs, and the decoder's persistent one-CTA-per-SM launches
+        # then need two rounds each (measured at N = 2: 18.4 ms per step overlapped, 9.6 serialised, 8.5 device-only).
         step_no = [0]
+        gdone = [None]
+        peer = None
+        fulls = None
+        if world > 1:
+            try:
+                peer = vitsdec.PeerGather((B, 1, frames * HOP), torch.float32, dev)
+            except Exception as e:
+                sys.stderr.write("bench: peer-memory gather unavailable (%r), using NCCL\n" % (e,))
+                fulls = [torch.empty((world * B, 1, frames * HOP), dtype=torch.float32, device=dev) for _ in range(2)]
 
         def gather_hook(y, stream):
-            w = dist.all_gather_into_tensor(fulls[step_no[0] % 2], y, async_op=True)
-            gathers.append(w)
-            if len(gathers) > 2:
-                gathers.pop(0)
+            if peer is not None:
+                peer.push(y, step_no[0], after=stream)
+            else:
+                dist.all_gather_into_tensor(fulls[step_no[0] % 2], y)   # the slot's stream waits for NCCL's
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                gdone[0] = ev
             step_no[0] += 1
 
         hook = gather_hook if world > 1 else None
         for i in range(8):   # each slot's plan reaches its graph (captured at the third use) before the timed region
-            pipe.submit(z_host, g_host, outs_host[i % 2], on_device=hook)
+            pipe.submit(z_host, g_host, outs_host[i % 2], on_device=hook, decode_after=gdone[0])
         pipe.wait_all()
-        for w in gathers:
-            w.wait()
+        if peer is not None:
+            peer.finish()
         barrier()
         e0.record()
         for i in range(args.steps):
-            pipe.submit(z_host, g_host, outs_host[i % 2], on_device=hook)
-        pipe.join()
-        for w in gathers:
-            w.wait()          # the current stream waits for the last gathers: they are inside the timed region
+            pipe.submit(z_host, g_host, outs_host[i % 2], on_device=hook, decode_after=gdone[0])
+        pipe.join()               # the current stream waits for every slot (decode, gather and D2H of the last steps)
+        if peer is not None:
+            peer.finish()         # ... and for every rank's pushes: the gathered batches are complete inside the region
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -551,6 +564,8 @@ def main():
         line["waveform_gather_ms"] = gather_ms
     if world > 1:
         line["e2e"]["includes_waveform_gather"] = True
+        line["e2e"]["gather"] = "copy-engine pushes over NVLink peer memory (sharding.PeerGather)" if peer is not None \
+            else "NCCL all_gather_into_tensor, serialised with the decodes"
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             val, dt, cores, kind, n = cpu_reference(1, frames, 2, 1)

@@ -624,3 +624,33 @@ def test_fused_last_pairs_launch_matches_separate_launches(B, T):
     if T >= 7:
         for k in ((0, 1), (1, 1)):
             check(ref, out[k])
+
+
+def test_peer_memory_gather_single_rank(tmp_path):
+    """sharding.PeerGather on a one-rank group (the driver's GPU test tier has one GPU): the symmetric buffer, the
+    copy-engine push behind a producer stream and the closing barrier.  The 2 / 4 / 8-rank path is what bench.py's e2e leg
+    runs under torchrun."""
+    import torch.distributed as dist
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    try:
+        dist.init_process_group("nccl", init_method="file://%s" % (tmp_path / "pg"), rank=0, world_size=1,
+                                device_id=torch.device(DEV))
+    except Exception as e:   # pragma: no cover - environment without NCCL
+        pytest.skip("no NCCL process group: %r" % (e,))
+    try:
+        try:
+            pg = vitsdec.PeerGather((4, 1, 2560), torch.float32, torch.device(DEV))
+        except Exception as e:
+            pytest.skip("symmetric memory unavailable: %r" % (e,))
+        s = torch.cuda.Stream(device=DEV)
+        with torch.cuda.stream(s):
+            y0 = torch.randn(4, 1, 2560, device=DEV)
+            y1 = torch.randn(4, 1, 2560, device=DEV)
+            pg.push(y0, 0, after=s)
+            pg.push(y1, 1, after=s)
+        pg.finish()
+        torch.cuda.synchronize()
+        assert torch.equal(pg.full(0), y0) and torch.equal(pg.full(1), y1)
+    finally:
+        dist.destroy_process_group()

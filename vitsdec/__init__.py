@@ -14,6 +14,7 @@ patch_reference = _pkg.patch_reference
 unpatch_reference = _pkg.unpatch_reference
 shard_range = _pkg.shard_range
 decode_sharded = _pkg.decode_sharded
+PeerGather = _pkg.PeerGather
 decode_chunked = _pkg.decode_chunked
 HostPipeline = _pkg.HostPipeline
 WavBatchWriter = _pkg.WavBatchWriter
