@@ -109,10 +109,10 @@ VITSDEC_API int vitsdec_wav_pcm16(int device, const float* wav_dev, int16_t* pcm
  *          "graph" = 0 plain kernel launches (default 1: the conv steps of a plan replay as one CUDA graph from the
  *          plan's third use on; 2: capture at the first use);
  *          "fold" = 0 keeps narrow layers on plain tiles (default 1: time-folded);
- *          "pairf" = 1 (default) runs the non-final ResBlock pairs of a 64-channel stage (2-sample folded view) and the
- *          k = 3 pairs of a 128-channel stage through conv_pairf.cu (both convs as 128-virtual-channel channels-as-M
- *          tiles, h kept in shared memory, two tiles in flight); 2: every pair that kernel supports, also the C = 32
- *          form (tests / experiments); 3: the 128-channel rule only (A/B); 0: never;
+ *          "pairf" = 1 (default) runs every non-final ResBlock pair of a 128-channel stage and the dilation-1, k >= 7
+ *          pairs of a 64-channel stage (2-sample folded view) through conv_pairf.cu (both convs as 128-virtual-channel
+ *          channels-as-M tiles, h kept in shared memory, two tiles in flight); 2: every pair that kernel supports, also
+ *          the C = 32 form (tests / experiments); 3: only the k <= 5 pairs of a 128-channel stage (A/B); 0: never;
  *          "mrfp": bit 0 (C = 32 stage): every ResBlock pair on the 2-sample folded view, and the last pair of every MRF
  *          branch + the branch sum + the average as ONE launch (conv_mrfp.cu) instead of three c1 launches and a fused-MRF
  *          launch; bit 1: the C = 64 pairs whose weights fit (k <= 7) through the same kernel on plain rows instead of

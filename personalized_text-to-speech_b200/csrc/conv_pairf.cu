@@ -498,15 +498,19 @@ static PfGeom pf_geom(int channels, int k, int dil) {
 
 int pairf_taps(int channels, int k) { return pf_geom(channels, k, 1).nt; }
 bool pairf_supported(int channels, int k, int dil) { return pf_geom(channels, k, dil).ok; }
-// Where this kernel is the default inside the 16 x 10 s decode (ncu launch lists under profiles/):
-//   C = 64 (2-sample folded view): every non-final pair -- the N = 64 time-as-M tiles of conv_pair.cu run the tensor pipe
-//           at 48 cycles per 32-cycle MMA and the k = 11 pairs did not fit there at all (two launches, 5 tensor passes);
-//   C = 128 (plain view): the k = 3 pairs, whose two convs are HBM-bound launches on their own; k >= 7 is MMA-bound
-//           either way and keeps the two launches (resident-free streaming costs the pair kernel ~20 % of the MMA rate);
+// Where this kernel is the default inside the 16 x 10 s decode (ncu launch lists under profiles/, A/B runs of bench.py):
+//   C = 128 (plain view): every non-final pair.  The k = 3 pairs were HBM-bound launches on their own (212 us fused, 231
+//           as two launches); for k = 7 / 11 the two launches are no slower in isolation, but each fused pair saves
+//           ~640 MB of DRAM traffic, and under the power cap every run of the step sits at that is what counts:
+//           -1.5 % per step with all four of them fused (9.16 -> 9.02 ms A/B, option pairf 1 vs 3-style rules);
+//   C = 64 (2-sample folded view): the dilation-1 pairs with k >= 7 -- the N = 64 time-as-M tiles of conv_pair.cu run the
+//           tensor pipe at 48 cycles per 32-cycle MMA and the k = 11 pairs did not fit there at all (two launches, 5 tensor
+//           passes); dilated pairs on a folded view and k = 3 stay on conv_pair.cu (sub-sequence MMAs of N = 80, see above);
 //   C = 32: conv_mrfp.cu (the 4-sample fold doubles the MACs of a k = 3 conv).
-// Option pairf: 0 never, 1 this rule, 2 wherever the kernel exists (tests), 3 the C = 128 rule only (A/B).
+// Option pairf: 0 never, 1 this rule, 2 wherever the kernel exists (tests), 3 C = 128 only and there k <= 5 only (the
+// first round-2 rule, A/B).
 bool pairf_preferred(int channels, int k, int dil) {
-  return (channels == 128 && k <= 5) || (channels == 64 && dil == 1 && k >= 7);
+  return channels == 128 || (channels == 64 && dil == 1 && k >= 7);
 }
 
 int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,

@@ -471,7 +471,8 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
                             L % d->layers[pit->second].fold_r == 0 &&
                             (d->pairf == 2 || (pairf_preferred(d->layers[pit->second].c_out, d->layers[pit->second].k,
                                                                d->layers[pit->second].dil) &&
-                                               (d->pairf == 1 || d->layers[pit->second].c_out == 128)));
+                                               (d->pairf != 3 || (d->layers[pit->second].c_out == 128 &&
+                                                                  d->layers[pit->second].k <= 5))));
         const bool pair_p = pit != d->l_pair.end() && d->layers[pit->second].pair_plain;
         // C = 32: the same pair on the 2-sample folded view (conv_mrfp.cu with one branch): N = 64 MMAs, 512-sample tiles
         const bool pair_m = pit != d->l_pair.end() && (d->mrfp & 1) && L % 2 == 0 && d->layers[pit->second].pair_plain &&
@@ -1020,7 +1021,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, ((((((((d->desc_mode * 4 + d->mrfp) * 4 + d->pdl) * 2 + d->par) * 4 + d->pairf) * 2 + d->fold) * 2 + d->debug_keep) * 2) + d->fuse_pairs), ws};
+    const PlanKey key{B, T, d->impl, ((((((((d->desc_mode * 4 + d->mrfp) * 4 + d->pdl) * 2 + d->par) * 8 + d->pairf) * 2 + d->fold) * 2 + d->debug_keep) * 2) + d->fuse_pairs), ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;

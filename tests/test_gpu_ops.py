@@ -231,7 +231,8 @@ def test_fused_resblock_pair_matches_torch_and_unfused(case):
                                   (2, 3000, 64, 3, 3), (2, 2002, 64, 7, 3), (1, 4444, 64, 11, 3), (2, 2000, 64, 7, 2),
                                   # C = 128 on the plain view (r = 1): dilation = rows between taps of one tile
                                   (2, 1000, 128, 3, 1), (1, 2240, 128, 3, 3), (3, 225, 128, 3, 5), (1, 7, 128, 3, 1),
-                                  (2, 900, 128, 7, 3), (1, 500, 128, 11, 1), (16, 448, 128, 3, 3)],
+                                  (2, 900, 128, 7, 3), (1, 500, 128, 11, 1), (16, 448, 128, 3, 3), (2, 1500, 128, 11, 3),
+                                  (2, 1100, 128, 7, 1), (3, 700, 128, 11, 5)],
                          ids=lambda c: "B%d_L%d_C%d_k%d_d%d" % c)
 def test_time_folded_fused_pair_matches_torch(case):
     B, L, C, k, d = case
