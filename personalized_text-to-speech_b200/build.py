@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvitsdec.so")            # the product: tcgen05 / TMA kernels only
 LIB_TEST = os.path.join(HERE, "libvitsdec_test.so")  # + the CUDA-core cross-check backend (option impl=1), tests only
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["decoder.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair.cu", "conv_pairf.cu", "conv_mrfp.cu", "pack.cu", "flow.cu"]
+SOURCES = ["decoder.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair.cu", "conv_pairf.cu", "conv_mrfp.cu", "conv_mrf128.cu", "pack.cu", "flow.cu"]
 # Test build: the same objects, except that decoder.cu is compiled with -DVITSDEC_TESTING (which is what makes impl=1
 # reachable) and conv_simt.cu, the CUDA-core restatement of the conv primitive, is linked in.  The product library has
 # no second backend (north_star: "no multi-backend dispatch").

@@ -31,6 +31,7 @@
 
 #include "../../include/vitsdec.h"
 #include "common.cuh"
+#include "conv_mrf128.h"
 #include "conv_mrfp.h"
 #include "conv_pair.h"
 #include "conv_pairf.h"
@@ -186,6 +187,8 @@ struct Step {           // one launch of the conv primitive
   bool is_mrfp = false;     // last pairs of all MRF branches + branch average in one launch (conv_mrfp.cu): layer = kMrfPair
   MrfpPlan mrfp;
   float mrfp_out_slope = 0.f;
+  bool is_mrf128 = false;   // the same fusion for a 128-channel stage (conv_mrf128.cu): layer = kMrfPair
+  Mrf128Plan mrf128;
   int branch = -1;          // MRF branch this launch belongs to (-1: trunk), for concurrent branches under the graph
   bf16* dbg_dst = nullptr;  // debug_keep: copy ep.out here after the launch
   size_t dbg_bytes = 0;
@@ -238,7 +241,7 @@ struct vitsdec_decoder {
   std::vector<int> stage_ch;
   int hop = 1;
   float* scale_scratch = nullptr;
-  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1, par = 1, mrfp = 1;
+  int impl = 0, desc_mode = 0, debug_keep = 0, profile = 0, fuse_pairs = 1, use_graph = 1, fold = 1, pairf = 1, par = 1, mrfp = 5;
   int c_z = 0;   // initial_channel rounded up to a multiple of 32: the packed latent and conv_pre's K are zero-padded
   int pdl = 1;   // option "pdl": programmatic dependent launch for launches that leave SMs idle (0 off, 2 every launch)
   int fp16 = 0;  // option "fp16": weights and stored activations are IEEE fp16 instead of bf16 (ConvEpilogue::f16)
@@ -445,7 +448,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
     const float next_slope = (i == nstage - 1) ? kPostSlope : kSlope;
     const bool fused = d->l_mrf[i] >= 0;
     // last pairs of all branches + MRF average as one launch (conv_mrfp.cu)
-    const bool use_mrfp = fused && d->impl == 0 && (d->mrfp & 1) && d->fuse_pairs && d->l_mrfp[i] >= 0 ;
+    const bool use_mrfp = fused && d->impl == 0 && (d->mrfp & (ch == 128 ? 4 : 1)) && d->fuse_pairs && d->l_mrfp[i] >= 0;
     float* S = reinterpret_cast<float*>(slot(5));
     const bf16* seg_in[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
     const bf16* seg_res[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
@@ -571,7 +574,13 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
       s.tc.p.g.B = B;
       int ks[kMpMaxBr] = {0, 0, 0}, dl[kMpMaxBr] = {1, 1, 1};
       for (int j = 0; j < nk; ++j) { ks[j] = d->layers[v.members[j]].k; dl[j] = d->layers[v.members[j]].dil; }
-      if (plan_conv_mrfp(&s.mrfp, B, L, ch, nk, ks, dl, seg_res, v.w, d->num_sms)) return 1;
+      if (ch == 128) {   // streamed weights, channels-as-M tiles (conv_mrf128.cu)
+        s.is_mrfp = false;
+        s.is_mrf128 = true;
+        if (plan_conv_mrf128(&s.mrf128, B, L, nk, ks, dl, seg_res, v.w, d->num_sms)) return 1;
+      } else if (plan_conv_mrfp(&s.mrfp, B, L, ch, nk, ks, dl, seg_res, v.w, d->num_sms)) {
+        return 1;
+      }
       pl.steps.push_back(s);
     } else if (fused) {
       // models.py:279-284: x = (rb0(x) + rb1(x) + rb2(x)) / nk -- the three last convs accumulate in one TMEM tile
@@ -596,7 +605,7 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
   // launch takes).  Long launches gain nothing (one CTA per SM, no room for the dependent's CTAs) and measured slower.
   for (Step& s : pl.steps) {
     const int tiles = s.is_mrfp ? s.mrfp.p.total_tiles : (s.is_pair ? s.pair.p.total_tiles : s.tc.p.total_tiles);
-    const bool on = d->impl == 0 && !s.is_pairf && (d->pdl == 2 || (d->pdl == 1 && tiles <= 2 * d->num_sms));   // a short launch
+    const bool on = d->impl == 0 && !s.is_pairf && !s.is_mrf128 && (d->pdl == 2 || (d->pdl == 1 && tiles <= 2 * d->num_sms));   // a short launch
     s.tc.pdl = on && !s.is_pair && !s.is_mrfp;
     s.pair.pdl = on && s.is_pair;
     s.mrfp.pdl = on && s.is_mrfp;
@@ -626,6 +635,13 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
 
 static int run_conv(vitsdec_decoder* d, Step& s, cudaStream_t st) {
   Layer& ly = d->layers[s.layer];
+  if (s.is_mrf128) {
+    const int nk = (int)ly.members.size() / 2;   // kMrfPair: c1 of every branch, then c2 of every branch
+    const float* b1[kM8MaxBr] = {nullptr, nullptr, nullptr};
+    for (int j = 0; j < nk; ++j) b1[j] = d->layers[ly.members[j]].bias;
+    const float* b2 = d->layers[d->layers[ly.members[nk]].mrf_group].bias;   // sum of the c2 biases (fused-MRF virtual layer)
+    return launch_conv_mrf128(s.mrf128, b1, b2, kSlope, s.mrfp_out_slope, s.ep.out, st, d->fp16);
+  }
   if (s.is_mrfp) {
     const int nk = (int)ly.members.size() / 2;   // kPair: {c1, c2}; kMrfPair: c1 of every branch, then c2 of every branch
     const float* b1[kMpMaxBr] = {nullptr, nullptr, nullptr};
@@ -863,7 +879,9 @@ int vitsdec_create(const vitsdec_hparams* hp, int device, vitsdec_decoder** out)
         ks[j] = d->layers[convs[convs.size() - 2]].k;
         dl[j] = d->layers[convs[convs.size() - 2]].dil;
       }
-      if (!mrfp_supported(d->stage_ch[i], hp->num_kernels, ks, dl)) continue;
+      if (!mrfp_supported(d->stage_ch[i], hp->num_kernels, ks, dl) &&
+          !mrf128_supported(d->stage_ch[i], hp->num_kernels, ks, dl))
+        continue;
       Layer v;
       v.name = "mrfp." + std::to_string(i);
       v.kind = kMrfPair;
@@ -1021,7 +1039,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, ((((((((d->desc_mode * 4 + d->mrfp) * 4 + d->pdl) * 2 + d->par) * 8 + d->pairf) * 2 + d->fold) * 2 + d->debug_keep) * 2) + d->fuse_pairs), ws};
+    const PlanKey key{B, T, d->impl, ((((((((d->desc_mode * 8 + d->mrfp) * 4 + d->pdl) * 2 + d->par) * 8 + d->pairf) * 2 + d->fold) * 2 + d->debug_keep) * 2) + d->fuse_pairs), ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -1206,7 +1224,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 3 ? 3 : value);
   else if (!strcmp(key, "par")) d->par = value ? 1 : 0;
-  else if (!strcmp(key, "mrfp")) d->mrfp = value < 0 ? 0 : (value > 3 ? 3 : value);   // bit 0: C = 32 stage, bit 1: C = 64 pairs
+  else if (!strcmp(key, "mrfp")) d->mrfp = value < 0 ? 0 : (value > 7 ? 7 : value);   // bit 0: C = 32 stage, bit 1: C = 64 pairs, bit 2: C = 128 stage tail
   else if (!strcmp(key, "pdl")) d->pdl = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "fp16")) {
     // the 16-bit storage format of weights AND activations: packed weights of the other format are useless, so every
@@ -1423,8 +1441,9 @@ int vitsdec_op_mrf_pairs(int device, int nbr, const void* const* xs, const float
                          const float* const* w2, const float* const* b2, void* y, int B, int L, int channels, const int* k,
                          const int* dilation, float slope, float out_slope, void* stream) {
   VD_CHECK(xs && w1 && b1 && w2 && b2 && y && k && dilation, "vitsdec_op_mrf_pairs: null argument");
-  VD_CHECK(nbr >= 1 && nbr <= kMpMaxBr && (channels == 32 || channels == 64) && L % (64 / channels) == 0 &&
-               mrfp_supported(channels, nbr, k, dilation),
+  const bool c128 = channels == 128 && nbr >= 1 && nbr <= kM8MaxBr && mrf128_supported(channels, nbr, k, dilation);
+  VD_CHECK(c128 || (nbr >= 1 && nbr <= kMpMaxBr && (channels == 32 || channels == 64) && L % (64 / channels) == 0 &&
+               mrfp_supported(channels, nbr, k, dilation)),
            "vitsdec_op_mrf_pairs: shape not supported by the fused kernel (C = 32 with an even length or C = 64, <= 3 "
            "branches, all weights resident in shared memory)");
   DeviceGuard guard(device);
@@ -1454,7 +1473,14 @@ int vitsdec_op_mrf_pairs(int device, int nbr, const void* const* xs, const float
   if (!rc)
     rc = launch_sum_bias(bias + kMpMaxBr * channels, nbr > 1 ? bias + (kMpMaxBr + 1) * channels : nullptr,
                          nbr > 2 ? bias + (kMpMaxBr + 2) * channels : nullptr, nullptr, b2sum, channels, st);
-  if (!rc) {
+  if (!rc && c128) {
+    static Mrf128Plan pl128;   // (a plan is ~1.5 KB of tensor maps and tables; op entries are serial test hooks)
+    const bf16* xin[kM8MaxBr] = {nullptr, nullptr, nullptr};
+    const float* bb[kM8MaxBr] = {nullptr, nullptr, nullptr};
+    for (int j = 0; j < nbr; ++j) { xin[j] = static_cast<const bf16*>(xs[j]); bb[j] = bias + j * channels; }
+    rc = plan_conv_mrf128(&pl128, B, L, nbr, k, dilation, xin, w, prop.multiProcessorCount);
+    rc = rc || launch_conv_mrf128(pl128, bb, b2sum, slope, out_slope, static_cast<bf16*>(y), st);
+  } else if (!rc) {
     MrfpPlan pl{};
     const bf16* xin[kMpMaxBr] = {nullptr, nullptr, nullptr};
     const float* bb[kMpMaxBr] = {nullptr, nullptr, nullptr};

@@ -42,8 +42,10 @@ namespace vd {
 
 typedef __nv_bfloat16 bf16;
 
-// z fp32 [B][C][T] (strided) -> fp32 [B][T][C]
-__global__ void flow_in_kernel(const float* __restrict__ z, long sb, long sc, float* __restrict__ out, int C, int T) {
+// z fp32 [B][C][T] (strided) -> fp32 [B][T][C], with the first coupling's Flip (reverse pass) and its operand
+// X0 = 16-bit copy of the first C/2 channels in the same pass (was a launch of its own)
+__global__ void flow_in_kernel(const float* __restrict__ z, long sb, long sc, float* __restrict__ out,
+                               bf16* __restrict__ x0, int C, int T, int flip, int f16) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -51,19 +53,39 @@ __global__ void flow_in_kernel(const float* __restrict__ z, long sb, long sc, fl
     tile[i][threadIdx.x] = (c < C && t < T) ? z[b * sb + c * sc + t] : 0.f;
   }
   __syncthreads();
+  const int half = C / 2;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int t = t0 + i, c = c0 + threadIdx.x;
-    if (t < T && c < C) out[((long)b * T + t) * C + c] = tile[threadIdx.x][i];
+    if (t < T && c < C) {
+      const int cc = flip ? C - 1 - c : c;
+      const float v = tile[threadIdx.x][i];
+      const long row = (long)b * T + t;
+      out[row * C + cc] = v;
+      if (cc < half) x0[row * half + cc] = pack_act_rt(v, f16);
+    }
   }
 }
 
-// fp32 [B][T][C] -> fp32 [B][C][T], optionally with the channel flip of a trailing Flip module
-__global__ void flow_out_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int T, int flip) {
+// fp32 [B][T][C] -> fp32 [B][C][T], optionally with the channel flip of a trailing Flip module; the LAST coupling's
+// x1 = (x1 - m) * mask (reverse) / m + x1 * mask (forward) is applied on the way (m: [rows][C/2], was a launch of its own)
+__global__ void flow_out_kernel(const float* __restrict__ x, const float* __restrict__ m, const float* __restrict__ mask,
+                                float* __restrict__ out, int C, int T, int flip, int reverse) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int half = C / 2;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int t = t0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (t < T && c < C) ? x[((long)b * T + t) * C + (flip ? C - 1 - c : c)] : 0.f;
+    float v = 0.f;
+    if (t < T && c < C) {
+      const int cs = flip ? C - 1 - c : c;
+      const long row = (long)b * T + t;
+      v = x[row * C + cs];
+      if (cs >= half) {
+        const float mv = m[row * half + cs - half], mk = mask[row];
+        v = reverse ? (v - mv) * mk : mv + v * mk;
+      }
+    }
+    tile[i][threadIdx.x] = v;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -72,36 +94,24 @@ __global__ void flow_out_kernel(const float* __restrict__ x, float* __restrict__
   }
 }
 
-// X <- flip(X) over channels when `flip` (modules.py:272), then X0 = bf16(X[:, :C/2]): the coupling layer's conv operand
-__global__ void flow_flip_split_kernel(float* __restrict__ x, bf16* __restrict__ x0, long rows, int C, int flip,
-                                       int f16) {
+// One coupling's x1 = (x1 - m) * mask (reverse) or m + x1 * mask (forward) -- m is already masked (modules.py:328,
+// 335-343, logs = 0) -- THEN the Flip in front of the next coupling (modules.py:272) and that coupling's operand
+// X0 = 16-bit copy of the new first half, in one pass over X (were two launches between every pair of couplings)
+__global__ void flow_couple_flip_split_kernel(float* __restrict__ x, const float* __restrict__ m,
+                                              const float* __restrict__ mask, bf16* __restrict__ x0, long rows, int C,
+                                              int reverse, int f16) {
   const int half = C / 2;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < rows * half; i += (long)gridDim.x * blockDim.x) {
     const long r = i / half;
     const int c = i % half;
     float* row = x + r * C;
-    float lo = row[c];
-    if (flip) {
-      const float hi = row[C - 1 - c];
-      row[c] = hi;
-      row[C - 1 - c] = lo;
-      lo = hi;
-    }
-    x0[i] = pack_act_rt(lo, f16);
-  }
-}
-
-// x1 = (x1 - m) * mask (reverse) or m + x1 * mask (forward); m is already masked (modules.py:328, 335-343, logs = 0)
-__global__ void flow_couple_kernel(float* __restrict__ x, const float* __restrict__ m, const float* __restrict__ mask,
-                                   long rows, int C, int reverse) {
-  const int half = C / 2;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < rows * half; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / half;
-    const int c = i % half;
-    const float mk = mask[r];
-    float* p = x + r * C + half + c;
-    const float mv = m[i];
-    *p = reverse ? (*p - mv) * mk : mv + *p * mk;
+    const float lo = row[c];                               // x0 of this coupling: unchanged
+    const float mv = m[r * half + (half - 1 - c)], mk = mask[r];
+    float hi = row[C - 1 - c];                             // x1 element that the flip brings to position c
+    hi = reverse ? (hi - mv) * mk : mv + hi * mk;
+    row[c] = hi;
+    row[C - 1 - c] = lo;
+    x0[i] = pack_act_rt(hi, f16);
   }
 }
 
@@ -109,12 +119,20 @@ __global__ void flow_fill_mask_kernel(float* mask, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) mask[i] = 1.f;
 }
 
-// cb[l][b][n] = cond.bias[l*N + n] + sum_ci w[l*N + n][ci] * g[b][ci]   (one warp per output; N = 2*hidden)
-__global__ void flow_cond_kernel(const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ g,
-                                 float* __restrict__ cb, int B, int N, int nl, int gin) {
+// cb[coupling][l][b][n] = cond.bias[l*N + n] + sum_ci w[l*N + n][ci] * g[b][ci]   (one warp per output; N = 2*hidden).
+// All couplings in ONE launch (blockIdx.z): the conditioning depends on g only, so it leaves the per-coupling chain.
+struct FlowCondPtrs {
+  const float* w[16];
+  const float* b[16];
+};
+__global__ void flow_cond_kernel(const FlowCondPtrs ptrs, const float* __restrict__ g, float* __restrict__ cb_all, int B,
+                                 int N, int nl, int gin) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   if (warp >= N * nl) return;
+  const float* __restrict__ wc = ptrs.w[blockIdx.z];
+  const float* __restrict__ bc = ptrs.b[blockIdx.z];
+  float* __restrict__ cb = cb_all + (size_t)blockIdx.z * nl * B * N;
   float s = 0.f;
   for (int i = lane; i < gin; i += 32) s = fmaf(wc[(long)warp * gin + i], g[(long)b * gin + i], s);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -230,7 +248,7 @@ static FlowWs flow_ws(const vitsdec_flow* f, int B, int T) {
   w.s = o; o += fl_align(rows * H * 4);
   w.outb = o; o += fl_align(rows * H * 2);
   w.m = o; o += fl_align(rows * (C / 2) * 4);
-  w.cb = o; o += fl_align((size_t)f->hp.n_layers * B * 2 * H * 4);
+  w.cb = o; o += fl_align((size_t)f->hp.n_flows * f->hp.n_layers * B * 2 * H * 4);
   w.mask = o; o += fl_align(rows * 4);
   w.g = o; o += fl_align((size_t)B * (f->hp.gin_channels > 0 ? f->hp.gin_channels : 1) * 4);
   w.total = o + 4096;
@@ -293,7 +311,7 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
         ConvEpilogue e{};
         e.out = ACT;
         e.gate = 1;
-        if (f->hp.gin_channels) e.bias_b = CB + (size_t)l * B * 2 * H;  // only used when g is given
+        if (f->hp.gin_channels) e.bias_b = CB + ((size_t)ci * nl + l) * B * 2 * H;  // only used when g is given
         if (push(ly.in, Hb[cur], e)) return 1;
       }
       {
@@ -529,22 +547,22 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
   else flow_fill_mask_kernel<<<grid1d(rows), 256, 0, st>>>(mask, rows);
   if (g) VD_CUDA(cudaMemcpyAsync(gws, g, (size_t)B * f->hp.gin_channels * 4, cudaMemcpyDeviceToDevice, st));
   {
+    // (+ the Flip in front of the first coupling of a reverse pass, and that coupling's 16-bit operand)
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    flow_in_kernel<<<grid, block, 0, st>>>(x, xsb, xsc, X, C, T);
+    flow_in_kernel<<<grid, block, 0, st>>>(x, xsb, xsc, X, X0, C, T, reverse ? 1 : 0, f->fp16);
   }
   VD_CUDA(cudaGetLastError());
   // reverse: Flip, coupling n-1, Flip, coupling n-2, ...   forward: coupling 0, Flip, coupling 1, Flip, ...
   auto enqueue = [&](cudaStream_t qs) -> int {
+    if (g) {   // the conditioning of every coupling: one launch, off the per-coupling chain
+      FlowCondPtrs ptrs{};
+      for (int i = 0; i < nf; ++i) { ptrs.w[i] = f->cpl[i].cond_w; ptrs.b[i] = f->cpl[i].cond_b; }
+      dim3 grid((nl * 2 * H * 32 + 255) / 256, B, nf);
+      flow_cond_kernel<<<grid, 256, 0, qs>>>(ptrs, gws, CB, B, 2 * H, nl, f->hp.gin_channels);
+      VD_CUDA(cudaGetLastError());
+    }
     for (int step = 0; step < nf; ++step) {
       const int ci = reverse ? nf - 1 - step : step;
-      FlowCoupling& c = f->cpl[ci];
-      const int flip_now = reverse ? 1 : (step > 0 ? 1 : 0);
-      flow_flip_split_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, X0, rows, C, flip_now, f->fp16);
-      if (g) {
-        dim3 grid((nl * 2 * H * 32 + 255) / 256, B);
-        flow_cond_kernel<<<grid, 256, 0, qs>>>(c.cond_w, c.cond_b, gws, CB, B, 2 * H, nl, f->hp.gin_channels);
-      }
-      VD_CUDA(cudaGetLastError());
       std::vector<FlowStep>& steps = plan->steps[ci];
       size_t si = 0;
       auto run = [&](bool with_cond) -> int {
@@ -558,8 +576,11 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
         if (run(false)) return 1;                             // res_skip (split epilogue)
       }
       if (run(false)) return 1;                               // post -> M
-      flow_couple_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, M, mask, rows, C, reverse ? 1 : 0);
-      VD_CUDA(cudaGetLastError());
+      if (step + 1 < nf) {   // couple, the Flip in front of the next coupling and its operand X0 in one pass
+        flow_couple_flip_split_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, M, mask, X0, rows, C, reverse ? 1 : 0,
+                                                                             f->fp16);
+        VD_CUDA(cudaGetLastError());
+      }                      // (the last coupling's couple happens inside the output transpose)
     }
     return 0;
   };
@@ -591,7 +612,7 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
   if (!launched && enqueue(st)) return 1;
   {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    flow_out_kernel<<<grid, block, 0, st>>>(X, out, C, T, reverse ? 0 : 1);   // forward ends with a Flip
+    flow_out_kernel<<<grid, block, 0, st>>>(X, M, mask, out, C, T, reverse ? 0 : 1, reverse ? 1 : 0);   // forward ends with a Flip
   }
   VD_CUDA(cudaGetLastError());
   return 0;

@@ -48,7 +48,7 @@ def main(path, out_json=None):
                 tp = r[key]
                 break
         print("%3d %-38s %8.1f %6.2f%% %10.1f %10.1f %10.1f" % (i, r["name"][:38], r[T], 100 * r[T] / tot, rd, wr, tp))
-        if "conv_tc" in r["name"] or "conv_pair" in r["name"] or "conv_mrfp" in r["name"]:   # conv_pair matches conv_pairf too
+        if "conv_tc" in r["name"] or "conv_pair" in r["name"] or "conv_mrf" in r["name"]:   # conv_pair matches conv_pairf too, conv_mrf both conv_mrfp and conv_mrf128
             conv["us"] += r[T]; conv["rd"] += rd; conv["wr"] += wr; conv["n"] += 1
     print("# tcgen05 conv kernels: %d launches, %.1f us (%.1f%% of the step), DRAM read %.0f MB + write %.0f MB per step"
           % (conv["n"], conv["us"], 100 * conv["us"] / tot, conv["rd"], conv["wr"]))
