@@ -162,6 +162,11 @@ struct FlowLayer {            // one WN layer
 
 struct FlowCoupling {
   FlowConv pre, post;
+  // skip sum of a WN as ONE launch (n_layers <= kMaxSeg): segment l = the skip rows of res_skip_layers[l] on acts_l, all
+  // accumulated in TMEM; the per-layer res_skip launch then only updates the residual stream (rows [0, H)) -- no fp32
+  // skip tensor read-modify-written by every layer (it made a 2 GFLOP 1 x 1 conv cost 23-28 us at 16 x 862)
+  FlowConv skip;
+  float* skip_b = nullptr;    // [n_layers][H]: the layers' skip biases; skip.bias is their sum
   std::vector<FlowLayer> layers;
   float* cond_w = nullptr;    // folded fp32 [nl*2H][gin]
   float* cond_b = nullptr;
@@ -226,6 +231,7 @@ struct vitsdec_flow {
   std::mutex mu;
   std::list<std::pair<std::tuple<int, int, const void*>, std::shared_ptr<FlowPlan>>> plans;
   cudaStream_t cstream = nullptr;   // capture-only stream
+  bool skipsum = false;             // the WN skip sum runs as one multi-segment launch (FlowCoupling::skip)
   int fp16 = 0;                     // vitsdec_flow_set_option("fp16"): conv operands / stored activations are fp16
   int pdl = 1;                      // vitsdec_flow_set_option("pdl"): 0 = no programmatic dependent launch
 };
@@ -244,7 +250,7 @@ static FlowWs flow_ws(const vitsdec_flow* f, int B, int T) {
   w.x0 = o; o += fl_align(rows * (C / 2) * 2);
   w.h0 = o; o += fl_align(rows * H * 2);
   w.h1 = o; o += fl_align(rows * H * 2);
-  w.act = o; o += fl_align(rows * H * 2);
+  w.act = o; o += (size_t)(f->skipsum ? f->hp.n_layers : 1) * fl_align(rows * H * 2);
   w.s = o; o += fl_align(rows * H * 4);
   w.outb = o; o += fl_align(rows * H * 2);
   w.m = o; o += fl_align(rows * (C / 2) * 4);
@@ -279,7 +285,7 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
   pl.steps.resize(f->cpl.size());
   for (size_t ci = 0; ci < f->cpl.size(); ++ci) {
     FlowCoupling& c = f->cpl[ci];
-    auto push = [&](const FlowConv& cv, const bf16* x, ConvEpilogue e) -> int {
+    auto push_n = [&](const FlowConv& cv, const bf16* const* xin, ConvEpilogue e) -> int {
       FlowStep s{};
       ConvGeom g = cv.geom;
       g.B = B; g.L = T;
@@ -289,7 +295,8 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
       e.f16 = f->fp16;
       if (e.out_slope == 0.f) e.out_slope = 1.f;
       if (e.mrf_scale == 0.f) e.mrf_scale = 1.f;
-      const bf16* xs[kMaxSeg] = {x, nullptr, nullptr, nullptr};
+      const bf16* xs[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
+      for (int i = 0; i < g.nseg; ++i) xs[i] = xin[i];
       if (plan_conv_tc(&s.tc, g, xs, cv.w, f->num_sms, 0, /*allow_swap=*/false)) return 1;
       s.ep = e;
       // programmatic dependent launch (see decoder.cu): the flow's launches are all short; the small kernels between
@@ -299,6 +306,9 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
       pl.steps[ci].push_back(s);
       return 0;
     };
+    auto push = [&](const FlowConv& cv, const bf16* x, ConvEpilogue e) -> int { return push_n(cv, &x, e); };
+    const size_t act_stride = fl_align((size_t)B * T * H * 2) / 2;   // elements between the layers' gate outputs (skipsum)
+    const bf16* acts[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
     int cur = 0;
     {  // pre
       ConvEpilogue e{};
@@ -307,14 +317,25 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
     }
     for (int l = 0; l < nl; ++l) {
       FlowLayer& ly = c.layers[l];
+      bf16* act_l = f->skipsum ? ACT + (size_t)l * act_stride : ACT;
       {
         ConvEpilogue e{};
-        e.out = ACT;
+        e.out = act_l;
         e.gate = 1;
         if (f->hp.gin_channels) e.bias_b = CB + ((size_t)ci * nl + l) * B * 2 * H;  // only used when g is given
         if (push(ly.in, Hb[cur], e)) return 1;
       }
-      {
+      if (f->skipsum) {
+        acts[l] = act_l;
+        if (ly.has_res) {           // residual stream only: x = (x + res_acts) * mask, modules.py:170-171
+          ConvEpilogue e{};
+          e.res[0] = Hb[cur];
+          e.nres = 1;
+          e.out = Hb[cur ^ 1];
+          if (push(ly.rs, act_l, e)) return 1;
+          cur ^= 1;
+        }
+      } else {
         ConvEpilogue e{};
         e.mrf = S;
         if (ly.has_res) {           // residual half -> next H (bf16), skip half -> S (fp32), one launch
@@ -331,6 +352,11 @@ static int flow_build_plan(vitsdec_flow* f, FlowPlan& pl, int B, int T, uint8_t*
         if (push(ly.rs, ACT, e)) return 1;
         if (ly.has_res) cur ^= 1;
       }
+    }
+    if (f->skipsum) {   // output = sum_l skip_l(acts_l), * mask (modules.py:173-176): one launch, the sum lives in TMEM
+      ConvEpilogue e{};
+      e.out = OUTB;
+      if (push_n(c.skip, acts, e)) return 1;
     }
     {  // post: fp32 store of m
       ConvEpilogue e{};
@@ -368,9 +394,18 @@ int vitsdec_flow_create(const vitsdec_flow_hparams* hp, int device, vitsdec_flow
   f->device = device;
   f->num_sms = prop.multiProcessorCount;
   const int C2 = hp->channels / 2, H = hp->hidden_channels, nl = hp->n_layers;
+  f->skipsum = nl <= kMaxSeg;
   f->cpl.resize(hp->n_flows);
   for (int i = 0; i < hp->n_flows; ++i) {
     FlowCoupling& c = f->cpl[i];
+    if (f->skipsum) {   // nl segments of one tap each, all at row offset 0
+      if (flow_conv_alloc(c.skip, H, H, nl, 1)) return 1;
+      ConvGeom& sg = c.skip.geom;
+      for (int l = 0; l < nl; ++l) { sg.tap_off[l] = 0; sg.seg_tap_end[l] = l + 1; }
+      sg.nseg = nl;
+      VD_CUDA(cudaMalloc(&c.skip_b, (size_t)nl * H * sizeof(float)));
+      VD_CUDA(cudaMemset(c.skip_b, 0, (size_t)nl * H * sizeof(float)));
+    }
     const std::string p = "flows." + std::to_string(2 * i) + ".";   // odd entries are Flip modules (models.py:199-201)
     if (flow_conv_alloc(c.pre, C2, H, 1, 1)) return 1;
     f->names.push_back(p + "pre");
@@ -381,7 +416,7 @@ int vitsdec_flow_create(const vitsdec_flow_hparams* hp, int device, vitsdec_flow
       VD_CHECK((hp->kernel_size - 1) / 2 * dil < 4096, "flow: dilation too large");
       if (flow_conv_alloc(ly.in, H, 2 * H, hp->kernel_size, dil)) return 1;
       ly.has_res = l < nl - 1;
-      if (flow_conv_alloc(ly.rs, H, ly.has_res ? 2 * H : H, 1, 1)) return 1;
+      if (flow_conv_alloc(ly.rs, H, (ly.has_res && !f->skipsum) ? 2 * H : H, 1, 1)) return 1;
       dil *= hp->dilation_rate;
     }
     for (int l = 0; l < nl; ++l) f->names.push_back(p + "enc.in_layers." + std::to_string(l));
@@ -405,7 +440,7 @@ void vitsdec_flow_destroy(vitsdec_flow* f) {
   cudaDeviceSynchronize();
   auto drop = [](FlowConv& c) { cudaFree(c.w); cudaFree(c.bias); };
   for (FlowCoupling& c : f->cpl) {
-    drop(c.pre); drop(c.post);
+    drop(c.pre); drop(c.post); drop(c.skip); cudaFree(c.skip_b);
     for (FlowLayer& l : c.layers) { drop(l.in); drop(l.rs); }
     cudaFree(c.cond_w); cudaFree(c.cond_b);
   }
@@ -458,9 +493,20 @@ int vitsdec_flow_load_layer(vitsdec_flow* f, const char* name, const float* w, c
     const int rows = ly.has_res ? 2 * H : H;
     VD_CHECK(rows <= 8192, "flow: too many channels");
     if (launch_wn_scale(w, wg, f->scale_scratch, rows, H, st)) return 1;
-    // rows [0, H) update the residual stream, rows [H, 2H) feed the skip sum (modules.py:170-173): one conv, the
-    // epilogue splits at column H
-    if (load_conv(ly.rs, w, f->scale_scratch, bias)) return 1;
+    // rows [0, H) update the residual stream, rows [H, 2H) feed the skip sum (modules.py:170-173)
+    if (f->skipsum) {
+      if (ly.has_res && load_conv(ly.rs, w, f->scale_scratch, bias)) return 1;   // ly.rs has H output rows here
+      const int srow = ly.has_res ? H : 0;   // the last layer's H rows are all skip
+      if (launch_pack_conv(w + (size_t)srow * H, f->scale_scratch + srow, c.skip.w + (size_t)li * H * H, H, H, 1, st, 0,
+                           f->fp16))
+        return 1;
+      if (launch_replicate_bias(bias + srow, c.skip_b + (size_t)li * H, H, 1, st)) return 1;
+      const float* sb[kMaxSeg] = {nullptr, nullptr, nullptr, nullptr};
+      for (int l = 0; l < nl; ++l) sb[l] = c.skip_b + (size_t)l * H;   // unloaded layers still hold zeros
+      if (launch_sum_bias(sb[0], sb[1], sb[2], sb[3], c.skip.bias, H, st)) return 1;
+    } else if (load_conv(ly.rs, w, f->scale_scratch, bias)) {   // one conv, the epilogue splits at column H
+      return 1;
+    }
   } else if (rest == "enc.cond_layer" && gin > 0) {
     const int rows = nl * 2 * H;
     VD_CHECK(rows <= 8192, "flow: too many conditioning channels");
@@ -573,8 +619,10 @@ int vitsdec_flow_apply(vitsdec_flow* f, const float* x, int64_t xsb, int64_t xsc
       if (run(false)) return 1;                               // pre
       for (int l = 0; l < nl; ++l) {
         if (run(g != nullptr)) return 1;                      // in_layer (+ cond) with the gate in its epilogue
-        if (run(false)) return 1;                             // res_skip (split epilogue)
+        if (!f->skipsum || f->cpl[ci].layers[l].has_res)
+          if (run(false)) return 1;                           // res_skip: residual rows (skipsum) or split epilogue
       }
+      if (f->skipsum && run(false)) return 1;                 // the WN's skip sum: one multi-segment launch
       if (run(false)) return 1;                               // post -> M
       if (step + 1 < nf) {   // couple, the Flip in front of the next coupling and its operand X0 in one pass
         flow_couple_flip_split_kernel<<<grid1d(rows * (C / 2)), 256, 0, qs>>>(X, M, mask, X0, rows, C, reverse ? 1 : 0,
