@@ -505,13 +505,13 @@ bool pairf_supported(int channels, int k, int dil) { return pf_geom(channels, k,
 //           -1.5 % per step with all four of them fused (9.16 -> 9.02 ms A/B, option pairf 1 vs 3-style rules);
 //   C = 64 (2-sample folded view): the dilation-1 pairs with k >= 7 -- the N = 64 time-as-M tiles of conv_pair.cu run the
 //           tensor pipe at 48 cycles per 32-cycle MMA and the k = 11 pairs did not fit there at all (two launches, 5 tensor
-//           passes) -- so the dilated k = 11 pair runs here too (as fast as its two launches, 640 MB less DRAM traffic);
-//           the other dilated pairs and k = 3 stay on conv_pair.cu (sub-sequence MMAs of N = 80, see above);
+//           passes); dilated pairs on a folded view and k = 3 stay where they were (sub-sequence MMAs of N = 80, see
+//           above: the dilated k = 11 pair measured 368 us here against 301 us as two folded launches);
 //   C = 32: conv_mrfp.cu (the 4-sample fold doubles the MACs of a k = 3 conv).
 // Option pairf: 0 never, 1 this rule, 2 wherever the kernel exists (tests), 3 C = 128 only and there k <= 5 only (the
 // first round-2 rule, A/B).
 bool pairf_preferred(int channels, int k, int dil) {
-  return channels == 128 || (channels == 64 && ((dil == 1 && k >= 7) || k >= 11));
+  return channels == 128 || (channels == 64 && dil == 1 && k >= 7);
 }
 
 int plan_conv_pairf(PairFPlan* pl, int B, int L, int channels, int k, int dil, const __nv_bfloat16* x,
