@@ -74,6 +74,25 @@ def test_full_config_vs_fp32_restatement(B, T, lens, reverse):
     assert torch.equal(y * (1 - m) != 0, ref * (1 - m) != 0)
 
 
+@pytest.mark.parametrize("n_layers", [1, 3, 5, 6])
+def test_layer_counts_around_the_skip_sum_segment_limit(n_layers):
+    """Up to 4 WN layers the skip sum of a coupling is ONE 4-segment launch accumulated in TMEM (flow.cu
+    FlowCoupling::skip); deeper WNs keep the per-layer split epilogue with the fp32 skip tensor.  Both against the fp32
+    restatement, both directions, ragged mask, dilation_rate 2."""
+    from oracle.flow_torch import FlowHParams
+    hp = FlowHParams(64, 64, 3, 2, n_layers, 2, 32)
+    F, sd = build(hp, 90 + n_layers)
+    B, T = 3, 200
+    rs = np.random.RandomState(n_layers)
+    x = torch.from_numpy(rs.standard_normal((B, hp.channels, T)).astype(np.float32))
+    g = torch.from_numpy(rs.standard_normal((B, hp.gin_channels, 1)).astype(np.float32))
+    m = mask_of((200, 57, 133), T)
+    for reverse in (False, True):
+        with torch.no_grad():
+            y = F(x.to(DEV), m.to(DEV), g=g.to(DEV), reverse=reverse).cpu()
+        check(flow_forward_torch(hp, sd, x, m, g, reverse=reverse), y)
+
+
 def test_reverse_inverts_forward_on_device():
     hp = FLOW_FINETUNE_SPEAKER
     F, _ = build(hp, 70)
