@@ -101,6 +101,19 @@ def test_chunk_plan_covers_once_and_clips_halos():
         assert covered == list(range(T))
 
 
+def test_uniform_chunk_plan_covers_once_with_equal_windows():
+    """decode_chunked's plan: windows of ONE length (one batched decode), every frame kept exactly once, at least `halo`
+    frames of context on every side that is not the utterance boundary."""
+    for (T, c, h) in ((5168, 512, 13), (100, 10, 12), (35, 10, 12), (1000, 8, 13), (539, 512, 13), (2 * 512 + 26, 512, 13)):
+        plan = chunked.chunk_plan_uniform(T, c, h)
+        kept = []
+        for lo, hi, klo, khi in plan:
+            assert 0 <= lo and hi <= T and hi - lo == c + 2 * h
+            assert (klo >= h or lo == 0) and ((hi - lo) - khi >= h or hi == T)
+            kept += list(range(lo + klo, lo + khi))
+        assert kept == list(range(T))
+
+
 def test_decode_chunked_with_oracle_decode_fn():
     hp = oracle.TINY
     sd = oracle.synth_state_dict(hp, 5, gain=2.0)
