@@ -117,7 +117,11 @@ class ResidualCouplingBlock(nn.Module):
         if ws is None or ws.numel() < nbytes or ws.device != device:
             if ws is None and len(self._ws) >= 4:
                 self._ws.pop(next(iter(self._ws)))
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            # geometric growth, as in Generator._workspace: a new pointer invalidates the stream's cached plans
+            grown = 0 if ws is None or ws.device != device else ws.numel() + ws.numel() // 2
+            ws = None
+            self._ws.pop(key, None)
+            ws = torch.empty(max(nbytes, grown), dtype=torch.uint8, device=device)
             self._ws[key] = ws
         return ws
 

@@ -238,7 +238,12 @@ class Generator(nn.Module):
         if ws is None or ws.numel() < nbytes or ws.device != device:
             if ws is None and len(self._ws) >= 4:
                 self._ws.pop(next(iter(self._ws)))
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            # grow geometrically: a new workspace pointer invalidates every cached plan of this stream (the C side keys
+            # plans on it), so a serving loop whose requests creep upwards must not re-allocate for every new maximum
+            grown = 0 if ws is None or ws.device != device else ws.numel() + ws.numel() // 2
+            ws = None                       # release the old block before asking for the larger one
+            self._ws.pop(key, None)
+            ws = torch.empty(max(nbytes, grown), dtype=torch.uint8, device=device)
             self._ws[key] = ws
         return ws
 
