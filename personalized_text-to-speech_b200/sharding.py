@@ -64,8 +64,8 @@ class PeerGather:
     every rank of the box) and copies its own waveforms into row ``rank`` of EVERY rank's buffer with plain device-to-device
     copies on a side stream: 14 MB per peer at NVLink speed (0.04 ms), issued by the copy engines while the SMs decode the
     next batch.  ``finish()`` is the only synchronisation: a barrier behind the last push, after which ``full(slot)`` holds
-    the whole batch on every rank.  Needs CUDA peer access between the ranks' GPUs (one NVSwitch box); ``available()``
-    says whether the rendezvous worked, callers fall back to ``decode_sharded``'s NCCL gather otherwise.
+    the whole batch on every rank.  Needs CUDA peer access between the ranks' GPUs (one NVSwitch box): the
+    constructor raises where the rendezvous is not possible, callers then fall back to ``decode_sharded``'s NCCL gather.
     """
 
     def __init__(self, shape_per_rank, dtype, device, group=None, slots=2):
@@ -77,14 +77,6 @@ class PeerGather:
         self.peers = [self.hdl.get_buffer(r, self.buf.shape, dtype) for r in range(self.world)]
         self.stream = torch.cuda.Stream(device=device)
         self.slots = slots
-
-    @staticmethod
-    def available(device):
-        try:
-            import torch.distributed._symmetric_memory  # noqa: F401
-            return dist.is_initialized() and torch.device(device).type == "cuda"
-        except Exception:
-            return False
 
     def push(self, y, slot, after=None):
         """Copy this rank's waveforms ``y`` into row ``rank`` of slot ``slot`` on every rank, behind the work already
