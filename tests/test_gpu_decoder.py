@@ -360,6 +360,29 @@ def test_host_pipeline_matches_direct_forward():
             assert torch.equal(o, G(z.to(DEV), g.to(DEV)).cpu())
     with pytest.raises(RuntimeError, match="pinned"):
         pipe.submit(torch.randn(B, hp.initial_channel, T), gs[0], outs[0])
+    # on_device hook (the decoded batch still on the GPU, in the slot's stream) and decode_after (the next decode waits
+    # for an event recorded behind a side-stream consumer -- how bench.py orders an NCCL gather between decodes)
+    side = torch.cuda.Stream(device=DEV)
+    seen, last = [], [None]
+
+    def hook(y, stream):
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            seen.append(y.sum())
+            y.record_stream(side)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        last[0] = ev
+
+    for z, g, o in zip(zs, gs, outs):
+        o.zero_()
+        pipe.submit(z, g, o, on_device=hook, decode_after=last[0])
+    pipe.wait_all()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for z, g, o, sm in zip(zs, gs, outs, seen):
+            ref = G(z.to(DEV), g.to(DEV))
+            assert torch.equal(o, ref.cpu()) and torch.equal(sm, ref.sum())
 
 
 # ---- option "fp16": fp16 instead of bf16 operands / stored activations (north_star: "bf16/fp16 operands, fp32
