@@ -117,7 +117,9 @@ VITSDEC_API int vitsdec_wav_pcm16(int device, const float* wav_dev, int16_t* pcm
  *          branch + the branch sum + the average as ONE launch (conv_mrfp.cu) instead of three c1 launches and a fused-MRF
  *          launch; bit 1: the C = 64 pairs whose weights fit (k <= 7) through the same kernel on plain rows instead of
  *          conv_pair.cu (measured neutral: 9.05 vs 9.07 ms per step, so off by default); bit 2: the same last-pairs + MRF
- *          fusion for a 128-channel stage (conv_mrf128.cu, streamed weights).  Default 5; 0 = the round-1 schedule;
+ *          fusion for a 128-channel stage (conv_mrf128.cu, streamed weights); bit 3: also the k < 9 pairs of the C = 32
+ *          stage through conv_mrfp.cu (by default they run on conv_pair.cu, which is faster for short kernels).  Default 5;
+ *          0 = the round-1 schedule;
  *          "par" = 0 serial MRF branches (default 1: the branches of a stage run concurrently under the graph);
  *          "pdl" = 0 no programmatic dependent launch (default 1: launches whose grid leaves SMs idle let the next launch
  *          of the stream start its prologue early; 2: every launch);

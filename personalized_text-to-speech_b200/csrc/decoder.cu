@@ -478,8 +478,11 @@ static int build_plan(vitsdec_decoder* d, Plan& pl, int B, int T, uint8_t* ws) {
                                                                   d->layers[pit->second].k <= 5))));
         const bool pair_p = pit != d->l_pair.end() && d->layers[pit->second].pair_plain;
         // C = 32: the same pair on the 2-sample folded view (conv_mrfp.cu with one branch): N = 64 MMAs, 512-sample tiles
+        // (for k < 9 conv_pair.cu's 256-sample tiles are the faster pair kernel: 124 / 178 us against 170 / 189 us for
+        // k = 3 / 7 in the 16 x 10 s decode; mrfp bit 3 runs every C = 32 pair here, the first round-2 rule)
         const bool pair_m = pit != d->l_pair.end() && (d->mrfp & 1) && L % 2 == 0 && d->layers[pit->second].pair_plain &&
-                            (d->layers[pit->second].c_out == 32 || (d->mrfp & 2)) &&
+                            ((d->layers[pit->second].c_out == 32 && (d->layers[pit->second].k >= 9 || (d->mrfp & 8))) ||
+                             (d->mrfp & 2)) &&
                             mrfp_supported(d->layers[pit->second].c_out, 1, &d->layers[pit->second].k,
                                            &d->layers[pit->second].dil);
         if (!last && d->impl == 0 && d->fuse_pairs && pair_m && !(pair_f && d->pairf == 2)) {
@@ -1039,7 +1042,7 @@ int vitsdec_decode(vitsdec_decoder* d, const float* z, int64_t zsb, int64_t zsc,
   {
     std::lock_guard<std::mutex> lock(d->mu);
     VD_CHECK(ws_bytes >= ws_layout(d, B, T).total, "vitsdec_decode: workspace too small");
-    const PlanKey key{B, T, d->impl, ((((((((d->desc_mode * 8 + d->mrfp) * 4 + d->pdl) * 2 + d->par) * 8 + d->pairf) * 2 + d->fold) * 2 + d->debug_keep) * 2) + d->fuse_pairs), ws};
+    const PlanKey key{B, T, d->impl, ((((((((d->desc_mode * 16 + d->mrfp) * 4 + d->pdl) * 2 + d->par) * 8 + d->pairf) * 2 + d->fold) * 2 + d->debug_keep) * 2) + d->fuse_pairs), ws};
     for (auto it = d->plans.begin(); it != d->plans.end(); ++it) {
       if (!(it->first < key) && !(key < it->first)) {
         plan = it->second;
@@ -1224,7 +1227,7 @@ int vitsdec_set_option(vitsdec_decoder* d, const char* key, int value) {
   else if (!strcmp(key, "fold")) d->fold = value ? 1 : 0;
   else if (!strcmp(key, "pairf")) d->pairf = value < 0 ? 0 : (value > 3 ? 3 : value);
   else if (!strcmp(key, "par")) d->par = value ? 1 : 0;
-  else if (!strcmp(key, "mrfp")) d->mrfp = value < 0 ? 0 : (value > 7 ? 7 : value);   // bit 0: C = 32 stage, bit 1: C = 64 pairs, bit 2: C = 128 stage tail
+  else if (!strcmp(key, "mrfp")) d->mrfp = value < 0 ? 0 : (value > 15 ? 15 : value);   // bit 0: C = 32 stage, bit 1: C = 64 pairs, bit 2: C = 128 stage tail, bit 3: every C = 32 pair
   else if (!strcmp(key, "pdl")) d->pdl = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "fp16")) {
     // the 16-bit storage format of weights AND activations: packed weights of the other format are useless, so every
