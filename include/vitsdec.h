@@ -102,7 +102,8 @@ VITSDEC_API int vitsdec_wav_pcm16(int device, const float* wav_dev, int16_t* pcm
 /* Options: "impl" = 0 tcgen05 tensor-core kernels (the only backend of libvitsdec.so); 1 = CUDA-core cross-check kernels,
  *          accepted by the test build libvitsdec_test.so only (build.py: -DVITSDEC_TESTING);
  *          "desc_mode" = debug / experiment knobs (0 is the product setting): bit 0 UMMA descriptor base
- *          offset, bit 11 (2048) LSU instead of TMA output stores in the channels-as-M epilogues, bit 12 (4096) no paired
+ *          offset, bit 2 (4) TMA L2 prefetch of residual tiles (on in round 1, measured 1 % slower since), bit 11 (2048) LSU
+ *          instead of TMA output stores in the channels-as-M epilogues, bit 12 (4096) no paired
  *          (tcgen05.mma.cta_group::2) tiles for 256-channel layers, bit 13 (8192) relay variant of their operand barriers;
  *          "debug_keep" = 1 keep named intermediates for vitsdec_debug_read; "profile" = 1 see below;
  *          "fuse_pairs" = 0 run every ResBlock conv as its own launch (default 1: fused pairs where they fit);
